@@ -1,0 +1,480 @@
+// core.h -- per-element arithmetic and index logic of the two-electron path.
+//
+// Everything here is __host__ __device__ so that the CUDA kernels (slater.cu,
+// rk.cu, block.cu) and the CPU-side logic checker under tests/hostcheck/ run
+// the very same statements.  The checker is test infrastructure: the product
+// never executes these functions on the host.
+//
+// Conventions: spline b-index i in 1..n_b (full index i+1),
+// cells v in 1..C, ordered band pairs p=(a,c) with |a-c| < ks numbered
+// a-major / c ascending, multipole k in 0..max_k (K1 = max_k+1).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BS2E_HD __host__ __device__ __forceinline__
+#else
+#define BS2E_HD inline
+#endif
+
+namespace bs2e {
+
+constexpr int kMaxOrder = 20;  // reference work arrays: bspline_tools.f90:163
+
+BS2E_HD int imin(int a, int b) { return a < b ? a : b; }
+BS2E_HD int imax(int a, int b) { return a > b ? a : b; }
+BS2E_HD int iabs(int a) { return a < 0 ? -a : a; }
+BS2E_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+struct PairAC { int a, c; };
+
+// ---------------------------------------------------------------------------
+// geometry of the B-spline basis (device pointers when used in kernels)
+// ---------------------------------------------------------------------------
+struct Geom {
+    int ks;      // spline order (namelist k)
+    int w;       // ks-1, half band width
+    int n;       // size(knots)-ks
+    int nb;      // n-2
+    int cells;   // number of knot intervals C
+    int K1;      // max_k+1
+    int kgl;     // Gauss-Legendre points per cell
+    int P;       // number of ordered band pairs
+    int ldP;     // padded leading dimension of one R^k plane (multiple of 16)
+    const double* t;     // knots, [n+ks]
+    const double* bp;    // breakpoints, [cells+1]
+    const double* glx;   // GL nodes on [-1,1], [kgl]
+    const double* glw;   // GL weights, [kgl]
+    const int* rowoff;   // [nb+2]: rowoff[a] = index of pair (a, max(1,a-w))
+    const PairAC* pair;  // [P]: pair index -> (a,c)
+};
+
+BS2E_HD int pair_clo(const Geom& g, int a) { return imax(1, a - g.w); }
+BS2E_HD int pair_index(const Geom& g, int a, int c) { return g.rowoff[a] + c - pair_clo(g, a); }
+// cells on which both splines of the pair live (bspline_tools.f90:50-54)
+BS2E_HD int pair_lo_cell(const Geom& g, int a, int c) { return imax(1, imax(a, c) - g.ks + 2); }
+BS2E_HD int pair_hi_cell(const Geom& g, int a, int c) { return imin(g.cells, imin(a, c) + 1); }
+
+// gfortran's r**k (integer k): square-and-multiply from the low bit
+BS2E_HD double powi(double x, int m)
+{
+    unsigned n = (unsigned)(m < 0 ? -m : m);
+    double y = (n & 1u) ? x : 1.0;
+    while (n >>= 1) {
+        x = x * x;
+        if (n & 1u) y *= x;
+    }
+    return m < 0 ? 1.0 / y : y;
+}
+
+// All `order` B-splines of that order that are non-zero on the knot interval
+// t(left) <= x < t(left+1) (1-based left), by the Cox-de Boor recurrence.
+// out[s] is the spline with full index left-order+1+s.
+BS2E_HD void bspline_values_left(const double* t, int order, int left, double x, double* out)
+{
+    double dl[kMaxOrder], dr[kMaxOrder];
+    out[0] = 1.0;
+    for (int j = 1; j < order; ++j) {
+        dr[j - 1] = t[left + j - 1] - x;
+        dl[j - 1] = x - t[left - j];
+        double saved = 0.0;
+        for (int i = 0; i < j; ++i) {
+            double term = out[i] / (dr[i] + dl[j - 1 - i]);
+            out[i] = saved + dr[i] * term;
+            saved = dl[j - 1 - i] * term;
+        }
+        out[j] = saved;
+    }
+}
+
+// All ks B-splines that are non-zero on cell v, evaluated at x.  out[s] is the
+// spline with FULL index v+s (b-index v+s-1).  Replaces the reference's ks
+// separate de Boor evaluations on unit coefficient vectors
+// (bspline_tools.f90:151-224 called from mat_els.f90:415-419,462-476).
+BS2E_HD void bspline_values(const double* t, int ks, int v, double x, double* out)
+{
+    bspline_values_left(t, ks, ks - 1 + v, x, out);
+}
+
+// ---------------------------------------------------------------------------
+// stage B: one R^k value from the staged cell integrals
+//   R^k(ab;cd), p1=(a,c), p2=(b,d)   (sparse_array_tools.f90:472-488)
+// mom_rk/mom_rmk : [K1][P][ks]   cell moments, slot = cell - lo_cell(pair)
+// pre            : [K1][P][ks+1] pre[t]  = sum_{slot <  t} mom_rk
+// sufx           : [K1][P][ks+1] sufx[t] = sum_{slot >= t} mom_rmk
+// rd             : [C][K1][ks*ks][ks*ks] same-cell integrals, local slots
+// ---------------------------------------------------------------------------
+struct CellData {
+    const double* mom_rk;
+    const double* mom_rmk;
+    const double* pre;
+    const double* sufx;
+    const double* rd;
+};
+
+BS2E_HD double rk_offdiag(const Geom& g, const CellData& cd, int k, int p1, int p2,
+                          int lo1, int lo2, int hi2)
+{
+    const int ks = g.ks;
+    const double* pre1 = cd.pre + ((size_t)k * g.P + p1) * (ks + 1);
+    const double* suf1 = cd.sufx + ((size_t)k * g.P + p1) * (ks + 1);
+    const double* rk2 = cd.mom_rk + ((size_t)k * g.P + p2) * ks;
+    const double* rmk2 = cd.mom_rmk + ((size_t)k * g.P + p2) * ks;
+    double acc = 0.0;
+    for (int s = 0; s <= hi2 - lo2; ++s) {
+        const int tt = lo2 + s - lo1;  // slot of cell u in pair 1's frame
+        acc += rmk2[s] * pre1[iclamp(tt, 0, ks)];
+        acc += rk2[s] * suf1[iclamp(tt + 1, 0, ks)];
+    }
+    return acc;
+}
+
+BS2E_HD double rk_diag(const Geom& g, const CellData& cd, int k, PairAC q1, PairAC q2,
+                       int vlo, int vhi)
+{
+    const int ks = g.ks, ks2 = ks * ks;
+    double d1 = 0.0, d2 = 0.0;
+    for (int v = vlo; v <= vhi; ++v) {
+        const int l1 = (q1.a + 1 - v) * ks + (q1.c + 1 - v);
+        const int l2 = (q2.a + 1 - v) * ks + (q2.c + 1 - v);
+        const double* blk = cd.rd + ((size_t)(v - 1) * g.K1 + k) * (size_t)ks2 * ks2;
+        d1 += blk[(size_t)l1 * ks2 + l2];  // electron 2 inside electron 1
+        d2 += blk[(size_t)l2 * ks2 + l1];  // electron 1 inside electron 2
+    }
+    return d1 + d2;
+}
+
+BS2E_HD double rk_element(const Geom& g, const CellData& cd, int k, int p1, int p2)
+{
+    const PairAC q1 = g.pair[p1], q2 = g.pair[p2];
+    const int lo1 = pair_lo_cell(g, q1.a, q1.c), hi1 = pair_hi_cell(g, q1.a, q1.c);
+    const int lo2 = pair_lo_cell(g, q2.a, q2.c), hi2 = pair_hi_cell(g, q2.a, q2.c);
+    double val = rk_offdiag(g, cd, k, p1, p2, lo1, lo2, hi2);
+    const int vlo = imax(lo1, lo2), vhi = imin(hi1, hi2);
+    if (vlo <= vhi) val += rk_diag(g, cd, k, q1, q2, vlo, vhi);
+    return val;
+}
+
+// One thread of the stage-B kernel: two adjacent p2 columns of kRkRows p1 rows
+// of the plane of multipole k.  Disjoint cell ranges collapse to one product
+// of total moments; overlapping ranges take the general element.
+constexpr int kRkRows = 16;      // p1 rows per CTA
+constexpr int kRkThreads = 128;  // each thread owns two adjacent p2 columns
+
+BS2E_HD void rk_build_thread(const Geom& g, const CellData& cd, double* R, int bx, int by, int k,
+                             int tx)
+{
+    const int p2 = (bx * kRkThreads + tx) * 2;
+    if (p2 >= g.ldP) return;
+    const int ks = g.ks;
+    const size_t kP = (size_t)k * g.P;
+
+    int lo2[2], hi2[2];
+    double trk2[2], trmk2[2];
+    bool ok[2];
+    for (int e = 0; e < 2; ++e) {
+        ok[e] = (p2 + e) < g.P;
+        lo2[e] = hi2[e] = 0;
+        trk2[e] = trmk2[e] = 0.0;
+        if (ok[e]) {
+            const PairAC q = g.pair[p2 + e];
+            lo2[e] = pair_lo_cell(g, q.a, q.c);
+            hi2[e] = pair_hi_cell(g, q.a, q.c);
+            trk2[e] = cd.pre[(kP + p2 + e) * (ks + 1) + ks];
+            trmk2[e] = cd.sufx[(kP + p2 + e) * (ks + 1)];
+        }
+    }
+    const int r0 = by * kRkRows;
+    for (int row = 0; row < kRkRows; ++row) {
+        const int p1 = r0 + row;
+        if (p1 >= g.P) break;
+        const PairAC q1 = g.pair[p1];
+        const int lo1 = pair_lo_cell(g, q1.a, q1.c), hi1 = pair_hi_cell(g, q1.a, q1.c);
+        const double trk1 = cd.pre[(kP + p1) * (ks + 1) + ks];
+        const double trmk1 = cd.sufx[(kP + p1) * (ks + 1)];
+        double out[2];
+        for (int e = 0; e < 2; ++e) {
+            if (!ok[e]) out[e] = 0.0;
+            else if (hi1 < lo2[e]) out[e] = trk1 * trmk2[e];   // electron 1 strictly inside
+            else if (hi2[e] < lo1) out[e] = trmk1 * trk2[e];   // electron 2 strictly inside
+            else out[e] = rk_element(g, cd, k, p1, p2 + e);
+        }
+        double* dst = R + (kP + p1) * g.ldP + p2;
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[1]);
+#else
+        dst[0] = out[0];
+        dst[1] = out[1];
+#endif
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage C: configuration blocks and the band-partner enumeration
+//   (hamiltonian.f90:150-205 pattern; orbital_tools.f90:157-193 ordering)
+// ---------------------------------------------------------------------------
+struct NcRow {      // one n_c row of an (l_c,l_d) configuration block
+    int nd_lo;      // first n_d present (nd_hi < nd_lo: row absent)
+    int nd_hi;
+    int start;      // 1-based configuration index of (n_c, nd_lo)
+    int pad;
+};
+
+struct BlockDesc {  // configurations sharing (l_1,l_2), contiguous in the list
+    int l1, l2;
+    int nc_lo, nc_hi;  // range of n_1 present
+};
+
+constexpr unsigned kDirAny = 1u;  // exists k: |ang_k| > 5e-15     (hamiltonian.f90:174)
+constexpr unsigned kExAny = 2u;   // same for the exchange ordering (l_d,l_c)
+
+struct KRange { signed char dlo, dhi, xlo, xhi; };  // k ranges (step 2) with non-zero factors
+
+struct Plan {
+    int nblk;
+    int n_config;
+    int full;
+    int L;
+    const BlockDesc* blk;        // [nblk]
+    const NcRow* ncrow;          // [nblk][nb+1], index n_c
+    const unsigned char* flags;  // [nblk][nblk]
+    const KRange* krange;        // [nblk][nblk]
+    const double* angD;          // [nblk][nblk][K1]   direct, |.|<5e-16 zeroed
+    const double* angX;          // [nblk][nblk][K1]   exchange * (-1)^(lc+ld+L)
+    const unsigned short* row_n1;   // [n_config]
+    const unsigned short* row_n2;   // [n_config]
+    const unsigned short* row_blk;  // [n_config]
+};
+
+// union of two closed integer intervals as <= 2 disjoint ascending intervals
+struct Union2 { int lo[2], hi[2]; int n; };
+
+BS2E_HD Union2 union2(int a1, int b1, int a2, int b2)
+{
+    Union2 u;
+    u.n = 0;
+    u.lo[0] = u.lo[1] = 0;
+    u.hi[0] = u.hi[1] = -1;
+    const bool e1 = a1 > b1, e2 = a2 > b2;
+    if (e1 && e2) return u;
+    if (e1) { u.lo[0] = a2; u.hi[0] = b2; u.n = 1; return u; }
+    if (e2) { u.lo[0] = a1; u.hi[0] = b1; u.n = 1; return u; }
+    if (a2 < a1) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+    if (a2 <= b1 + 1) {  // overlapping or adjacent: one interval
+        u.lo[0] = a1; u.hi[0] = imax(b1, b2); u.n = 1;
+    } else {
+        u.lo[0] = a1; u.hi[0] = b1; u.lo[1] = a2; u.hi[1] = b2; u.n = 2;
+    }
+    return u;
+}
+
+BS2E_HD int union2_count(const Union2& u)
+{
+    int c = 0;
+    for (int q = 0; q < u.n; ++q) c += u.hi[q] - u.lo[q] + 1;
+    return c;
+}
+
+struct RowInfo { int i; int bi; int na, nb; int la, lb; };
+
+BS2E_HD RowInfo row_info(const Plan& pl, int i /*1-based*/)
+{
+    RowInfo r;
+    r.i = i;
+    r.bi = pl.row_blk[i - 1];
+    r.na = pl.row_n1[i - 1];
+    r.nb = pl.row_n2[i - 1];
+    r.la = pl.blk[r.bi].l1;
+    r.lb = pl.blk[r.bi].l2;
+    return r;
+}
+
+// per (row, column block): which selection rules can fire
+struct Coupling {
+    bool dirany, exany, same, samex;
+    BS2E_HD bool any() const { return dirany || exany || same; }
+};
+
+BS2E_HD Coupling coupling(const Plan& pl, const RowInfo& r, int bj)
+{
+    Coupling c;
+    const unsigned f = pl.flags[(size_t)r.bi * pl.nblk + bj];
+    c.dirany = (f & kDirAny) != 0;
+    c.exany = (f & kExAny) != 0;
+    c.same = (bj == r.bi);                 // l_eq  (l_a=l_c, l_b=l_d)
+    c.samex = c.same && (r.la == r.lb);    // l_eq_ex (configs keep l_1 >= l_2)
+    return c;
+}
+
+// n_c windows of a row inside column block bj (ascending, <= 2 intervals)
+BS2E_HD Union2 nc_windows(const Geom& g, const Plan& pl, const RowInfo& r, int bj)
+{
+    const BlockDesc b = pl.blk[bj];
+    int lo = b.nc_lo, hi = b.nc_hi;
+    if (!pl.full && bj == r.bi) lo = imax(lo, r.na);  // j >= i
+    return union2(imax(lo, r.na - g.w), imin(hi, r.na + g.w),
+                  imax(lo, r.nb - g.w), imin(hi, r.nb + g.w));
+}
+
+// One (row, column block, n_c) segment: the n_d intervals with direct support
+// (D) and with exchange support (X), already clipped to the configurations
+// that exist and to j >= i.
+struct Segment {
+    int dlo, dhi, xlo, xhi;
+    int jbase;  // configuration index j = jbase + n_d
+};
+
+BS2E_HD Segment segment(const Geom& g, const Plan& pl, const RowInfo& r, int bj, int nc)
+{
+    Segment s;
+    const NcRow row = pl.ncrow[(size_t)bj * (g.nb + 1) + nc];
+    int lo = row.nd_lo, hi = row.nd_hi;
+    if (!pl.full && bj == r.bi && nc == r.na) lo = imax(lo, r.nb);  // j >= i
+    s.jbase = row.start - row.nd_lo;
+    if (iabs(r.na - nc) <= g.w) { s.dlo = imax(lo, r.nb - g.w); s.dhi = imin(hi, r.nb + g.w); }
+    else { s.dlo = 0; s.dhi = -1; }
+    if (iabs(r.nb - nc) <= g.w) { s.xlo = imax(lo, r.na - g.w); s.xhi = imin(hi, r.na + g.w); }
+    else { s.xlo = 0; s.xhi = -1; }
+    return s;
+}
+
+// stored sets of a segment (hamiltonian.f90:188-198)
+BS2E_HD Union2 seg_H(const Segment& s, const Coupling& c)
+{
+    const bool d = c.same || c.dirany, x = c.same || c.exany;
+    return union2(d ? s.dlo : 0, d ? s.dhi : -1, x ? s.xlo : 0, x ? s.xhi : -1);
+}
+BS2E_HD Union2 seg_S(const Segment& s, const Coupling& c)
+{
+    return union2(c.same ? s.dlo : 0, c.same ? s.dhi : -1, c.samex ? s.xlo : 0, c.samex ? s.xhi : -1);
+}
+
+// number of stored H and S entries of one row (replaces hamiltonian.f90:348-416)
+BS2E_HD void row_count(const Geom& g, const Plan& pl, int i, long long* nH, long long* nS)
+{
+    const RowInfo r = row_info(pl, i);
+    long long cH = 0, cS = 0;
+    for (int bj = (pl.full ? 0 : r.bi); bj < pl.nblk; ++bj) {
+        const Coupling c = coupling(pl, r, bj);
+        if (!c.any()) continue;
+        const Union2 win = nc_windows(g, pl, r, bj);
+        for (int q = 0; q < win.n; ++q)
+            for (int nc = win.lo[q]; nc <= win.hi[q]; ++nc) {
+                const Segment s = segment(g, pl, r, bj, nc);
+                cH += union2_count(seg_H(s, c));
+                if (c.same) cS += union2_count(seg_S(s, c));
+            }
+    }
+    *nH = cH;
+    *nS = cS;
+}
+
+// Traversal of the stored H entries of one row in ascending column order, in
+// chunks of <= 32 consecutive n_d (one warp step each).  f(bj, nc, seg, cpl,
+// base, hi): columns n_d = base .. min(base+31, hi) of segment seg.
+template <class F>
+BS2E_HD void for_each_chunk(const Geom& g, const Plan& pl, const RowInfo& r, F&& f)
+{
+    for (int bj = (pl.full ? 0 : r.bi); bj < pl.nblk; ++bj) {
+        const Coupling c = coupling(pl, r, bj);
+        if (!c.any()) continue;
+        const Union2 win = nc_windows(g, pl, r, bj);
+        for (int q = 0; q < win.n; ++q)
+            for (int nc = win.lo[q]; nc <= win.hi[q]; ++nc) {
+                const Segment s = segment(g, pl, r, bj, nc);
+                const Union2 uh = seg_H(s, c);
+                for (int z = 0; z < uh.n; ++z)
+                    for (int base = uh.lo[z]; base <= uh.hi[z]; base += 32)
+                        f(bj, nc, s, c, base, uh.hi[z]);
+            }
+    }
+}
+
+// one-particle matrices in band storage: M[l][n][n'-n+w], complex interleaved;
+// entries outside the band are exact zeros in the reference's dense arrays
+struct OneBody {
+    const double* Hb;  // [lmax+1][nb+1][2w+1][2]
+    const double* Sb;  // [nb+1][2w+1][2]
+};
+
+struct Cplx { double re, im; };
+BS2E_HD Cplx cmul(Cplx a, Cplx b) { return Cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+BS2E_HD Cplx cadd(Cplx a, Cplx b) { return Cplx{a.re + b.re, a.im + b.im}; }
+
+BS2E_HD Cplx band_S(const Geom& g, const OneBody& ob, int n, int np)
+{
+    const int d = np - n + g.w;
+    if (d < 0 || d > 2 * g.w) return Cplx{0.0, 0.0};
+    const double* q = ob.Sb + ((size_t)n * (2 * g.w + 1) + d) * 2;
+    return Cplx{q[0], q[1]};
+}
+BS2E_HD Cplx band_H(const Geom& g, const OneBody& ob, int l, int n, int np)
+{
+    const int d = np - n + g.w;
+    if (d < 0 || d > 2 * g.w) return Cplx{0.0, 0.0};
+    const double* q = ob.Hb + (((size_t)l * (g.nb + 1) + n) * (2 * g.w + 1) + d) * 2;
+    return Cplx{q[0], q[1]};
+}
+
+struct Element { Cplx H, S; bool storeS; };
+
+// value of the (i,j) entry, j = (bj, nc, nd)
+//   mat_els.f90:552-571 r_12_tens, :608-633 c_mat_neq_tens,
+//   :664-678 S_mat_neq, :697-715 H_1p_neq; hamiltonian.f90:183-193
+BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
+                              const double* R, const RowInfo& r, const Coupling& c,
+                              int bj, int nc, int nd, bool sup, bool sup_ex)
+{
+    Element e;
+    e.H = Cplx{0.0, 0.0};
+    e.S = Cplx{0.0, 0.0};
+    const bool allowed = (sup && c.dirany) || (sup_ex && c.exany);
+    const size_t plane = (size_t)g.P * g.ldP;
+    const size_t cpl = ((size_t)r.bi * pl.nblk + bj);
+    if (allowed) {
+        const KRange kr = pl.krange[cpl];
+        double res = 0.0;
+        if (sup) {  // sum_k ang_k R^k(n_a n_b; n_c n_d)
+            const double* ang = pl.angD + cpl * g.K1;
+            const double* Rp = R + (size_t)pair_index(g, r.na, nc) * g.ldP + pair_index(g, r.nb, nd);
+            double acc = 0.0;
+            for (int k = kr.dlo; k <= kr.dhi; k += 2) acc += Rp[k * plane] * ang[k];
+            res += acc;
+        }
+        if (sup_ex) {  // (-1)^(lc+ld+L) sum_k ang^ex_k R^k(n_a n_b; n_d n_c), read through
+                       // the electron-exchange symmetry R^k(ab;dc) = R^k(ba;cd)
+            const double* ang = pl.angX + cpl * g.K1;
+            const double* Rp = R + (size_t)pair_index(g, r.nb, nc) * g.ldP + pair_index(g, r.na, nd);
+            double acc = 0.0;
+            for (int k = kr.xlo; k <= kr.xhi; k += 2) acc += Rp[k * plane] * ang[k];
+            res += acc;
+        }
+        e.H.re = res;
+    }
+    e.storeS = (sup && c.same) || (sup_ex && c.samex);
+    if (e.storeS) {
+        const BlockDesc bc = pl.blk[bj];
+        const int lc = bc.l1, ld = bc.l2;
+        Cplx h = Cplx{0.0, 0.0}, s = Cplx{0.0, 0.0};
+        if (c.same) {
+            const Cplx Sbd = band_S(g, ob, r.nb, nd), Sac = band_S(g, ob, r.na, nc);
+            h = cadd(h, cmul(band_H(g, ob, r.la, r.na, nc), Sbd));
+            h = cadd(h, cmul(band_H(g, ob, r.lb, r.nb, nd), Sac));
+            s = cadd(s, cmul(Sac, Sbd));
+        }
+        if (c.samex) {
+            const double sgn = ((pl.L + lc + ld) & 1) ? -1.0 : 1.0;
+            const Cplx Sbc = band_S(g, ob, r.nb, nc), Sad = band_S(g, ob, r.na, nd);
+            Cplx hx = cadd(cmul(band_H(g, ob, r.la, r.na, nd), Sbc),
+                           cmul(band_H(g, ob, r.lb, r.nb, nc), Sad));
+            h = cadd(h, Cplx{hx.re * sgn, hx.im * sgn});
+            Cplx sx = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
+            s = cadd(s, sx);
+        }
+        e.H = cadd(e.H, h);
+        e.S = s;
+    }
+    return e;
+}
+
+}  // namespace bs2e

@@ -1,0 +1,133 @@
+// ctx.h -- internal state behind the opaque handles of include/bs2e.h
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "core.h"
+#include "geom_host.h"
+
+namespace bs2e {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+void set_last_error(const std::string& msg);
+extern std::atomic<long long> g_launches;
+
+#define BS2E_CUDA(call)                                                            \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess)                                                     \
+            throw ::bs2e::Error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define BS2E_LAUNCHED()                                  \
+    do {                                                 \
+        ::bs2e::g_launches.fetch_add(1);                 \
+        BS2E_CUDA(cudaGetLastError());                   \
+    } while (0)
+
+template <class T>
+T* dev_alloc(size_t n)
+{
+    T* p = nullptr;
+    BS2E_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+    return p;
+}
+template <class T>
+T* dev_upload(const std::vector<T>& v, cudaStream_t st)
+{
+    T* p = dev_alloc<T>(v.size());
+    if (!v.empty())
+        BS2E_CUDA(cudaMemcpyAsync(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    return p;
+}
+
+}  // namespace bs2e
+
+struct bs2e_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int max_k = 0;
+
+    // host copy of the basis geometry
+    bs2e::HostGeom host;
+    bs2e::Geom hg{};  // = host.g, pointers are HOST pointers
+    long long nnz_4d = 0, nnz_6d = 0;
+
+    // device copy
+    bs2e::Geom dg{};  // pointers in dg are DEVICE pointers
+    double *d_t = nullptr, *d_bp = nullptr, *d_glx = nullptr, *d_glw = nullptr;
+    int* d_rowoff = nullptr;
+    bs2e::PairAC* d_pair = nullptr;
+
+    // stage A products
+    double *d_mom_rk = nullptr, *d_mom_rmk = nullptr;  // [K1][P][ks]
+    double *d_pre = nullptr, *d_sufx = nullptr;        // [K1][P][ks+1]
+    double* d_rd = nullptr;                            // [C][K1][ks^2][ks^2]
+    bool have_cells = false;
+
+    // stage B product
+    double* d_R = nullptr;  // [K1][P][ldP]
+    bool have_R = false;
+
+    // stage C inputs (band storage)
+    int lmax_1p = -1;
+    double *d_Hb = nullptr, *d_Sb = nullptr;
+    bool have_1p = false;
+
+    bs2e::CellData cell_data() const
+    {
+        return bs2e::CellData{d_mom_rk, d_mom_rmk, d_pre, d_sufx, d_rd};
+    }
+    bs2e::OneBody one_body() const { return bs2e::OneBody{d_Hb, d_Sb}; }
+};
+
+struct bs2e_block {
+    bs2e_ctx* ctx = nullptr;
+    int L = 0, full = 0, lmax = 0;
+    long long n_config = 0, row_lo = 1, row_hi = 0;
+    bs2e::Plan dplan{};  // device pointers
+    // device-side plan storage
+    bs2e::BlockDesc* d_blk = nullptr;
+    bs2e::NcRow* d_ncrow = nullptr;
+    unsigned char* d_flags = nullptr;
+    bs2e::KRange* d_krange = nullptr;
+    double *d_angD = nullptr, *d_angX = nullptr;
+    unsigned short *d_row_n1 = nullptr, *d_row_n2 = nullptr, *d_row_blk = nullptr;
+    // CSR fragment (device)
+    long long *d_cntH = nullptr, *d_cntS = nullptr;  // [nrows+1] counts
+    long long *d_Hptr = nullptr, *d_Sptr = nullptr;  // [nrows+1] 1-based
+    long long *d_Hidx = nullptr, *d_Sidx = nullptr;
+    double *d_Hdat = nullptr, *d_Sdat = nullptr;
+    long long nnzH = 0, nnzS = 0;
+    void* d_scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    bool assembled = false;
+};
+
+namespace bs2e {
+// stage launchers (slater.cu, rk.cu, block.cu)
+void run_slater_cells(bs2e_ctx* c);
+void run_rk_build(bs2e_ctx* c);
+void fetch_r_k(bs2e_ctx* c, double* r_k, double* r_m_k, int64_t* iv, int64_t* i, int64_t* j);
+void fetch_r_d_k(bs2e_ctx* c, double* r_d_k, int64_t* iv, int64_t* i, int64_t* j, int64_t* ip,
+                 int64_t* jp);
+void fetch_rk_keys(bs2e_ctx* c, long long n_keys, const int64_t* keys, double* vals);
+void fetch_rk_plane(bs2e_ctx* c, int k, double* out);
+
+bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
+                       const int64_t* conf_l, int full, long long row_lo, long long row_hi);
+void block_assemble(bs2e_block* b);
+void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat, int64_t* S_ptr,
+                    int64_t* S_idx, double* S_dat);
+void block_row_counts(bs2e_block* b, int64_t* cH, int64_t* cS);
+void block_checksum(bs2e_block* b, uint64_t* sH, uint64_t* sS);
+void block_free(bs2e_block* b);
+}  // namespace bs2e

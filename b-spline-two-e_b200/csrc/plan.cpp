@@ -1,0 +1,169 @@
+// plan.cpp -- host part of stage C: derive the (l1,l2) block structure from
+// the configuration list that count_configs generated
+// (src/tools/orbital_tools.f90:157-193) and tabulate the angular factors
+// ang_k_LS (src/tools/wigner_tools.f90:126-138) per pair of blocks with the
+// thresholds of src/mat_els/hamiltonian.f90:174 (5e-15, sparsity pattern) and
+// src/mat_els/mat_els.f90:568 (5e-16, terms of the k sum).
+#include "plan.h"
+
+#include <cmath>
+#include <mutex>
+#include <set>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "wigner.h"
+
+namespace bs2e {
+
+// ---------------------------------------------------------------------------
+// angular tables, memoised per process ("tabulated on the host, uploaded once")
+// ---------------------------------------------------------------------------
+namespace {
+std::mutex g_ang_mu;
+std::unordered_map<uint64_t, double> g_ang_memo;
+
+double ang_cached(int k, int la, int lb, int lc, int ld, int L)
+{
+    const uint64_t key = ((uint64_t)k << 40) | ((uint64_t)la << 32) | ((uint64_t)lb << 24) |
+                         ((uint64_t)lc << 16) | ((uint64_t)ld << 8) | (uint64_t)L;
+    {
+        std::lock_guard<std::mutex> lk(g_ang_mu);
+        auto it = g_ang_memo.find(key);
+        if (it != g_ang_memo.end()) return it->second;
+    }
+    const double v = ang_k_LS(k, la, lb, lc, ld, L);
+    std::lock_guard<std::mutex> lk(g_ang_mu);
+    g_ang_memo.emplace(key, v);
+    return v;
+}
+}  // namespace
+
+HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_t* conf_n,
+                         const int64_t* conf_l, int full, long long row_lo, long long row_hi)
+{
+    typedef std::invalid_argument Error;
+    if (n_config <= 0) throw Error("block_plan: n_config must be positive");
+    if (n_config > 2147483000LL) throw Error("block_plan: n_config exceeds 32-bit row indices");
+    if (row_lo < 1 || row_hi > n_config || row_hi < row_lo)
+        throw Error("block_plan: row range outside 1..n_config");
+    if (hg.nb > 65535) throw Error("block_plan: n_b exceeds 16-bit storage");
+    if (L < 0 || L > 255) throw Error("block_plan: L out of range");
+
+    std::vector<BlockDesc> blocks;
+    std::vector<NcRow> ncrow;
+    std::vector<unsigned short> rn1(n_config), rn2(n_config), rblk(n_config);
+    std::set<std::pair<int, int>> seen;
+    const int stride = hg.nb + 1;
+    int prev_n1 = 0, prev_n2 = 0;
+    for (long long i = 0; i < n_config; ++i) {
+        const long long n1 = conf_n[2 * i], n2 = conf_n[2 * i + 1];
+        const long long l1 = conf_l[2 * i], l2 = conf_l[2 * i + 1];
+        if (n1 < 1 || n1 > hg.nb || n2 < 1 || n2 > hg.nb)
+            throw Error("block_plan: configuration n outside 1..n_b");
+        if (l2 < 0 || l1 < l2 || l1 > 120)
+            throw Error("block_plan: configurations must have l(1) >= l(2) >= 0 (count_configs order)");
+        const bool newblk = blocks.empty() || blocks.back().l1 != l1 || blocks.back().l2 != l2;
+        if (newblk) {
+            if (!seen.insert({(int)l1, (int)l2}).second)
+                throw Error("block_plan: configurations of one (l1,l2) pair are not contiguous");
+            blocks.push_back(BlockDesc{(int)l1, (int)l2, (int)n1, (int)n1});
+            ncrow.resize(blocks.size() * (size_t)stride, NcRow{1, 0, 0, 0});
+        }
+        BlockDesc& b = blocks.back();
+        NcRow& row = ncrow[(blocks.size() - 1) * (size_t)stride + n1];
+        if (newblk || n1 != prev_n1) {
+            if (!newblk && n1 < prev_n1)
+                throw Error("block_plan: n(1) not ascending inside an (l1,l2) block");
+            if (row.nd_hi >= row.nd_lo) throw Error("block_plan: duplicate n(1) row");
+            row.nd_lo = (int)n2;
+            row.nd_hi = (int)n2;
+            row.start = (int)(i + 1);
+            b.nc_hi = (int)n1;
+        } else {
+            if (n2 != prev_n2 + 1)
+                throw Error("block_plan: n(2) not consecutive inside an n(1) row");
+            row.nd_hi = (int)n2;
+        }
+        prev_n1 = (int)n1;
+        prev_n2 = (int)n2;
+        rn1[i] = (unsigned short)n1;
+        rn2[i] = (unsigned short)n2;
+        rblk[i] = (unsigned short)(blocks.size() - 1);
+    }
+    const int nblk = (int)blocks.size();
+    if (nblk > 65535) throw Error("block_plan: too many (l1,l2) blocks");
+
+    // angular tables (hamiltonian.f90:171-178 pattern test, mat_els.f90:566-570 sum)
+    const int K1 = hg.K1;
+    std::vector<double> angD((size_t)nblk * nblk * K1, 0.0), angX((size_t)nblk * nblk * K1, 0.0);
+    std::vector<unsigned char> flags((size_t)nblk * nblk, 0);
+    std::vector<KRange> krange((size_t)nblk * nblk);
+    for (int bi = 0; bi < nblk; ++bi)
+        for (int bj = 0; bj < nblk; ++bj) {
+            const int la = blocks[bi].l1, lb = blocks[bi].l2;
+            const int lc = blocks[bj].l1, ld = blocks[bj].l2;
+            const size_t o = (size_t)bi * nblk + bj;
+            const double sgn = ((lc + ld + L) & 1) ? -1.0 : 1.0;
+            unsigned f = 0;
+            KRange kr{1, 0, 1, 0};
+            bool dfirst = true, xfirst = true;
+            for (int k = 0; k < K1; ++k) {
+                const double ad = ang_cached(k, la, lb, lc, ld, L);
+                const double ax = ang_cached(k, la, lb, ld, lc, L);
+                if (fabs(ad) > 5.e-15) f |= kDirAny;
+                if (fabs(ax) > 5.e-15) f |= kExAny;
+                if (!(fabs(ad) < 5.e-16)) {
+                    angD[o * K1 + k] = ad;
+                    if (dfirst) { kr.dlo = (signed char)k; dfirst = false; }
+                    kr.dhi = (signed char)k;
+                }
+                if (!(fabs(ax) < 5.e-16)) {
+                    angX[o * K1 + k] = sgn * ax;
+                    if (xfirst) { kr.xlo = (signed char)k; xfirst = false; }
+                    kr.xhi = (signed char)k;
+                }
+            }
+            flags[o] = (unsigned char)f;
+            krange[o] = kr;
+        }
+
+    HostPlan hp;
+    hp.nblk = nblk;
+    hp.L = L;
+    hp.full = full ? 1 : 0;
+    hp.n_config = n_config;
+    hp.lmax = 0;
+    for (auto& d : blocks) hp.lmax = d.l1 > hp.lmax ? d.l1 : hp.lmax;
+    hp.blocks = std::move(blocks);
+    hp.ncrow = std::move(ncrow);
+    hp.flags = std::move(flags);
+    hp.krange = std::move(krange);
+    hp.angD = std::move(angD);
+    hp.angX = std::move(angX);
+    hp.row_n1 = std::move(rn1);
+    hp.row_n2 = std::move(rn2);
+    hp.row_blk = std::move(rblk);
+    return hp;
+}
+
+Plan HostPlan::view() const
+{
+    Plan pl;
+    pl.nblk = nblk;
+    pl.n_config = (int)n_config;
+    pl.full = full;
+    pl.L = L;
+    pl.blk = blocks.data();
+    pl.ncrow = ncrow.data();
+    pl.flags = flags.data();
+    pl.krange = krange.data();
+    pl.angD = angD.data();
+    pl.angX = angX.data();
+    pl.row_n1 = row_n1.data();
+    pl.row_n2 = row_n2.data();
+    pl.row_blk = row_blk.data();
+    return pl;
+}
+
+}  // namespace bs2e

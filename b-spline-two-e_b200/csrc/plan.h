@@ -1,0 +1,25 @@
+// plan.h -- host-side plan of one symmetry block (see plan.cpp)
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "core.h"
+
+namespace bs2e {
+
+struct HostPlan {
+    int nblk = 0, L = 0, full = 0, lmax = 0;
+    long long n_config = 0;
+    std::vector<BlockDesc> blocks;
+    std::vector<NcRow> ncrow;
+    std::vector<unsigned char> flags;
+    std::vector<KRange> krange;
+    std::vector<double> angD, angX;
+    std::vector<unsigned short> row_n1, row_n2, row_blk;
+    Plan view() const;  // Plan over the HOST arrays
+};
+
+HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_t* conf_n,
+                         const int64_t* conf_l, int full, long long row_lo, long long row_hi);
+
+}  // namespace bs2e

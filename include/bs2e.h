@@ -1,0 +1,164 @@
+/*
+ * bs2e.h -- C ABI of libbs2e_gpu.so: the B200 (sm_100a) implementation of the
+ * two-electron matrix-element hot path of edvinolo/b-spline-two-e.
+ *
+ * The reference has no FFI layer for this path; the seams are three Fortran
+ * calls in src/apps/main_basis_setup.f90:
+ *     :80   call setup_Slater_integrals(splines,max_k,k_GL,r_k,r_m_k,r_d_k)
+ *     :85   call compute_R_k_map(r_d_k,r_k,r_m_k,splines,max_k,R_p)
+ *     :108  call construct_block_tensor(H_vec,S,splines,bas%syms(i),max_k,R_p,
+ *                                       H_diag%blocks(i),S_diag%blocks(i),full)
+ * Each entry point below names the reference routine it stands in for.  The
+ * ISO_C_BINDING module a maintainer adds on the Fortran side is
+ * fortran/bs2e_gpu_binding.f90.
+ *
+ * Conventions: every integer is int64_t (the reference is built with
+ * -fdefault-integer-8), reals are double, complex numbers are interleaved
+ * (re,im) doubles, arrays are column-major, spline / configuration / CSR
+ * indices are 1-based exactly as the reference stores them.  Every function
+ * returns 0 on success and a non-zero status otherwise; the message is
+ * available from bs2e_last_error() (thread local).  There is no CPU fallback:
+ * without a usable CUDA device every compute entry point fails.
+ */
+#ifndef BS2E_H
+#define BS2E_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bs2e_ctx bs2e_ctx;      /* device-resident basis + R^k tensor */
+typedef struct bs2e_block bs2e_block;  /* one symmetry block being assembled */
+
+const char *bs2e_last_error(void);
+int bs2e_device_count(int64_t *count);
+
+/* Stands in for the state the reference keeps in type(b_spline)
+ * (src/tools/bspline_tools.f90:4-40) plus the Gauss-Legendre rule that
+ * setup_GL(k_GL,-1,1,x,w) returns (src/tools/quad_tools.f90:14-27; the nodes
+ * come from fortran-stdlib on the caller's side so they are bit-identical to
+ * what the reference integrates with).  knots has n_knots = n + k entries.   */
+int bs2e_ctx_create(int64_t k_spline, int64_t n_knots, const double *knots,
+                    int64_t max_k, int64_t k_GL, const double *gl_x,
+                    const double *gl_w, int64_t device, bs2e_ctx **ctx);
+int bs2e_ctx_destroy(bs2e_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t). */
+int bs2e_ctx_set_stream(bs2e_ctx *ctx, void *cuda_stream);
+int bs2e_ctx_sync(bs2e_ctx *ctx);
+
+/* sparse_4d%count_nnz / sparse_6d%count_nnz / count_nnz_R_k
+ * (src/tools/sparse_array_tools.f90:276-366); P*P = count_nnz_R_k.          */
+int bs2e_sizes(bs2e_ctx *ctx, int64_t *n_b, int64_t *cells, int64_t *P,
+               int64_t *nnz_4d, int64_t *nnz_6d);
+
+/* ---- stage A: setup_Slater_integrals (src/mat_els/mat_els.f90:172-292,
+ *      392-491).  Results stay on the device.                               */
+int bs2e_slater_cells(bs2e_ctx *ctx);
+/* Copy the cell integrals back in the reference's entry order so that the
+ * Fortran sparse_4d / sparse_6d objects can be populated:
+ * r_k, r_m_k: data(nnz_4d, 0:max_k); iv,i,j: (nnz_4d)  (mat_els.f90:430-438)
+ * r_d_k: data(nnz_6d, 0:max_k); iv,i,j,i_p,j_p: (nnz_6d) (mat_els.f90:484-490)
+ * Any pointer may be NULL to skip that array.                               */
+int bs2e_get_r_k(bs2e_ctx *ctx, double *r_k, double *r_m_k,
+                 int64_t *iv, int64_t *i, int64_t *j);
+int bs2e_get_r_d_k(bs2e_ctx *ctx, double *r_d_k, int64_t *iv, int64_t *i,
+                   int64_t *j, int64_t *i_p, int64_t *j_p);
+
+/* ---- stage B: compute_R_K_map (src/tools/sparse_array_tools.f90:452-493).
+ *      The R^k tensor stays on the device; the Fortran Nd_DOK becomes a
+ *      holder of the context handle.                                        */
+int bs2e_rk_build(bs2e_ctx *ctx);
+/* Nd_DOK%get_val (sparse_array_tools.f90:536-555) for n_keys keys (a,b,c,d):
+ * keys is (4, n_keys), vals is (max_k+1, n_keys); a key outside the band
+ * structure is an error, as in the reference.                               */
+int bs2e_rk_get(bs2e_ctx *ctx, int64_t n_keys, const int64_t *keys, double *vals);
+/* One multipole plane as a dense (P,P) matrix, out[p1*P + p2]; pair numbering
+ * is a-major / c ascending over ordered band pairs (a,c).                   */
+int bs2e_rk_plane(bs2e_ctx *ctx, int64_t k, double *out);
+
+/* ---- stage C inputs: H_vec(0:max_l_1p)%data and S as passed to
+ *      construct_block_tensor (hamiltonian.f90:106-108): dense complex
+ *      n_b x n_b column-major matrices, H_vec concatenated over l.          */
+int bs2e_set_one_particle(bs2e_ctx *ctx, int64_t max_l_1p, const double *H_vec,
+                          const double *S);
+
+/* ---- stage C: one symmetry block.
+ * conf_n / conf_l are (2, n_config): term%configs(:)%n and %l
+ * (src/tools/orbital_tools.f90:15-19) in the order count_configs generates
+ * (orbital_tools.f90:157-193).  L is term%l; full as in the reference.
+ *
+ * bs2e_block_count   = count_nnz            (hamiltonian.f90:348-416)
+ * bs2e_block_fill    = construct_block_tensor (hamiltonian.f90:106-283),
+ *                      filling arrays the caller allocated from the counts:
+ *                      index_ptr(n_config+1), indices(nnz), data(nnz).
+ * The counts are those of the pattern the reference EMITS (they coincide with
+ * count_nnz whenever the reference itself does not overrun its arrays, see
+ * SURVEY.md F5).                                                            */
+int bs2e_block_count(bs2e_ctx *ctx, int64_t L, int64_t n_config,
+                     const int64_t *conf_n, const int64_t *conf_l, int64_t full,
+                     int64_t *nnz_H, int64_t *nnz_S);
+int bs2e_block_fill(bs2e_ctx *ctx, int64_t L, int64_t n_config,
+                    const int64_t *conf_n, const int64_t *conf_l, int64_t full,
+                    int64_t *H_ptr, int64_t *H_idx, double *H_dat,
+                    int64_t *S_ptr, int64_t *S_idx, double *S_dat);
+
+/* Split form of the same work, used for device-resident pipelines and for
+ * sharding rows over GPUs: rows row_lo..row_hi (1-based, inclusive) of the
+ * block are planned/counted, assembled on the device and downloaded as a CSR
+ * fragment whose index_ptr starts at 1.                                     */
+int bs2e_block_plan(bs2e_ctx *ctx, int64_t L, int64_t n_config,
+                    const int64_t *conf_n, const int64_t *conf_l, int64_t full,
+                    int64_t row_lo, int64_t row_hi, bs2e_block **blk);
+int bs2e_block_nnz(bs2e_block *blk, int64_t *nnz_H, int64_t *nnz_S);
+/* per-row entry counts of the planned rows (row_hi-row_lo+1 values each) */
+int bs2e_block_row_counts(bs2e_block *blk, int64_t *cnt_H, int64_t *cnt_S);
+int bs2e_block_assemble(bs2e_block *blk);
+int bs2e_block_download(bs2e_block *blk, int64_t *H_ptr, int64_t *H_idx, double *H_dat,
+                        int64_t *S_ptr, int64_t *S_idx, double *S_dat);
+/* 64-bit checksums of the device-resident fragment (indices and raw data
+ * bits), for runs whose output is too large to bring to the host.           */
+int bs2e_block_checksum(bs2e_block *blk, uint64_t *sum_H, uint64_t *sum_S);
+int bs2e_block_free(bs2e_block *blk);
+
+/* Pinned host memory for callers that want full-speed transfers. */
+int bs2e_host_alloc(int64_t bytes, void **ptr);
+int bs2e_host_free(void *ptr);
+
+/* Number of kernels this library has launched since load (all contexts). */
+int64_t bs2e_launch_count(void);
+
+/* ---- host-side companions of the path (no GPU needed).  They restate the
+ *      cheap reference routines whose OUTPUT feeds the hot path, so that a
+ *      driver without the Fortran program (tests, bench.py) can produce the
+ *      same inputs.                                                         */
+/* grid_tools.f90:6-55 generate_grid; returns the number of knots (or -1). */
+int64_t bs2e_host_generate_grid(int64_t k, int64_t m, int64_t Z, double h_max,
+                                double r_max, double *grid, int64_t cap);
+/* quad_tools.f90:14-27 setup_GL on [a,b] */
+int bs2e_host_gauss_legendre(int64_t N, double a, double b, double *x, double *w);
+/* bspline_tools.f90:364-373 find_max_n_b */
+int64_t bs2e_host_find_max_n_b(int64_t k, int64_t n_knots, const double *knots, double x);
+/* mat_els.f90:85-118 setup_S and :47-83 setup_H_one_particle (hydrogenic
+ * potential, potentials.f90:35-43; CAP, CAP_tools.f90:24-34)                */
+int bs2e_host_setup_S(int64_t k, int64_t n_knots, const double *knots, int64_t k_GL, double *S);
+int bs2e_host_setup_H_one_particle(int64_t k, int64_t n_knots, const double *knots,
+                                   int64_t Z, int64_t l, int64_t CAP_order, double CAP_r_0,
+                                   double CAP_eta_re, double CAP_eta_im, int64_t k_GL, double *H);
+/* orbital_tools.f90:245-343 init_basis (two_el): symmetry list, then
+ * count_configs (:119-216) per symmetry.                                    */
+int64_t bs2e_host_basis_syms(int64_t max_L, int64_t z_pol, int64_t *sym_l,
+                             int64_t *sym_m, int64_t *sym_pi, int64_t cap);
+int64_t bs2e_host_count_configs(int64_t term_l, int64_t term_pi, int64_t max_l_1p,
+                                int64_t n_b, int64_t k_spline, int64_t max_n_b,
+                                int64_t n_all_l, int64_t l_2_max, int64_t *conf_n,
+                                int64_t *conf_l, int64_t *conf_eqv, int64_t cap);
+/* wigner_tools.f90:30-60,126-138 (exact arithmetic instead of GSL) */
+double bs2e_host_three_j0(int64_t ja, int64_t jb, int64_t jc);
+double bs2e_host_six_j(int64_t ja, int64_t jb, int64_t jc, int64_t jd, int64_t je, int64_t jf);
+double bs2e_host_ang_k_LS(int64_t k, int64_t la, int64_t lb, int64_t lc, int64_t ld, int64_t L);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BS2E_H */

@@ -1,0 +1,213 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE.  Executes the thread-level bodies of
+// the CUDA kernels (core.h / slater_core.h, compiled here as plain C++) in
+// serial loops on the CPU, so the index logic of the GPU path can be checked
+// against the oracle in the GPU-less CI container.  Never linked into, loaded
+// by, or shipped with the product library.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../b-spline-two-e_b200/csrc/core.h"
+#include "../../b-spline-two-e_b200/csrc/geom_host.h"
+#include "../../b-spline-two-e_b200/csrc/plan.h"
+#include "../../b-spline-two-e_b200/csrc/slater_core.h"
+
+using namespace bs2e;
+
+static std::string g_err;
+
+struct HcCtx {
+    HostGeom hg;
+    std::vector<double> mom_rk, mom_rmk, pre, sufx, rd, R;
+    std::vector<double> Hb, Sb;
+    int lmax_1p = -1;
+};
+
+extern "C" {
+
+const char* hc_last_error() { return g_err.c_str(); }
+
+HcCtx* hc_create(int64_t ks, int64_t nt, const double* knots, int64_t max_k, int64_t kgl,
+                 const double* glx, const double* glw)
+{
+    try {
+        HcCtx* c = new HcCtx();
+        build_host_geom(c->hg, (int)ks, (int)nt, knots, (int)max_k, (int)kgl, glx, glw);
+        return c;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void hc_destroy(HcCtx* c) { delete c; }
+
+void hc_sizes(HcCtx* c, int64_t* nb, int64_t* cells, int64_t* P, int64_t* ldP, int64_t* nnz4,
+              int64_t* nnz6)
+{
+    *nb = c->hg.g.nb; *cells = c->hg.g.cells; *P = c->hg.g.P; *ldP = c->hg.g.ldP;
+    *nnz4 = c->hg.nnz_4d; *nnz6 = c->hg.nnz_6d;
+}
+
+// emulates run_slater_cells: one "CTA" per cell, nthr threads, phases separated
+// where the kernel has __syncthreads()
+void hc_slater_cells(HcCtx* c, int64_t nthr_mom, int64_t nthr_diag, int64_t ksplit)
+{
+    const Geom& g = c->hg.g;
+    const size_t ks2 = (size_t)g.ks * g.ks;
+    c->mom_rk.assign((size_t)g.K1 * g.P * g.ks, 0.0);
+    c->mom_rmk.assign((size_t)g.K1 * g.P * g.ks, 0.0);
+    c->pre.assign((size_t)g.K1 * g.P * (g.ks + 1), -1.0);
+    c->sufx.assign((size_t)g.K1 * g.P * (g.ks + 1), -1.0);
+    c->rd.assign((size_t)g.cells * g.K1 * ks2 * ks2, -7.0);
+    std::vector<double> sm(mom_smem_doubles(g));
+    for (int v = 1; v <= g.cells; ++v) {
+        MomSmem m = mom_smem_carve(g, sm.data());
+        for (int t = 0; t < nthr_mom; ++t) mom_phase_tables(g, v, m, t, (int)nthr_mom);
+        for (int t = 0; t < nthr_mom; ++t)
+            mom_phase_integrate(g, v, m, t, (int)nthr_mom, c->mom_rk.data(), c->mom_rmk.data());
+    }
+    for (size_t idx = 0; idx < (size_t)g.K1 * g.P; ++idx)
+        pair_prefix_item(g, idx, c->mom_rk.data(), c->mom_rmk.data(), c->pre.data(), c->sufx.data());
+    std::vector<double> sd(diag_smem_doubles(g));
+    for (int v = 1; v <= g.cells; ++v)
+        for (int by = 0; by < ksplit; ++by) {
+            DiagSmem d = diag_smem_carve(g, sd.data());
+            for (int t = 0; t < nthr_diag; ++t) diag_phase_tables(g, v, d, t, (int)nthr_diag);
+            for (int k = by; k < g.K1; k += (int)ksplit) {
+                for (int t = 0; t < nthr_diag; ++t) diag_phase_powers(g, k, d, t, (int)nthr_diag);
+                for (int t = 0; t < nthr_diag; ++t) diag_phase_inner(g, k, d, t, (int)nthr_diag);
+                for (int t = 0; t < nthr_diag; ++t)
+                    diag_phase_outer(g, v, k, d, t, (int)nthr_diag, c->rd.data());
+            }
+        }
+}
+
+void hc_get_moments(HcCtx* c, double* mom_rk, double* mom_rmk, double* rd)
+{
+    if (mom_rk) memcpy(mom_rk, c->mom_rk.data(), sizeof(double) * c->mom_rk.size());
+    if (mom_rmk) memcpy(mom_rmk, c->mom_rmk.data(), sizeof(double) * c->mom_rmk.size());
+    if (rd) memcpy(rd, c->rd.data(), sizeof(double) * c->rd.size());
+}
+
+// emulates run_rk_build with the same grid/thread decomposition
+void hc_rk_build(HcCtx* c)
+{
+    const Geom& g = c->hg.g;
+    c->R.assign((size_t)g.K1 * g.P * g.ldP, -3.0);
+    CellData cd{c->mom_rk.data(), c->mom_rmk.data(), c->pre.data(), c->sufx.data(), c->rd.data()};
+    const int gx = (g.ldP / 2 + kRkThreads - 1) / kRkThreads, gy = (g.P + kRkRows - 1) / kRkRows;
+    for (int k = 0; k < g.K1; ++k)
+        for (int by = 0; by < gy; ++by)
+            for (int bx = 0; bx < gx; ++bx)
+                for (int tx = 0; tx < kRkThreads; ++tx)
+                    rk_build_thread(g, cd, c->R.data(), bx, by, k, tx);
+}
+
+void hc_get_R(HcCtx* c, double* R) { memcpy(R, c->R.data(), sizeof(double) * c->R.size()); }
+// install an externally computed R (layout [K1][P][ldP]) for stage-C-only checks
+void hc_set_R(HcCtx* c, const double* R)
+{
+    const Geom& g = c->hg.g;
+    c->R.assign(R, R + (size_t)g.K1 * g.P * g.ldP);
+}
+
+int hc_set_one_particle(HcCtx* c, int64_t max_l_1p, const double* H_vec, const double* S)
+{
+    try {
+        const Geom& g = c->hg.g;
+        const size_t per_l = band_doubles(g);
+        c->Hb.assign((size_t)(max_l_1p + 1) * per_l, 0.0);
+        c->Sb.assign(per_l, 0.0);
+        pack_band(g, S, c->Sb.data(), "S");
+        for (int l = 0; l <= max_l_1p; ++l)
+            pack_band(g, H_vec + (size_t)l * g.nb * g.nb * 2, c->Hb.data() + l * per_l, "H_vec");
+        c->lmax_1p = (int)max_l_1p;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// emulates block_plan (count kernel + scan) for rows row_lo..row_hi
+int hc_block_count(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
+                   const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
+                   int64_t* H_ptr, int64_t* S_ptr)
+{
+    try {
+        HostPlan hp = build_host_plan(c->hg.g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
+        const Plan pl = hp.view();
+        long long accH = 1, accS = 1;
+        for (long long i = row_lo; i <= row_hi; ++i) {
+            long long h, s;
+            row_count(c->hg.g, pl, (int)i, &h, &s);
+            H_ptr[i - row_lo] = accH;
+            S_ptr[i - row_lo] = accS;
+            accH += h;
+            accS += s;
+        }
+        H_ptr[row_hi - row_lo + 1] = accH;
+        S_ptr[row_hi - row_lo + 1] = accS;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// emulates block_fill_kernel: one "warp" per row, 32 lanes, ballot emulated
+int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
+                  const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
+                  const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
+                  int64_t* S_idx, double* S_dat)
+{
+    try {
+        const Geom& g = c->hg.g;
+        HostPlan hp = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
+        if (hp.lmax > c->lmax_1p) throw std::invalid_argument("l exceeds max_l_1p");
+        const Plan pl = hp.view();
+        const OneBody ob{c->Hb.data(), c->Sb.data()};
+        const double* R = c->R.data();
+        for (long long i = row_lo; i <= row_hi; ++i) {
+            const RowInfo r = row_info(pl, (int)i);
+            long long hpos = H_ptr[i - row_lo] - 1, spos = S_ptr[i - row_lo] - 1;
+            for_each_chunk(g, pl, r, [&](int bj, int nc, const Segment& s, const Coupling& cp, int base, int hi) {
+                bool storeS[32];
+                Element el[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int nd = base + lane;
+                    const bool act = nd <= hi;
+                    storeS[lane] = false;
+                    if (act) {
+                        const bool sup = nd >= s.dlo && nd <= s.dhi;
+                        const bool sup_ex = nd >= s.xlo && nd <= s.xhi;
+                        el[lane] = element_value(g, pl, ob, R, r, cp, bj, nc, nd, sup, sup_ex);
+                        storeS[lane] = el[lane].storeS;
+                        H_idx[hpos + lane] = (long long)s.jbase + nd;
+                        H_dat[2 * (hpos + lane)] = el[lane].H.re;
+                        H_dat[2 * (hpos + lane) + 1] = el[lane].H.im;
+                    }
+                }
+                hpos += imin(32, hi - base + 1);
+                int cnt = 0;
+                for (int lane = 0; lane < 32; ++lane)
+                    if (storeS[lane]) {
+                        const long long pos = spos + cnt++;
+                        S_idx[pos] = (long long)s.jbase + base + lane;
+                        S_dat[2 * pos] = el[lane].S.re;
+                        S_dat[2 * pos + 1] = el[lane].S.im;
+                    }
+                spos += cnt;
+            });
+            if (hpos != H_ptr[i - row_lo + 1] - 1 || spos != S_ptr[i - row_lo + 1] - 1)
+                throw std::logic_error("fill wrote a different number of entries than counted, row " +
+                                       std::to_string(i));
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+}  // extern "C"
