@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "b-spline-two-e_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+# Small deterministic basis_input namelists (the namelist is the seed; the
+# reference has no random inputs).  Chosen to hit the edge cases of the path:
+# radial truncation of the second electron (r_2_max), the large-r angular
+# hole (r_all_l / max_l2), odd and even L, z_pol on and off, full on and off.
+SMALL_CASES = {
+    "tiny_k4": dict(k=4, m=2, Z=1, h_max=1.0, r_max=6.0, k_GL=8, max_k=2, max_L=1, max_l_1p=1,
+                    max_l2=1, CAP_eta=0j, CAP_r_0=4.0, full=True, z_pol=True),
+    "trunc_k5": dict(k=5, m=2, Z=2, h_max=1.0, r_max=8.0, k_GL=9, max_k=3, max_L=2, max_l_1p=2,
+                     max_l2=1, r_2_max=5.0, r_all_l=6.0, CAP_eta=5e-3 + 0j, CAP_r_0=5.0,
+                     full=False, z_pol=False),
+    "wide_k6": dict(k=6, m=3, Z=2, h_max=0.8, r_max=10.0, k_GL=12, max_k=5, max_L=3, max_l_1p=3,
+                    max_l2=3, r_2_max=6.0, CAP_eta=1e-3 + 0j, CAP_r_0=7.0, full=False, z_pol=True),
+}
+
+
+@pytest.fixture(scope="session")
+def small_cases():
+    return SMALL_CASES

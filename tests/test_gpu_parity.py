@@ -1,0 +1,241 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI.
+
+Tolerance (north_star): relative 1e-12 on R^k and on H/S entries, sparsity
+pattern and indices exact.  R^k and the cell integrals are sums of
+non-negative terms, so 1e-12 is a plain relative bound there; H entries mix
+signs and are compared against max(|entry|, largest entry of the row)."""
+import numpy as np
+import pytest
+
+import bs2e
+from oracle import bs2e_oracle as O
+from parity_utils import REL_TOL, assert_csr_equal, assert_rel
+from conftest import SMALL_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(params, blocks=True):
+    run = O.OracleRun(**params)
+    run.slater(); run.rk_map()
+    if blocks:
+        run.one_particle(); run.basis()
+    return run
+
+
+def _ctx(run):
+    # same Gauss-Legendre nodes on both sides, as in the Fortran integration
+    # where the caller hands the library the rule it integrates with
+    glx, glw = O.gauss_legendre(run.p["k_GL"])
+    return bs2e.Context(run.p["k"], run.grid, run.p["max_k"], run.p["k_GL"], glx, glw)
+
+
+@pytest.fixture(scope="module", params=list(SMALL_CASES))
+def case(request):
+    run = _oracle(SMALL_CASES[request.param])
+    ctx = _ctx(run)
+    ctx.slater_cells()
+    ctx.rk_build()
+    ctx.set_one_particle(run.H_vec, run.S)
+    yield run, ctx
+    ctx.close()
+
+
+def test_sizes(case):
+    run, ctx = case
+    assert (ctx.n_b, ctx.cells, ctx.P) == (run.bs.n_b, run.bs.cells, run.bs.num_pairs())
+    assert (ctx.nnz_4d, ctx.nnz_6d) == (run.s4.nnz, run.s6.nnz)
+
+
+def test_stage_A_in_reference_entry_order(case):
+    run, ctx = case
+    rk, rmk, iv, i, j = ctx.get_r_k()
+    s4 = run.s4
+    assert np.array_equal(iv, s4.iv) and np.array_equal(i, s4.i) and np.array_equal(j, s4.j)
+    assert_rel(rk, s4.r_k, what="r_k")
+    assert_rel(rmk, s4.r_m_k, what="r_m_k")
+    d, iv, i, j, ip, jp = ctx.get_r_d_k()
+    s6 = run.s6
+    for a, b in ((iv, s6.iv), (i, s6.i), (j, s6.j), (ip, s6.i_p), (jp, s6.j_p)):
+        assert np.array_equal(a, b)
+    assert_rel(d, s6.data, what="r_d_k")
+
+
+def test_stage_B_Rk_planes_and_get_val(case):
+    run, ctx = case
+    for k in range(run.p["max_k"] + 1):
+        assert_rel(ctx.rk_plane(k), run.R[:, :, k], what=f"R^{k}")
+    rng = np.random.default_rng(5)
+    nb, w = ctx.n_b, ctx.k - 1
+    keys = []
+    for _ in range(500):
+        a = int(rng.integers(1, nb + 1)); c = int(rng.integers(max(1, a - w), min(nb, a + w) + 1))
+        b = int(rng.integers(1, nb + 1)); d = int(rng.integers(max(1, b - w), min(nb, b + w) + 1))
+        keys.append((a, b, c, d))
+    vals = ctx.rk_get(keys)
+    ref = np.array([O.R_get_val(run.bs, run.p["max_k"], run.R, *q) for q in keys])
+    assert_rel(vals, ref, what="rk_get")
+    with pytest.raises(bs2e.Bs2eError):       # Nd_DOK%get_val on a missing key is an error
+        ctx.rk_get([(1, 1, 1 + ctx.k, 1)])
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_stage_C_blocks(case, full):
+    run, ctx = case
+    run.p["full"] = full
+    for s in run.syms:
+        if s.n_config == 0:
+            continue
+        nnz = O.count_nnz(run.bs.k, s, run.p["max_k"], full)
+        H, S, emitted = run.block(s, nnz=nnz)
+        assert emitted == nnz
+        assert ctx.block_count(s, full) == nnz
+        Hg, Sg = ctx.block_fill(s, full, nnz)
+        assert_csr_equal(Hg, H, what=f"H L={s.l} pi={s.pi} full={full}")
+        assert_csr_equal(Sg, S, what=f"S L={s.l} pi={s.pi} full={full}")
+
+
+def test_row_range_fragments_and_checksum(case):
+    run, ctx = case
+    s = max(run.syms, key=lambda q: q.n_config)
+    n = s.n_config
+    whole = ctx.block_plan(s, False)
+    whole.assemble()
+    H, S = whole.download()
+    cH, cS = whole.row_counts()
+    assert np.array_equal(np.cumsum(cH) + 1, H.index_ptr[1:])
+    cut = n // 2
+    a = ctx.block_plan(s, False, rows=(1, cut)); a.assemble()
+    b = ctx.block_plan(s, False, rows=(cut + 1, n)); b.assemble()
+    Ha, Sa = a.download(); Hb, Sb = b.download()
+    assert np.array_equal(np.concatenate([Ha.indices, Hb.indices]), H.indices)
+    assert np.array_equal(np.concatenate([Ha.data, Hb.data]), H.data)        # bit-identical
+    assert np.array_equal(np.concatenate([Sa.data, Sb.data]), S.data)
+    assert np.array_equal(np.concatenate([Ha.index_ptr[:-1], Hb.index_ptr + Ha.index_ptr[-1] - 1]), H.index_ptr)
+    c1, c2 = whole.checksum(), whole.checksum()
+    assert c1 == c2 and c1[0] != 0
+    for blk in (whole, a, b):
+        blk.free()
+
+
+def test_errors_are_reported(case):
+    run, ctx = case
+    s = run.syms[0]
+    bad = bs2e.Sym(s.l, s.m, s.pi, s.conf_n.copy(), s.conf_l.copy(), s.conf_eqv)
+    bad.conf_n[0, 0] = ctx.n_b + 5
+    with pytest.raises(bs2e.Bs2eError):
+        ctx.block_count(bad, False)
+    fresh = _ctx(run)
+    with pytest.raises(bs2e.Bs2eError):      # stage B before stage A
+        fresh.rk_build()
+    fresh.close()
+
+
+def test_reference_test_grid_full(tmp_path):
+    """grid of the reference's tests/test_mat_els.f90 (k=8, n_b=46, max_k=4), L=0 and L=1 blocks"""
+    run = _oracle(dict(k=8, m=3, Z=2, h_max=1.5, r_max=15.0, k_GL=14, max_k=4, max_L=1,
+                       max_l_1p=2, max_l2=2, CAP_eta=5e-3 + 0j, CAP_r_0=10.0, full=False, z_pol=True))
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    for k in range(5):
+        assert_rel(ctx.rk_plane(k), run.R[:, :, k], what=f"R^{k}")
+    for s in run.syms:
+        nnz = O.count_nnz(8, s, 4, False)
+        H, S, _ = run.block(s, nnz=nnz)
+        Hg, Sg = ctx.construct_block_tensor(s, False)
+        assert_csr_equal(Hg, H, what=f"H L={s.l}")
+        assert_csr_equal(Sg, S, what=f"S L={s.l}")
+    ctx.close()
+
+
+def test_product_host_inputs_end_to_end():
+    """the product's own host inputs (csrc/host.cpp) through BasisSetup.run()"""
+    p = SMALL_CASES["trunc_k5"]
+    run = _oracle(p)
+    setup = bs2e.BasisSetup(**p)
+    H_diag, S_diag = setup.run()
+    for s, Hg, Sg in zip(run.syms, H_diag, S_diag):
+        H, S, _ = run.block(s)
+        # product GL nodes / one-particle matrices differ from the oracle's by rounding
+        assert_csr_equal(Hg, H, scale_tol=5e-12, what=f"H L={s.l}")
+        assert_csr_equal(Sg, S, scale_tol=5e-12, what=f"S L={s.l}")
+    setup.ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 1 at full size: size-independent properties + sampled rows
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cfg1():
+    p = bs2e.CONFIGS["cfg1"]
+    run = O.OracleRun(**p)
+    run.slater(); run.rk_map(); run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    yield run, ctx
+    ctx.close()
+
+
+def test_cfg1_Rk_full_tensor(cfg1):
+    run, ctx = cfg1
+    assert ctx.P == 1384 and ctx.nnz_4d == 5794 and ctx.nnz_6d == 369346
+    for k in range(5):
+        Rg = ctx.rk_plane(k)
+        assert Rg.min() >= 0.0
+        assert np.max(np.abs(Rg - Rg.T)) <= 1e-13 * Rg.max()      # R^k(ab;cd) = R^k(ba;dc)
+        assert_rel(Rg, run.R[:, :, k], what=f"cfg1 R^{k}")
+
+
+def test_cfg1_blocks_properties_and_sampled_rows(cfg1):
+    run, ctx = cfg1
+    by_Lpi = {}
+    for s in run.syms:
+        blk = ctx.block_plan(s, False)
+        blk.assemble()
+        H, S = blk.download()
+        n = s.n_config
+        # CSR contract of the consumers (PARDISO mtype 6): sorted, diagonal first, S subset of H
+        for M in (H, S):
+            assert M.index_ptr[0] == 1 and M.index_ptr[-1] - 1 == M.nnz
+            assert np.array_equal(M.indices[M.index_ptr[:-1] - 1], np.arange(1, n + 1))
+            rows = np.repeat(np.arange(n), np.diff(M.index_ptr))
+            assert np.all((np.diff(M.indices) > 0) | (np.diff(rows) > 0))
+        keyH = (np.repeat(np.arange(n), np.diff(H.index_ptr)).astype(np.int64) << 32) | H.indices
+        keyS = (np.repeat(np.arange(n), np.diff(S.index_ptr)).astype(np.int64) << 32) | S.indices
+        assert np.all(np.isin(keyS, keyH))
+        # blocks that differ only in M are identical (H,S do not depend on M)
+        prev = by_Lpi.setdefault((s.l, s.pi), (H, S))
+        if prev[0] is not H:
+            assert np.array_equal(prev[0].indices, H.indices) and np.array_equal(prev[0].data, H.data)
+            assert np.array_equal(prev[1].data, S.data)
+        # sampled row ranges against the oracle (the full O(n^2) scan is the reference's cost)
+        if prev[0] is H:
+            for lo in (1, n // 2, n - 39):
+                hi = lo + 39
+                cap = (int(H.index_ptr[hi] - H.index_ptr[lo - 1]), int(S.index_ptr[hi] - S.index_ptr[lo - 1]))
+                Ho, So, em = run.block(s, rows=(lo, hi), nnz=cap)
+                assert em == cap
+                a, b = H.index_ptr[lo - 1] - 1, H.index_ptr[hi] - 1
+                frag = O.CSR(None, cap[0], H.index_ptr[lo - 1:hi + 1] - a, H.indices[a:b], H.data[a:b])
+                ref = O.CSR(None, cap[0], Ho.index_ptr[lo - 1:hi + 1], Ho.indices, Ho.data)
+                assert_csr_equal(frag, ref, what=f"cfg1 H rows {lo}-{hi} L={s.l}")
+                a, b = S.index_ptr[lo - 1] - 1, S.index_ptr[hi] - 1
+                frag = O.CSR(None, cap[1], S.index_ptr[lo - 1:hi + 1] - a, S.indices[a:b], S.data[a:b])
+                ref = O.CSR(None, cap[1], So.index_ptr[lo - 1:hi + 1], So.indices, So.data)
+                assert_csr_equal(frag, ref, what=f"cfg1 S rows {lo}-{hi} L={s.l}")
+        blk.free()
+
+
+def test_cfg1_full_true_upper_triangle_matches(cfg1):
+    run, ctx = cfg1
+    s = run.syms[1]   # L=1 even parity, the smallest block with l-changing couplings
+    up = ctx.block_plan(s, False); up.assemble(); Hu, Su = up.download(); up.free()
+    fl = ctx.block_plan(s, True); fl.assemble(); Hf, Sf = fl.download(); fl.free()
+    n = s.n_config
+    rows = np.repeat(np.arange(1, n + 1), np.diff(Hf.index_ptr))
+    keep = Hf.indices >= rows
+    assert np.array_equal(Hf.indices[keep], Hu.indices)
+    assert np.array_equal(Hf.data[keep], Hu.data)
+    rows = np.repeat(np.arange(1, n + 1), np.diff(Sf.index_ptr))
+    keep = Sf.indices >= rows
+    assert np.array_equal(Sf.data[keep], Su.data)
