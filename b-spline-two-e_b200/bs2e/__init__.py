@@ -51,6 +51,7 @@ ABI = {
     "bs2e_block_plan": (C.c_int, [vp, i64, i64, _pi, _pi, i64, i64, i64, C.POINTER(vp)]),
     "bs2e_block_nnz": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "bs2e_block_row_counts": (C.c_int, [vp, vp, vp]),
+    "bs2e_block_recount": (C.c_int, [vp]),
     "bs2e_block_assemble": (C.c_int, [vp]),
     "bs2e_block_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "bs2e_block_checksum": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -228,6 +229,9 @@ class Block:
         cS = np.zeros(self.nrows, np.int64)
         _chk(lib().bs2e_block_row_counts(self.h, _ptr(cH), _ptr(cS)))
         return cH, cS
+
+    def recount(self):
+        _chk(lib().bs2e_block_recount(self.h))
 
     def assemble(self):
         _chk(lib().bs2e_block_assemble(self.h))

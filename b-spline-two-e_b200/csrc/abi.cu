@@ -258,6 +258,15 @@ int bs2e_block_row_counts(bs2e_block* b, int64_t* cnt_H, int64_t* cnt_S)
     });
 }
 
+int bs2e_block_recount(bs2e_block* b)
+{
+    return guarded("bs2e_block_recount", [&] {
+        if (!b) throw Error("null block");
+        use_device(b->ctx);
+        block_count_scan(b, false);
+    });
+}
+
 int bs2e_block_assemble(bs2e_block* b)
 {
     return guarded("bs2e_block_assemble", [&] {

@@ -104,6 +104,35 @@ __global__ void checksum_kernel(long long n, const long long* __restrict__ idx,
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// count pass + exclusive scan -> 1-based index_ptr of the planned rows
+void block_count_scan(bs2e_block* b, bool read_totals)
+{
+    bs2e_ctx* c = b->ctx;
+    cudaStream_t st = c->stream;
+    const long long nrows = b->row_hi - b->row_lo + 1;
+    block_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(
+        c->dg, b->dplan, b->row_lo, nrows, b->d_cntH, b->d_cntS);
+    BS2E_LAUNCHED();
+    size_t tmp = b->scan_tmp_bytes;
+    BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntH, b->d_Hptr, nrows + 1, st));
+    g_launches.fetch_add(2);  // DeviceScanInitKernel + DeviceScanKernel
+    BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntS, b->d_Sptr, nrows + 1, st));
+    g_launches.fetch_add(2);
+    ptr_one_based_kernel<<<(unsigned)((nrows + 1 + 255) / 256), 256, 0, st>>>(nrows + 1, b->d_Hptr,
+                                                                             b->d_Sptr);
+    BS2E_LAUNCHED();
+    if (read_totals) {
+        long long lastH = 0, lastS = 0;
+        BS2E_CUDA(cudaMemcpyAsync(&lastH, b->d_Hptr + nrows, sizeof(long long),
+                                  cudaMemcpyDeviceToHost, st));
+        BS2E_CUDA(cudaMemcpyAsync(&lastS, b->d_Sptr + nrows, sizeof(long long),
+                                  cudaMemcpyDeviceToHost, st));
+        BS2E_CUDA(cudaStreamSynchronize(st));
+        b->nnzH = lastH - 1;
+        b->nnzS = lastS - 1;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // plan: derive the block structure from the configuration list, count, scan
 // ---------------------------------------------------------------------------
@@ -156,28 +185,11 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         b->d_cntS = dev_alloc<long long>(nrows + 1);
         b->d_Hptr = dev_alloc<long long>(nrows + 1);
         b->d_Sptr = dev_alloc<long long>(nrows + 1);
-        block_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(
-            c->dg, pl, row_lo, nrows, b->d_cntH, b->d_cntS);
-        BS2E_LAUNCHED();
         size_t tmp = 0;
         BS2E_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b->d_cntH, b->d_Hptr, nrows + 1, st));
         b->scan_tmp_bytes = tmp;
         BS2E_CUDA(cudaMalloc(&b->d_scan_tmp, tmp ? tmp : 1));
-        BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntH, b->d_Hptr, nrows + 1, st));
-        g_launches.fetch_add(1);
-        BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntS, b->d_Sptr, nrows + 1, st));
-        g_launches.fetch_add(1);
-        ptr_one_based_kernel<<<(unsigned)((nrows + 1 + 255) / 256), 256, 0, st>>>(
-            nrows + 1, b->d_Hptr, b->d_Sptr);
-        BS2E_LAUNCHED();
-        long long lastH = 0, lastS = 0;
-        BS2E_CUDA(cudaMemcpyAsync(&lastH, b->d_Hptr + nrows, sizeof(long long),
-                                  cudaMemcpyDeviceToHost, st));
-        BS2E_CUDA(cudaMemcpyAsync(&lastS, b->d_Sptr + nrows, sizeof(long long),
-                                  cudaMemcpyDeviceToHost, st));
-        BS2E_CUDA(cudaStreamSynchronize(st));
-        b->nnzH = lastH - 1;
-        b->nnzS = lastS - 1;
+        block_count_scan(b, true);
     } catch (...) {
         block_free(b);
         throw;

@@ -124,6 +124,7 @@ void fetch_rk_plane(bs2e_ctx* c, int k, double* out);
 
 bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
                        const int64_t* conf_l, int full, long long row_lo, long long row_hi);
+void block_count_scan(bs2e_block* b, bool read_totals);
 void block_assemble(bs2e_block* b);
 void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat, int64_t* S_ptr,
                     int64_t* S_idx, double* S_dat);

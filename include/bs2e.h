@@ -113,6 +113,10 @@ int bs2e_block_plan(bs2e_ctx *ctx, int64_t L, int64_t n_config,
 int bs2e_block_nnz(bs2e_block *blk, int64_t *nnz_H, int64_t *nnz_S);
 /* per-row entry counts of the planned rows (row_hi-row_lo+1 values each) */
 int bs2e_block_row_counts(bs2e_block *blk, int64_t *cnt_H, int64_t *cnt_S);
+/* Repeat the count pass + scan of an existing plan with everything already
+ * resident on the device (no host synchronisation); used for device-timed
+ * benchmarking of the count stage. */
+int bs2e_block_recount(bs2e_block *blk);
 int bs2e_block_assemble(bs2e_block *blk);
 int bs2e_block_download(bs2e_block *blk, int64_t *H_ptr, int64_t *H_idx, double *H_dat,
                         int64_t *S_ptr, int64_t *S_idx, double *S_dat);

@@ -594,6 +594,53 @@ void orc_setup_Slater_diag(const orc_bspline *bs, int64_t max_k, int64_t k_GL,
     free(ptr0); free(x); free(w); free(Bout); free(Bin);
 }
 
+/* Timing helper for the CPU baseline: the reference-faithful evaluation
+ * (de Boor call per point, threads over k only) of setup_Slater_diag for every
+ * jp_step-th value of the outermost index j_b_p.  Returns a checksum so the
+ * work cannot be optimised away; *entries receives the number of (entry,k)
+ * values computed.                                                          */
+double orc_time_Slater_diag_sample(const orc_bspline *bs, int64_t max_k, int64_t k_GL,
+                                   int64_t jp_step, int64_t *entries)
+{
+    const int64_t nb = bs->n_b, cells = bs->nbp - 1, ks = bs->k;
+    double *x = (double *)malloc(sizeof(double) * (size_t)k_GL);
+    double *w = (double *)malloc(sizeof(double) * (size_t)k_GL);
+    orc_gauss_legendre(k_GL, -1.0, 1.0, x, w);
+    diag_ctx ctx = { bs, k_GL, x, w, NULL, NULL };
+    double total = 0.0;
+    int64_t count = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total, count)
+    for (int64_t k = 0; k <= max_k; ++k) {
+        double *cw = (double *)calloc((size_t)bs->n, sizeof(double));
+        int64_t idx[4];
+        for (int64_t j_b_p = 1; j_b_p <= nb; j_b_p += jp_step) {
+            idx[3] = j_b_p;
+            for (int64_t j_b = 1; j_b <= nb; ++j_b) {
+                if (iabs64(j_b - j_b_p) >= ks) continue;
+                idx[2] = j_b;
+                for (int64_t i_b_p = 1; i_b_p <= nb; ++i_b_p) {
+                    idx[1] = i_b_p;
+                    for (int64_t i_b = 1; i_b <= nb; ++i_b) {
+                        idx[0] = i_b;
+                        if (iabs64(i_b - i_b_p) >= ks) continue;
+                        for (int64_t i_r = 1; i_r <= cells; ++i_r) {
+                            int i_sup = support(bs, i_r, i_b + 1) && support(bs, i_r, i_b_p + 1);
+                            int j_sup = support(bs, i_r, j_b + 1) && support(bs, i_r, j_b_p + 1);
+                            if (!(i_sup && j_sup)) continue;
+                            total += diag_entry(&ctx, cw, i_r, idx, k);
+                            count++;
+                        }
+                    }
+                }
+            }
+        }
+        free(cw);
+    }
+    free(x); free(w);
+    *entries = count;
+    return total;
+}
+
 /* ======================================================================== */
 /* sparse_array_tools.f90:452-493 compute_R_K_map  (+ :495-555 Nd_DOK)       */
 /* ======================================================================== */
@@ -925,14 +972,28 @@ static int64_t conf_lmax(int64_t n_config, const int64_t *conf_l)
 /* ======================================================================== */
 /* hamiltonian.f90:348-416  count_nnz                                        */
 /* ======================================================================== */
+void orc_count_nnz_rows(int64_t k_spline, int64_t term_l, int64_t n_config,
+                        const int64_t *conf_n, const int64_t *conf_l,
+                        int64_t max_k, int64_t full, int64_t row_lo, int64_t row_hi,
+                        int64_t *res);
+
 void orc_count_nnz(int64_t k_spline, int64_t term_l, int64_t n_config,
                    const int64_t *conf_n, const int64_t *conf_l,
                    int64_t max_k, int64_t full, int64_t *res)
 {
+    orc_count_nnz_rows(k_spline, term_l, n_config, conf_n, conf_l, max_k, full, 1, n_config, res);
+}
+
+/* the same scan restricted to outer rows row_lo..row_hi (sampled timing) */
+void orc_count_nnz_rows(int64_t k_spline, int64_t term_l, int64_t n_config,
+                        const int64_t *conf_n, const int64_t *conf_l,
+                        int64_t max_k, int64_t full, int64_t row_lo, int64_t row_hi,
+                        int64_t *res)
+{
     ang_memo memo;
     memo_init(&memo, conf_lmax(n_config, conf_l), max_k, term_l);
     res[0] = 0; res[1] = 0;
-    for (int64_t i = 1; i <= n_config; ++i) {
+    for (int64_t i = row_lo; i <= row_hi; ++i) {
         int64_t n_a = conf_n[2 * (i - 1)], n_b = conf_n[2 * (i - 1) + 1];
         int64_t l_a = conf_l[2 * (i - 1)], l_b = conf_l[2 * (i - 1) + 1];
         for (int64_t j = (full ? 1 : i); j <= n_config; ++j) {

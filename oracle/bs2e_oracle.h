@@ -82,6 +82,11 @@ void orc_setup_Slater_diag(const orc_bspline *bs, int64_t max_k, int64_t k_GL,
                            int64_t *i_p, int64_t *j_p,
                            int64_t tabulate, int64_t par_mode);
 
+/* CPU-baseline timing helper: reference-faithful setup_Slater_diag on every
+ * jp_step-th outermost index; returns a checksum, *entries = values computed */
+double orc_time_Slater_diag_sample(const orc_bspline *bs, int64_t max_k, int64_t k_GL,
+                                   int64_t jp_step, int64_t *entries);
+
 /* ---- sparse_array_tools.f90:452-555 : Nd_DOK replaced by a dense table --- */
 /* R is stored as R[(p1*P + p2)*(max_k+1) + k] with p = orc_pair_index(a,c).
  * Accumulation order is the reference's loop order, so sums are bit-equal to
@@ -120,6 +125,10 @@ int64_t orc_init_basis_syms(int64_t max_L, int64_t z_pol,
 void orc_count_nnz(int64_t k_spline, int64_t term_l, int64_t n_config,
                    const int64_t *conf_n, const int64_t *conf_l,
                    int64_t max_k, int64_t full, int64_t *nnz /*2*/);
+void orc_count_nnz_rows(int64_t k_spline, int64_t term_l, int64_t n_config,
+                        const int64_t *conf_n, const int64_t *conf_l,
+                        int64_t max_k, int64_t full, int64_t row_lo, int64_t row_hi,
+                        int64_t *nnz /*2*/);
 
 /* ---- hamiltonian.f90:106-283 + mat_els.f90:552-571,608-633,664-715 ------- */
 /* Fills CSR arrays sized from cap_H/cap_S.  Returns 0 on success; -1 if the

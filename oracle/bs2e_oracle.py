@@ -62,6 +62,7 @@ def lib():
         "orc_pair_index": (i64, [vp, i64, i64]),
         "orc_setup_Slater_off_diag": (None, [vp, i64, i64, _pd, _pd, _pi, _pi, _pi]),
         "orc_setup_Slater_diag": (None, [vp, i64, i64, _pd, _pi, _pi, _pi, _pi, _pi, i64, i64]),
+        "orc_time_Slater_diag_sample": (f64, [vp, i64, i64, i64, C.POINTER(i64)]),
         "orc_compute_R_k_map": (None, [vp, i64, i64, _pd, _pd, _pi, _pi, _pi,
                                        i64, _pd, _pi, _pi, _pi, _pi, _pd]),
         "orc_R_get_val": (C.c_int, [vp, i64, _pd, i64, i64, i64, i64, _pd]),
@@ -72,6 +73,7 @@ def lib():
         "orc_count_configs": (i64, [i64] * 8 + [_pi, _pi, _pi, i64]),
         "orc_init_basis_syms": (i64, [i64, i64, _pi, _pi, _pi]),
         "orc_count_nnz": (None, [i64, i64, i64, _pi, _pi, i64, i64, _pi]),
+        "orc_count_nnz_rows": (None, [i64, i64, i64, _pi, _pi, i64, i64, i64, i64, _pi]),
         "orc_construct_block_tensor": (C.c_int, [vp, i64, _pd, _pd, i64, i64, _pi, _pi,
                                                  i64, _pd, i64, i64, i64,
                                                  i64, _pi, _pi, _pd,
@@ -203,6 +205,12 @@ def setup_Slater_diag(bs: BSpline, max_k, k_GL, tabulate=1, par_mode=1) -> Spars
     return Sparse6d(nnz, d.reshape(nnz, max_k + 1, order="F"), iv, i, j, ip, jp)
 
 
+def time_Slater_diag_sample(bs: BSpline, max_k, k_GL, jp_step):
+    n = i64()
+    chk = lib().orc_time_Slater_diag_sample(bs._h, max_k, k_GL, jp_step, C.byref(n))
+    return chk, int(n.value)
+
+
 def compute_R_k_map(bs: BSpline, max_k, s4: Sparse4d, s6: Sparse6d):
     """Returns R as an array [P, P, max_k+1] (p1 = pair(a,c), p2 = pair(b,d))."""
     P = bs.num_pairs()
@@ -263,11 +271,13 @@ def init_basis(max_L, max_l_1p, n_b, k_spline, max_n_b, n_all_l, l_2_max, z_pol)
     return syms
 
 
-def count_nnz(k_spline, sym: Sym, max_k, full):
+def count_nnz(k_spline, sym: Sym, max_k, full, rows=None):
     res = np.zeros(2, np.int64)
-    lib().orc_count_nnz(k_spline, sym.l, sym.n_config,
-                        np.ascontiguousarray(sym.conf_n.reshape(-1)),
-                        np.ascontiguousarray(sym.conf_l.reshape(-1)), max_k, int(bool(full)), res)
+    lo, hi = (1, sym.n_config) if rows is None else rows
+    lib().orc_count_nnz_rows(k_spline, sym.l, sym.n_config,
+                             np.ascontiguousarray(sym.conf_n.reshape(-1)),
+                             np.ascontiguousarray(sym.conf_l.reshape(-1)), max_k, int(bool(full)),
+                             lo, hi, res)
     return int(res[0]), int(res[1])
 
 
