@@ -17,6 +17,8 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <set>
@@ -24,6 +26,7 @@
 
 #include "ctx.h"
 #include "plan.h"
+#include "site_core.h"
 
 namespace bs2e {
 
@@ -87,6 +90,222 @@ block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, lon
         }
         spos += __popc(m);
     });
+}
+
+// ---------------------------------------------------------------------------
+// site-centric fill: one CTA per radial site (n_a,n_b), see site_core.h.
+//   phase 1  per column block bj and n_c slot: clipped windows T[bj][q];
+//            R^k values of both windows -> shared memory, Rv[k][slot]
+//   phase 2  per (bj, storage mode): prefix over the n_c slots of the number of
+//            stored entries, hp[bj][mode][q] (mode: D, X, D+X, diagonal pair)
+//   phase 3  per row of the site: offsets of its column blocks inside the row
+//   phase 4  warps grab (row, column block) pairs from a shared counter and
+//            walk the OUTPUT positions of the pair 32 at a time (all lanes
+//            busy): n_c slot by binary search in hp, n_d by interval
+//            arithmetic, sum_k ang_k R^k from shared memory, coalesced stores
+// Nothing is computed per pair except the copy of its 2*K1 angular factors.
+// ---------------------------------------------------------------------------
+struct SiteList {
+    const unsigned* key;  // [nsites]  n_a << 16 | n_b
+    const int* ptr;       // [nsites+1] into rows
+    const int* rows;      // 1-based configuration (row) indices, ascending per site
+    int nsites;
+};
+
+struct SiteSmem {   // element counts of the dynamic shared memory carve-up
+    int nsmax;      // slots (stride of Rv over k)
+    int ncmax;      // n_c slots
+    int cap;        // (row, column block) pairs per group
+    size_t bytes;
+};
+
+__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int nw, int cap)
+{
+    const size_t nsmax = (size_t)site_max_slots(g), ncmax = (size_t)site_max_nc(g);
+    size_t b = 0;
+    b += sizeof(double) * nsmax * g.K1;                               // Rv
+    b += sizeof(double) * (size_t)nw * 2 * g.K1;                       // wang
+    b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                     // T
+    b += sizeof(int) * (size_t)cap;                                    // off
+    b += sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1);  // hp
+    b += sizeof(unsigned short) * (size_t)nblk * (ncmax + 1);           // sp
+    return b + 16;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+constexpr int kSiteWarps = 8;
+constexpr int kSiteMinBlocks = 3;
+constexpr size_t kSiteSmemLimit = 200 * 1024;
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, kSiteMinBlocks)
+site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, SiteList sl, SiteSmem lay,
+                 long long row_lo, const long long* __restrict__ Hptr,
+                 const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
+                 double2* __restrict__ Hdat, long long* __restrict__ Sidx,
+                 double2* __restrict__ Sdat)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int K1 = g.K1, nsmax = lay.nsmax, ncmax = lay.ncmax, cap = lay.cap;
+    const int nblk = pl.nblk;
+    double* Rv = reinterpret_cast<double*>(smraw);
+    double* wang_all = Rv + (size_t)nsmax * K1;
+    SiteEntry* T = reinterpret_cast<SiteEntry*>(wang_all + (size_t)NW * 2 * K1);
+    int* off = reinterpret_cast<int*>(T + (size_t)nblk * ncmax);
+    unsigned short* hp = reinterpret_cast<unsigned short*>(off + cap);
+    unsigned short* sp = hp + (size_t)nblk * kModes * (ncmax + 1);
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sidx = blockIdx.x;
+    const unsigned key = sl.key[sidx];
+    const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
+    const int* srows = sl.rows + sl.ptr[sidx];
+    const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
+    const int nnc = s.nnc, top = search_top(nnc);
+
+    // ---- phase 1: clipped windows per column block; stage both R^k windows ----
+    for (int item = tid; item < nblk * nnc; item += NW * 32) {
+        const int bj = item / nnc, q = item - bj * nnc;
+        T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+    }
+    {
+        const int ns = s.nD + s.nX;
+        const size_t plane = (size_t)g.P * g.ldP;
+        for (int slot = tid; slot < ns; slot += NW * 32) {
+            const double* src = R + site_slot_source(g, s, slot);
+            int k = 0;
+            for (; k + 4 <= K1; k += 4) {
+                const double v0 = __ldg(src + (size_t)k * plane);
+                const double v1 = __ldg(src + (size_t)(k + 1) * plane);
+                const double v2 = __ldg(src + (size_t)(k + 2) * plane);
+                const double v3 = __ldg(src + (size_t)(k + 3) * plane);
+                Rv[(size_t)k * nsmax + slot] = v0;
+                Rv[(size_t)(k + 1) * nsmax + slot] = v1;
+                Rv[(size_t)(k + 2) * nsmax + slot] = v2;
+                Rv[(size_t)(k + 3) * nsmax + slot] = v3;
+            }
+            for (; k < K1; ++k) Rv[(size_t)k * nsmax + slot] = __ldg(src + (size_t)k * plane);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode) ----
+    for (int task = warp; task < nblk * kModes; task += NW) {
+        const int bj = task / kModes, mode = task - bj * kModes;
+        const bool useD = mode_useD(mode), useX = mode_useX(mode);
+        const bool diag = mode == kModeDiag;
+        const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
+        unsigned short* hpq = hp + (size_t)task * (ncmax + 1);
+        unsigned short* spq = sp + (size_t)bj * (ncmax + 1);
+        int run = 0, srun = 0;
+        for (int q0 = 0; q0 < nnc; q0 += 32) {
+            const int q = q0 + lane;
+            int ch = 0, cs = 0;
+            if (q < nnc) {
+                SiteEntry e = T[bj * ncmax + q];
+                if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
+                ch = entry_count(e, useD, useX);
+                if (diag) cs = entry_count(e, true, samex);
+            }
+            const int inc = warp_incl_scan(ch, lane);
+            if (q < nnc) hpq[q] = (unsigned short)(run + inc - ch);
+            run += __shfl_sync(0xffffffffu, inc, 31);
+            if (diag) {
+                const int sinc = warp_incl_scan(cs, lane);
+                if (q < nnc) spq[q] = (unsigned short)(srun + sinc - cs);
+                srun += __shfl_sync(0xffffffffu, sinc, 31);
+            }
+        }
+        if (lane == 0) hpq[nnc] = (unsigned short)run;
+    }
+
+    double* wang = wang_all + (size_t)warp * 2 * K1;
+    const int G = cap / nblk;  // rows per group (host guarantees >= 1)
+
+    for (int g0 = 0; g0 < nr; g0 += G) {
+        const int gr = imin(G, nr - g0), npairs = gr * nblk;
+        __syncthreads();  // phase 2 / previous group finished
+        if (tid == 0) s_next = 0;
+        // ---- phase 3: offsets of the column blocks inside each row ----
+        for (int ri = warp; ri < gr; ri += NW) {
+            const RowInfo r = row_info(pl, srows[g0 + ri]);
+            int run = 0;
+            for (int b0 = 0; b0 < nblk; b0 += 32) {
+                const int bj = b0 + lane;
+                int c = 0;
+                if (bj < nblk) {
+                    const int mode = pair_mode(pl, r, bj);
+                    if (mode >= 0) c = hp[((size_t)bj * kModes + mode) * (ncmax + 1) + nnc];
+                }
+                const int inc = warp_incl_scan(c, lane);
+                if (bj < nblk) off[ri * nblk + bj] = run + inc - c;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncthreads();
+        // ---- phase 4: fill ----
+        for (;;) {
+            int p = 0;
+            if (lane == 0) p = atomicAdd(&s_next, 1);
+            p = __shfl_sync(0xffffffffu, p, 0);
+            if (p >= npairs) break;
+            const int ri = p / nblk, bj = p - ri * nblk;
+            const int rowi = srows[g0 + ri];
+            const RowInfo r = row_info(pl, rowi);
+            const int mode = pair_mode(pl, r, bj);
+            if (mode < 0) continue;
+            const unsigned short* hpq = hp + ((size_t)bj * kModes + mode) * (ncmax + 1);
+            const int total = hpq[nnc];
+            if (total == 0) continue;
+            const Coupling c = coupling(pl, r, bj);
+            const bool useD = mode_useD(mode), useX = mode_useX(mode);
+            const bool diag = mode == kModeDiag, cut = diag && !pl.full;
+            const size_t cpl = (size_t)r.bi * nblk + bj;
+            __syncwarp();
+            for (int k = lane; k < K1; k += 32) {
+                wang[k] = pl.angD[cpl * K1 + k];
+                wang[K1 + k] = pl.angX[cpl * K1 + k];
+            }
+            __syncwarp();
+            const KRange kr = pl.krange[cpl];
+            const long long wrow = (long long)rowi - row_lo;
+            const long long hbase = Hptr[wrow] - 1 + off[p];
+            const long long sbase = Sptr[wrow] - 1;
+            const SiteEntry* Tb = T + bj * ncmax;
+            const unsigned short* spq = sp + (size_t)bj * (ncmax + 1);
+            for (int o = lane; o < total; o += 32) {
+                const int q = prefix_search(hpq, nnc, top, o);
+                const int nc = site_nc(s, q);
+                SiteEntry e = Tb[q];
+                if (cut) e = entry_cut(e, s, nc);
+                const int nd = entry_nd(e, useD, useX, o - (int)hpq[q]);
+                const bool sup = nd >= (int)e.dlo && nd <= (int)e.dhi;
+                const bool sup_ex = nd >= (int)e.xlo && nd <= (int)e.xhi;
+                const Element el = element_value_at(
+                    g, pl, ob, Rv + (sup ? site_slotD(s, nc, nd) : 0), (size_t)nsmax,
+                    Rv + (sup_ex ? site_slotX(s, nc, nd) : 0), (size_t)nsmax, wang, wang + K1, kr, r, c,
+                    bj, nc, nd, sup, sup_ex);
+                const long long j = (long long)e.jbase + nd;
+                Hidx[hbase + o] = j;
+                Hdat[hbase + o] = make_double2(el.H.re, el.H.im);
+                if (el.storeS) {
+                    const long long pos =
+                        sbase + spq[q] + union_below(true, e.dlo, e.dhi, c.samex, e.xlo, e.xhi, nd);
+                    Sidx[pos] = j;
+                    Sdat[pos] = make_double2(el.S.re, el.S.im);
+                }
+            }
+        }
+    }
 }
 
 __global__ void checksum_kernel(long long n, const long long* __restrict__ idx,
@@ -165,6 +384,12 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         b->d_row_n1 = dev_upload(hp.row_n1, st);
         b->d_row_n2 = dev_upload(hp.row_n2, st);
         b->d_row_blk = dev_upload(hp.row_blk, st);
+        b->nsites = (int)hp.site_key.size();
+        if (b->nsites > 0) {
+            b->d_site_key = dev_upload(hp.site_key, st);
+            b->d_site_ptr = dev_upload(hp.site_ptr, st);
+            b->d_site_rows = dev_upload(hp.site_rows, st);
+        }
         Plan& pl = b->dplan;
         pl.nblk = nblk;
         pl.n_config = (int)n_config;
@@ -210,11 +435,39 @@ void block_assemble(bs2e_block* b)
         b->d_Sdat = dev_alloc<double>(2 * (size_t)b->nnzS);
     }
     const long long nrows = b->row_hi - b->row_lo + 1;
-    block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,
-                        c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, b->row_lo, nrows,
-                                     b->d_Hptr, b->d_Sptr, b->d_Hidx,
-                                     reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx,
-                                     reinterpret_cast<double2*>(b->d_Sdat));
+    // site kernel unless its shared-memory windows do not fit (large k_s * max_k)
+    // or BS2E_FILL=row asks for the row kernel (kept for A/B measurements)
+    constexpr int NW = kSiteWarps;
+    const Geom& g = c->dg;
+    const char* mode = getenv("BS2E_FILL");
+    bool use_site = b->nsites > 0 && !(mode && strcmp(mode, "row") == 0) && site_max_nc(g) <= 255;
+    SiteSmem lay{};
+    if (use_site) {
+        lay.nsmax = site_max_slots(g);
+        lay.ncmax = site_max_nc(g);
+        const int cap_want = std::max(b->dplan.nblk, std::min(2048, b->dplan.nblk * b->dplan.nblk));
+        lay.cap = cap_want;
+        lay.bytes = site_smem_bytes(g, b->dplan.nblk, NW, lay.cap);
+        if (lay.bytes > kSiteSmemLimit) {  // shrink the pair group before giving up
+            lay.cap = b->dplan.nblk;
+            lay.bytes = site_smem_bytes(g, b->dplan.nblk, NW, lay.cap);
+        }
+        if (lay.bytes > kSiteSmemLimit || 2 * site_max_slots(g) > 65535) use_site = false;
+    }
+    if (use_site) {
+        BS2E_CUDA(cudaFuncSetAttribute(site_fill_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)lay.bytes));
+        const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
+        site_fill_kernel<NW><<<(unsigned)b->nsites, NW * 32, lay.bytes, c->stream>>>(
+            c->dg, b->dplan, c->one_body(), c->d_R, sl, lay, b->row_lo, b->d_Hptr, b->d_Sptr, b->d_Hidx,
+            reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
+    } else {
+        block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,
+                            c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, b->row_lo, nrows,
+                                         b->d_Hptr, b->d_Sptr, b->d_Hidx,
+                                         reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx,
+                                         reinterpret_cast<double2*>(b->d_Sdat));
+    }
     BS2E_LAUNCHED();
     b->assembled = true;
 }
@@ -279,6 +532,7 @@ void block_free(bs2e_block* b)
     cudaFree(b->d_blk); cudaFree(b->d_ncrow); cudaFree(b->d_flags); cudaFree(b->d_krange);
     cudaFree(b->d_angD); cudaFree(b->d_angX);
     cudaFree(b->d_row_n1); cudaFree(b->d_row_n2); cudaFree(b->d_row_blk);
+    cudaFree(b->d_site_key); cudaFree(b->d_site_ptr); cudaFree(b->d_site_rows);
     cudaFree(b->d_cntH); cudaFree(b->d_cntS); cudaFree(b->d_Hptr); cudaFree(b->d_Sptr);
     cudaFree(b->d_Hidx); cudaFree(b->d_Sidx); cudaFree(b->d_Hdat); cudaFree(b->d_Sdat);
     cudaFree(b->d_scan_tmp);

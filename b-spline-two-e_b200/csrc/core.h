@@ -421,32 +421,30 @@ struct Element { Cplx H, S; bool storeS; };
 // value of the (i,j) entry, j = (bj, nc, nd)
 //   mat_els.f90:552-571 r_12_tens, :608-633 c_mat_neq_tens,
 //   :664-678 S_mat_neq, :697-715 H_1p_neq; hamiltonian.f90:183-193
-BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
-                              const double* R, const RowInfo& r, const Coupling& c,
-                              int bj, int nc, int nd, bool sup, bool sup_ex)
+// Rd[k*sd] = R^k(n_a n_b; n_c n_d); Rx[k*sx] = R^k(n_a n_b; n_d n_c), read through the
+// electron-exchange symmetry R^k(ab;dc) = R^k(ba;cd); angD/angX: K1 factors of the (bi,bj)
+// pair (exchange already multiplied by (-1)^(lc+ld+L)).  The pointers may refer to global
+// memory (row kernel) or to the staged site window in shared memory (site kernel).
+BS2E_HD Element element_value_at(const Geom& g, const Plan& pl, const OneBody& ob,
+                                 const double* Rd, size_t sd, const double* Rx, size_t sx,
+                                 const double* angD, const double* angX, KRange kr,
+                                 const RowInfo& r, const Coupling& c, int bj, int nc, int nd,
+                                 bool sup, bool sup_ex)
 {
     Element e;
     e.H = Cplx{0.0, 0.0};
     e.S = Cplx{0.0, 0.0};
     const bool allowed = (sup && c.dirany) || (sup_ex && c.exany);
-    const size_t plane = (size_t)g.P * g.ldP;
-    const size_t cpl = ((size_t)r.bi * pl.nblk + bj);
     if (allowed) {
-        const KRange kr = pl.krange[cpl];
         double res = 0.0;
         if (sup) {  // sum_k ang_k R^k(n_a n_b; n_c n_d)
-            const double* ang = pl.angD + cpl * g.K1;
-            const double* Rp = R + (size_t)pair_index(g, r.na, nc) * g.ldP + pair_index(g, r.nb, nd);
             double acc = 0.0;
-            for (int k = kr.dlo; k <= kr.dhi; k += 2) acc += Rp[k * plane] * ang[k];
+            for (int k = kr.dlo; k <= kr.dhi; k += 2) acc += Rd[k * sd] * angD[k];
             res += acc;
         }
-        if (sup_ex) {  // (-1)^(lc+ld+L) sum_k ang^ex_k R^k(n_a n_b; n_d n_c), read through
-                       // the electron-exchange symmetry R^k(ab;dc) = R^k(ba;cd)
-            const double* ang = pl.angX + cpl * g.K1;
-            const double* Rp = R + (size_t)pair_index(g, r.nb, nc) * g.ldP + pair_index(g, r.na, nd);
+        if (sup_ex) {  // (-1)^(lc+ld+L) sum_k ang^ex_k R^k(n_a n_b; n_d n_c)
             double acc = 0.0;
-            for (int k = kr.xlo; k <= kr.xhi; k += 2) acc += Rp[k * plane] * ang[k];
+            for (int k = kr.xlo; k <= kr.xhi; k += 2) acc += Rx[k * sx] * angX[k];
             res += acc;
         }
         e.H.re = res;
@@ -468,13 +466,28 @@ BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
             Cplx hx = cadd(cmul(band_H(g, ob, r.la, r.na, nd), Sbc),
                            cmul(band_H(g, ob, r.lb, r.nb, nc), Sad));
             h = cadd(h, Cplx{hx.re * sgn, hx.im * sgn});
-            Cplx sx = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
-            s = cadd(s, sx);
+            Cplx sx2 = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
+            s = cadd(s, sx2);
         }
         e.H = cadd(e.H, h);
         e.S = s;
     }
     return e;
+}
+
+// the same with R^k gathered from the global tensor R[k][p1][p2]
+BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
+                              const double* R, const RowInfo& r, const Coupling& c,
+                              int bj, int nc, int nd, bool sup, bool sup_ex)
+{
+    const size_t plane = (size_t)g.P * g.ldP;
+    const size_t cpl = ((size_t)r.bi * pl.nblk + bj);
+    const double* Rd = R;
+    const double* Rx = R;
+    if (sup) Rd = R + (size_t)pair_index(g, r.na, nc) * g.ldP + pair_index(g, r.nb, nd);
+    if (sup_ex) Rx = R + (size_t)pair_index(g, r.nb, nc) * g.ldP + pair_index(g, r.na, nd);
+    return element_value_at(g, pl, ob, Rd, plane, Rx, plane, pl.angD + cpl * g.K1,
+                            pl.angX + cpl * g.K1, pl.krange[cpl], r, c, bj, nc, nd, sup, sup_ex);
 }
 
 }  // namespace bs2e

@@ -128,7 +128,50 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
             krange[o] = kr;
         }
 
+    // rows of the requested range grouped by radial site (counting sort on the
+    // site key, then sites ordered by descending row count so that the heaviest
+    // CTAs of the site kernel start first)
+    std::vector<unsigned> site_key;
+    std::vector<int> site_ptr, site_rows;
+    if ((size_t)stride * stride <= ((size_t)1 << 26)) {  // else: no site list, the row kernel is used
+        const long long nrows = row_hi - row_lo + 1;
+        const size_t nkeys = (size_t)stride * stride;
+        std::vector<int> kcount(nkeys + 1, 0);
+        for (long long i = row_lo - 1; i < row_hi; ++i) ++kcount[(size_t)rn1[i] * stride + rn2[i] + 1];
+        // distinct sites, bucketed by their number of rows
+        std::vector<int> per_n(nblk + 2, 0);
+        for (size_t kq = 0; kq < nkeys; ++kq)
+            if (kcount[kq + 1] > 0) ++per_n[kcount[kq + 1]];
+        std::vector<int> first_of_n(nblk + 2, 0);  // first site index holding n rows
+        int nsites = 0;
+        for (int n = nblk; n >= 1; --n) { first_of_n[n] = nsites; nsites += per_n[n]; }
+        site_key.resize(nsites);
+        site_ptr.assign(nsites + 1, 0);
+        std::vector<int> site_of_key(nkeys, -1);
+        {
+            std::vector<int> fill = first_of_n;
+            for (size_t kq = 0; kq < nkeys; ++kq) {
+                const int n = kcount[kq + 1];
+                if (n <= 0) continue;
+                const int sidx = fill[n]++;
+                site_of_key[kq] = sidx;
+                site_key[sidx] = ((unsigned)(kq / stride) << 16) | (unsigned)(kq % stride);
+                site_ptr[sidx + 1] = n;
+            }
+        }
+        for (int q = 0; q < nsites; ++q) site_ptr[q + 1] += site_ptr[q];
+        site_rows.resize((size_t)nrows);
+        std::vector<int> cursor(site_ptr.begin(), site_ptr.end() - 1);
+        for (long long i = row_lo - 1; i < row_hi; ++i) {
+            const int sidx = site_of_key[(size_t)rn1[i] * stride + rn2[i]];
+            site_rows[cursor[sidx]++] = (int)(i + 1);
+        }
+    }
+
     HostPlan hp;
+    hp.site_key = std::move(site_key);
+    hp.site_ptr = std::move(site_ptr);
+    hp.site_rows = std::move(site_rows);
     hp.nblk = nblk;
     hp.L = L;
     hp.full = full ? 1 : 0;

@@ -16,6 +16,10 @@ struct HostPlan {
     std::vector<KRange> krange;
     std::vector<double> angD, angX;
     std::vector<unsigned short> row_n1, row_n2, row_blk;
+    // rows row_lo..row_hi grouped by radial site (n1,n2), sites with most rows first
+    std::vector<unsigned> site_key;  // n1 << 16 | n2
+    std::vector<int> site_ptr;       // [nsites+1]
+    std::vector<int> site_rows;      // 1-based row indices, ascending inside a site
     Plan view() const;  // Plan over the HOST arrays
 };
 

@@ -11,6 +11,7 @@
 #include "../../b-spline-two-e_b200/csrc/geom_host.h"
 #include "../../b-spline-two-e_b200/csrc/plan.h"
 #include "../../b-spline-two-e_b200/csrc/slater_core.h"
+#include "../../b-spline-two-e_b200/csrc/site_core.h"
 
 using namespace bs2e;
 
@@ -203,6 +204,123 @@ int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                 throw std::logic_error("fill wrote a different number of entries than counted, row " +
                                        std::to_string(i));
         }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// emulates site_fill_kernel phase by phase: one "CTA" per radial site; warp
+// scans become serial prefix sums, everything lane-level comes from site_core.h
+int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
+                 const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
+                 const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
+                 int64_t* S_idx, double* S_dat)
+{
+    try {
+        const Geom& g = c->hg.g;
+        HostPlan hp_ = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
+        if (hp_.lmax > c->lmax_1p) throw std::invalid_argument("l exceeds max_l_1p");
+        if (hp_.site_key.empty()) throw std::logic_error("no site list");
+        const Plan pl = hp_.view();
+        const OneBody ob{c->Hb.data(), c->Sb.data()};
+        const double* R = c->R.data();
+        const int K1 = g.K1, nsmax = site_max_slots(g), ncmax = site_max_nc(g), nblk = pl.nblk;
+        const size_t plane = (size_t)g.P * g.ldP;
+        std::vector<double> Rv((size_t)nsmax * K1);
+        std::vector<SiteEntry> T((size_t)nblk * ncmax);
+        std::vector<unsigned short> hp((size_t)nblk * kModes * (ncmax + 1)), sp((size_t)nblk * (ncmax + 1));
+        std::vector<long long> written_H(row_hi - row_lo + 1, 0), written_S(row_hi - row_lo + 1, 0);
+        const int nsites = (int)hp_.site_key.size();
+        long long rows_seen = 0;
+        for (int sidx = 0; sidx < nsites; ++sidx) {
+            const unsigned key = hp_.site_key[sidx];
+            const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
+            const int nnc = s.nnc, top = search_top(nnc);
+            if (nnc > ncmax || s.nD + s.nX > nsmax) throw std::logic_error("site exceeds smem bounds");
+            // phase 1
+            for (int bj = 0; bj < nblk; ++bj)
+                for (int q = 0; q < nnc; ++q) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+            std::fill(Rv.begin(), Rv.end(), -9.0);
+            for (int slot = 0; slot < s.nD + s.nX; ++slot)
+                for (int k = 0; k < K1; ++k)
+                    Rv[(size_t)k * nsmax + slot] = R[site_slot_source(g, s, slot) + (size_t)k * plane];
+            // phase 2
+            for (int task = 0; task < nblk * kModes; ++task) {
+                const int bj = task / kModes, mode = task - bj * kModes;
+                const bool useD = mode_useD(mode), useX = mode_useX(mode), diag = mode == kModeDiag;
+                const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
+                int run = 0, srun = 0;
+                for (int q = 0; q < nnc; ++q) {
+                    SiteEntry e = T[bj * ncmax + q];
+                    if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
+                    hp[(size_t)task * (ncmax + 1) + q] = (unsigned short)run;
+                    run += entry_count(e, useD, useX);
+                    if (diag) {
+                        sp[(size_t)bj * (ncmax + 1) + q] = (unsigned short)srun;
+                        srun += entry_count(e, true, samex);
+                    }
+                }
+                hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)run;
+            }
+            for (int ri = hp_.site_ptr[sidx]; ri < hp_.site_ptr[sidx + 1]; ++ri) {
+                const int rowi = hp_.site_rows[ri];
+                ++rows_seen;
+                const RowInfo r = row_info(pl, rowi);
+                if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
+                const long long wrow = rowi - row_lo;
+                int offrun = 0;  // phase 3 (running form of the scan over column blocks)
+                for (int bj = 0; bj < nblk; ++bj) {
+                    const int mode = pair_mode(pl, r, bj);
+                    if (mode < 0) continue;
+                    const unsigned short* hpq = hp.data() + ((size_t)bj * kModes + mode) * (ncmax + 1);
+                    const int total = hpq[nnc];
+                    if (total == 0) continue;
+                    // phase 4
+                    const Coupling cp = coupling(pl, r, bj);
+                    const bool useD = mode_useD(mode), useX = mode_useX(mode);
+                    const bool cut = mode == kModeDiag && !pl.full;
+                    const size_t cpl = (size_t)r.bi * nblk + bj;
+                    const long long hbase = H_ptr[wrow] - 1 + offrun, sbase = S_ptr[wrow] - 1;
+                    for (int o = 0; o < total; ++o) {
+                        const int q = prefix_search(hpq, nnc, top, o);
+                        const int nc = site_nc(s, q);
+                        SiteEntry e = T[bj * ncmax + q];
+                        if (cut) e = entry_cut(e, s, nc);
+                        const int nd = entry_nd(e, useD, useX, o - (int)hpq[q]);
+                        const bool sup = nd >= (int)e.dlo && nd <= (int)e.dhi;
+                        const bool sup_ex = nd >= (int)e.xlo && nd <= (int)e.xhi;
+                        if (!sup && !sup_ex) throw std::logic_error("output position maps outside both windows");
+                        const Element el = element_value_at(
+                            g, pl, ob, Rv.data() + (sup ? site_slotD(s, nc, nd) : 0), (size_t)nsmax,
+                            Rv.data() + (sup_ex ? site_slotX(s, nc, nd) : 0), (size_t)nsmax,
+                            pl.angD + cpl * K1, pl.angX + cpl * K1, pl.krange[cpl], r, cp, bj, nc, nd, sup,
+                            sup_ex);
+                        const long long j = (long long)e.jbase + nd;
+                        H_idx[hbase + o] = j;
+                        H_dat[2 * (hbase + o)] = el.H.re;
+                        H_dat[2 * (hbase + o) + 1] = el.H.im;
+                        ++written_H[wrow];
+                        if (el.storeS) {
+                            const long long pos = sbase + sp[(size_t)bj * (ncmax + 1) + q] +
+                                                  union_below(true, e.dlo, e.dhi, cp.samex, e.xlo, e.xhi, nd);
+                            S_idx[pos] = j;
+                            S_dat[2 * pos] = el.S.re;
+                            S_dat[2 * pos + 1] = el.S.im;
+                            ++written_S[wrow];
+                        }
+                    }
+                    offrun += total;
+                }
+                if (offrun != H_ptr[wrow + 1] - H_ptr[wrow])
+                    throw std::logic_error("site fill: row " + std::to_string(rowi) + " counted differently");
+            }
+        }
+        if (rows_seen != row_hi - row_lo + 1) throw std::logic_error("site list does not cover the rows");
+        for (long long q = 0; q <= row_hi - row_lo; ++q)
+            if (written_H[q] != H_ptr[q + 1] - H_ptr[q] || written_S[q] != S_ptr[q + 1] - S_ptr[q])
+                throw std::logic_error("site fill wrote a different number of entries than counted");
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -59,8 +59,9 @@ def test_stage_B_Rk(case):
         assert np.all(R[:, :, hc.P:] == 0.0)
 
 
+@pytest.mark.parametrize("kernel", ["row", "site"])
 @pytest.mark.parametrize("full", [False, True])
-def test_stage_C_blocks(case, full):
+def test_stage_C_blocks(case, full, kernel):
     run, hc = case
     hc.set_R(np.transpose(run.R, (2, 0, 1)))
     hc.set_one_particle(run.H_vec, run.S)
@@ -71,9 +72,21 @@ def test_stage_C_blocks(case, full):
         nnz = O.count_nnz(run.bs.k, s, run.p["max_k"], full)
         H, S, emitted = run.block(s, nnz=nnz)
         assert emitted == nnz
-        (Hp, Hi, Hd), (Sp, Si, Sd) = hc.block(s.l, s.conf_n, s.conf_l, full)
+        (Hp, Hi, Hd), (Sp, Si, Sd) = hc.block(s.l, s.conf_n, s.conf_l, full, kernel=kernel)
         assert_csr_equal(O.CSR(H.shape, len(Hi), Hp, Hi, Hd), H, what=f"H L={s.l} pi={s.pi}")
         assert_csr_equal(O.CSR(S.shape, len(Si), Sp, Si, Sd), S, what=f"S L={s.l} pi={s.pi}")
+
+
+def test_site_and_row_kernels_bit_identical(case):
+    run, hc = case
+    hc.set_R(np.transpose(run.R, (2, 0, 1)))
+    hc.set_one_particle(run.H_vec, run.S)
+    for s in run.syms:
+        for full in (False, True):
+            a = hc.block(s.l, s.conf_n, s.conf_l, full, kernel="row")
+            b = hc.block(s.l, s.conf_n, s.conf_l, full, kernel="site")
+            for (p1, i1, d1), (p2, i2, d2) in zip(a, b):
+                assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
 
 
 def test_row_range_fragments_concatenate(case):
