@@ -112,10 +112,17 @@ struct SiteList {
     int nsites;
 };
 
+struct alignas(16) RowCache {  // per row of the site: what a pair needs to know about its row
+    long long hbase, sbase;    // 0-based position of the first H / S entry of the row
+    int bi, la, lb, pad;
+};
+
 struct SiteSmem {   // element counts of the dynamic shared memory carve-up
     int nsmax;      // slots (stride of Rv over k)
     int ncmax;      // n_c slots
     int cap;        // (row, column block) pairs per group
+    int lanes_per_slot;  // power of two >= 2w+1 (<= 32)
+    int wide_two_pass;   // 2*(2w+1) > 32
     size_t bytes;
 };
 
@@ -126,7 +133,8 @@ __host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int n
     b += sizeof(double) * nsmax * g.K1;                               // Rv
     b += sizeof(double) * (size_t)nw * 2 * g.K1;                       // wang
     b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                     // T
-    b += sizeof(int) * (size_t)cap;                                    // off
+    b += sizeof(int2) * (size_t)cap;                                   // plist
+    b += sizeof(RowCache) * (size_t)nblk;                              // rcache
     b += sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1);  // hp
     b += sizeof(unsigned short) * (size_t)nblk * (ncmax + 1);           // sp
     return b + 16;
@@ -143,7 +151,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 }
 
 constexpr int kSiteWarps = 8;
-constexpr int kSiteMinBlocks = 3;
+constexpr int kSiteMinBlocks = 4;
 constexpr size_t kSiteSmemLimit = 200 * 1024;
 
 template <int NW>
@@ -160,10 +168,11 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
     double* Rv = reinterpret_cast<double*>(smraw);
     double* wang_all = Rv + (size_t)nsmax * K1;
     SiteEntry* T = reinterpret_cast<SiteEntry*>(wang_all + (size_t)NW * 2 * K1);
-    int* off = reinterpret_cast<int*>(T + (size_t)nblk * ncmax);
-    unsigned short* hp = reinterpret_cast<unsigned short*>(off + cap);
+    RowCache* rcache = reinterpret_cast<RowCache*>(T + (size_t)nblk * ncmax);  // rows of the group
+    int2* plist = reinterpret_cast<int2*>(rcache + nblk);                       // coupled pairs of the group
+    unsigned short* hp = reinterpret_cast<unsigned short*>(plist + cap);
     unsigned short* sp = hp + (size_t)nblk * kModes * (ncmax + 1);
-    __shared__ int s_next;
+    __shared__ int s_next, s_npairs;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sidx = blockIdx.x;
@@ -171,13 +180,11 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
     const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
     const int* srows = sl.rows + sl.ptr[sidx];
     const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
-    const int nnc = s.nnc, top = search_top(nnc);
+    const int nnc = s.nnc;
 
     // ---- phase 1: clipped windows per column block; stage both R^k windows ----
-    for (int item = tid; item < nblk * nnc; item += NW * 32) {
-        const int bj = item / nnc, q = item - bj * nnc;
-        T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
-    }
+    for (int q = lane; q < nnc; q += 32)
+        for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
     {
         const int ns = s.nD + s.nX;
         const size_t plane = (size_t)g.P * g.ldP;
@@ -198,110 +205,136 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
         }
     }
     __syncthreads();
-    // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode) ----
-    for (int task = warp; task < nblk * kModes; task += NW) {
+    // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode);
+    //      one thread per (bj, mode), serial over the slots ----
+    for (int task = tid; task < nblk * kModes; task += NW * 32) {
         const int bj = task / kModes, mode = task - bj * kModes;
         const bool useD = mode_useD(mode), useX = mode_useX(mode);
         const bool diag = mode == kModeDiag;
         const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
-        unsigned short* hpq = hp + (size_t)task * (ncmax + 1);
-        unsigned short* spq = sp + (size_t)bj * (ncmax + 1);
+        unsigned short* hpq = hp + task * (ncmax + 1);
+        unsigned short* spq = sp + bj * (ncmax + 1);
         int run = 0, srun = 0;
-        for (int q0 = 0; q0 < nnc; q0 += 32) {
-            const int q = q0 + lane;
-            int ch = 0, cs = 0;
-            if (q < nnc) {
-                SiteEntry e = T[bj * ncmax + q];
-                if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
-                ch = entry_count(e, useD, useX);
-                if (diag) cs = entry_count(e, true, samex);
-            }
-            const int inc = warp_incl_scan(ch, lane);
-            if (q < nnc) hpq[q] = (unsigned short)(run + inc - ch);
-            run += __shfl_sync(0xffffffffu, inc, 31);
+        for (int q = 0; q < nnc; ++q) {
+            SiteEntry e = T[bj * ncmax + q];
+            if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
+            hpq[q] = (unsigned short)run;
+            run += entry_count(e, useD, useX);
             if (diag) {
-                const int sinc = warp_incl_scan(cs, lane);
-                if (q < nnc) spq[q] = (unsigned short)(srun + sinc - cs);
-                srun += __shfl_sync(0xffffffffu, sinc, 31);
+                spq[q] = (unsigned short)srun;
+                srun += entry_count(e, true, samex);
             }
         }
-        if (lane == 0) hpq[nnc] = (unsigned short)run;
+        hpq[nnc] = (unsigned short)run;
     }
 
-    double* wang = wang_all + (size_t)warp * 2 * K1;
+    double* wang = wang_all + warp * 2 * K1;
     const int G = cap / nblk;  // rows per group (host guarantees >= 1)
+    double* const Hd = reinterpret_cast<double*>(Hdat);
+    double* const Sd = reinterpret_cast<double*>(Sdat);
+    const int lpw = lay.lanes_per_slot;          // lanes per n_c slot in the single-window modes
+    const int sub = lane / lpw, idx1 = lane - sub * lpw, spi = 32 / lpw;
 
     for (int g0 = 0; g0 < nr; g0 += G) {
-        const int gr = imin(G, nr - g0), npairs = gr * nblk;
+        const int gr = imin(G, nr - g0);
         __syncthreads();  // phase 2 / previous group finished
-        if (tid == 0) s_next = 0;
-        // ---- phase 3: offsets of the column blocks inside each row ----
+        if (tid == 0) { s_next = 0; s_npairs = 0; }
+        __syncthreads();
+        // ---- phase 3: coupled pairs of each row and their offsets inside the row ----
         for (int ri = warp; ri < gr; ri += NW) {
-            const RowInfo r = row_info(pl, srows[g0 + ri]);
+            const int rowi = srows[g0 + ri];
+            const RowInfo r = row_info(pl, rowi);
+            if (lane == 0) {
+                const long long wrow = (long long)rowi - row_lo;
+                rcache[ri] = RowCache{Hptr[wrow] - 1, Sptr[wrow] - 1, r.bi, r.la, r.lb, 0};
+            }
             int run = 0;
             for (int b0 = 0; b0 < nblk; b0 += 32) {
                 const int bj = b0 + lane;
-                int c = 0;
+                int c = 0, mode = -1;
                 if (bj < nblk) {
-                    const int mode = pair_mode(pl, r, bj);
-                    if (mode >= 0) c = hp[((size_t)bj * kModes + mode) * (ncmax + 1) + nnc];
+                    mode = pair_mode(pl, r, bj);
+                    if (mode >= 0) {
+                        const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
+                        mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
+                        c = hb[mode * (ncmax + 1)];
+                    }
                 }
                 const int inc = warp_incl_scan(c, lane);
-                if (bj < nblk) off[ri * nblk + bj] = run + inc - c;
+                const unsigned live = __ballot_sync(0xffffffffu, c > 0);
+                int base = 0;
+                if (lane == 0 && live) base = atomicAdd(&s_npairs, __popc(live));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (c > 0) {
+                    const int slot = base + __popc(live & ((1u << lane) - 1u));
+                    plist[slot] = make_int2(ri | (bj << 12) | (mode << 24), run + inc - c);
+                }
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
         __syncthreads();
+        const int npairs = s_npairs;
         // ---- phase 4: fill ----
         for (;;) {
             int p = 0;
             if (lane == 0) p = atomicAdd(&s_next, 1);
             p = __shfl_sync(0xffffffffu, p, 0);
             if (p >= npairs) break;
-            const int ri = p / nblk, bj = p - ri * nblk;
-            const int rowi = srows[g0 + ri];
-            const RowInfo r = row_info(pl, rowi);
-            const int mode = pair_mode(pl, r, bj);
-            if (mode < 0) continue;
-            const unsigned short* hpq = hp + ((size_t)bj * kModes + mode) * (ncmax + 1);
-            const int total = hpq[nnc];
-            if (total == 0) continue;
-            const Coupling c = coupling(pl, r, bj);
-            const bool useD = mode_useD(mode), useX = mode_useX(mode);
-            const bool diag = mode == kModeDiag, cut = diag && !pl.full;
-            const size_t cpl = (size_t)r.bi * nblk + bj;
+            const int2 pe = plist[p];
+            const int ri = pe.x & 0xfff, bj = (pe.x >> 12) & 0xfff, mode = pe.x >> 24;
+            const RowCache rc = rcache[ri];
+            RowInfo r;
+            r.i = 0;
+            r.bi = rc.bi;
+            r.na = s.na;
+            r.nb = s.nb;
+            r.la = rc.la;
+            r.lb = rc.lb;
+            const int cpl = r.bi * nblk + bj;
+            const unsigned fl = pl.flags[cpl];
+            PairCtx pc;
+            pc.pk = pair_k(pl.krange[cpl]);
             __syncwarp();
-            for (int k = lane; k < K1; k += 32) {
-                wang[k] = pl.angD[cpl * K1 + k];
-                wang[K1 + k] = pl.angX[cpl * K1 + k];
+            for (int i = lane; i < pc.pk.nkd; i += 32) wang[i] = pl.angD[(size_t)cpl * K1 + pc.pk.dlo + 2 * i];
+            for (int i = lane; i < pc.pk.nkx; i += 32) wang[K1 + i] = pl.angX[(size_t)cpl * K1 + pc.pk.xlo + 2 * i];
+            __syncwarp();
+            pc.Tb = T + bj * ncmax;
+            pc.hpq = hp + (bj * kModes + mode) * (ncmax + 1);
+            pc.spq = sp + bj * (ncmax + 1);
+            pc.Rv = Rv;
+            pc.wa_d = wang;
+            pc.wa_x = wang + K1;
+            pc.nsmax = nsmax;
+            pc.bj = bj;
+            pc.diag = mode == kModeDiag;
+            pc.dirany = (fl & kDirAny) != 0;
+            pc.exany = (fl & kExAny) != 0;
+            pc.samex = pc.diag && r.la == r.lb;
+            pc.cut = pc.diag && !pl.full;
+            {
+                const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
+                pc.win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
             }
-            __syncwarp();
-            const KRange kr = pl.krange[cpl];
-            const long long wrow = (long long)rowi - row_lo;
-            const long long hbase = Hptr[wrow] - 1 + off[p];
-            const long long sbase = Sptr[wrow] - 1;
-            const SiteEntry* Tb = T + bj * ncmax;
-            const unsigned short* spq = sp + (size_t)bj * (ncmax + 1);
-            for (int o = lane; o < total; o += 32) {
-                const int q = prefix_search(hpq, nnc, top, o);
-                const int nc = site_nc(s, q);
-                SiteEntry e = Tb[q];
-                if (cut) e = entry_cut(e, s, nc);
-                const int nd = entry_nd(e, useD, useX, o - (int)hpq[q]);
-                const bool sup = nd >= (int)e.dlo && nd <= (int)e.dhi;
-                const bool sup_ex = nd >= (int)e.xlo && nd <= (int)e.xhi;
-                const Element el = element_value_at(
-                    g, pl, ob, Rv + (sup ? site_slotD(s, nc, nd) : 0), (size_t)nsmax,
-                    Rv + (sup_ex ? site_slotX(s, nc, nd) : 0), (size_t)nsmax, wang, wang + K1, kr, r, c,
-                    bj, nc, nd, sup, sup_ex);
-                const long long j = (long long)e.jbase + nd;
-                Hidx[hbase + o] = j;
-                Hdat[hbase + o] = make_double2(el.H.re, el.H.im);
-                if (el.storeS) {
-                    const long long pos =
-                        sbase + spq[q] + union_below(true, e.dlo, e.dhi, c.samex, e.xlo, e.xhi, nd);
-                    Sidx[pos] = j;
-                    Sdat[pos] = make_double2(el.S.re, el.S.im);
+            pc.hbase = rc.hbase + pe.y;
+            pc.sbase = rc.sbase;
+            const Segs segs = pair_segments(s, pc.win, pc.cut);
+            for (int t = 0; t < 3; ++t) {
+                const Seg sg = segs_at(segs, t);
+                const int q0 = sg.q0, q1 = sg.q1, win = sg.win;
+                if (win != kModeDX) {
+                    // one window: lpw lanes per n_c slot, 32/lpw slots per step
+                    for (int qb = q0; qb < q1; qb += spi) {
+                        const int q = qb + sub;
+                        if (q < q1) site_lane<false>(g, pl, ob, s, r, pc, win, q, idx1, 0, Hidx, Hd, Sidx, Sd);
+                    }
+                } else {
+                    // union of both windows: one slot per step, <= 2*(2w+1) <= 64 entries
+                    for (int q = q0; q < q1; ++q) {
+                        const int cnt = (int)pc.hpq[q + 1] - (int)pc.hpq[q];
+                        if (cnt == 0) continue;
+                        site_lane<true>(g, pl, ob, s, r, pc, win, q, lane, cnt, Hidx, Hd, Sidx, Sd);
+                        if (cnt > 32) site_lane<true>(g, pl, ob, s, r, pc, win, q, lane + 32, cnt, Hidx, Hd, Sidx, Sd);
+                    }
                 }
             }
         }
@@ -440,10 +473,13 @@ void block_assemble(bs2e_block* b)
     constexpr int NW = kSiteWarps;
     const Geom& g = c->dg;
     const char* mode = getenv("BS2E_FILL");
-    bool use_site = b->nsites > 0 && !(mode && strcmp(mode, "row") == 0) && site_max_nc(g) <= 255;
+    bool use_site = b->nsites > 0 && !(mode && strcmp(mode, "row") == 0) && 2 * g.w + 1 <= 32;
     SiteSmem lay{};
     if (use_site) {
         lay.nsmax = site_max_slots(g);
+        lay.lanes_per_slot = 1;
+        while (lay.lanes_per_slot < 2 * g.w + 1) lay.lanes_per_slot *= 2;
+        lay.wide_two_pass = 2 * (2 * g.w + 1) > 32;
         lay.ncmax = site_max_nc(g);
         const int cap_want = std::max(b->dplan.nblk, std::min(2048, b->dplan.nblk * b->dplan.nblk));
         lay.cap = cap_want;
@@ -452,7 +488,7 @@ void block_assemble(bs2e_block* b)
             lay.cap = b->dplan.nblk;
             lay.bytes = site_smem_bytes(g, b->dplan.nblk, NW, lay.cap);
         }
-        if (lay.bytes > kSiteSmemLimit || 2 * site_max_slots(g) > 65535) use_site = false;
+        if (lay.bytes > kSiteSmemLimit || 2 * site_max_slots(g) > 65535 || b->dplan.nblk > 4095) use_site = false;
     }
     if (use_site) {
         BS2E_CUDA(cudaFuncSetAttribute(site_fill_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -418,16 +418,85 @@ BS2E_HD Cplx band_H(const Geom& g, const OneBody& ob, int l, int n, int np)
 
 struct Element { Cplx H, S; bool storeS; };
 
-// value of the (i,j) entry, j = (bj, nc, nd)
+// ---- element formulas -------------------------------------------------------
 //   mat_els.f90:552-571 r_12_tens, :608-633 c_mat_neq_tens,
 //   :664-678 S_mat_neq, :697-715 H_1p_neq; hamiltonian.f90:183-193
-// Rd[k*sd] = R^k(n_a n_b; n_c n_d); Rx[k*sx] = R^k(n_a n_b; n_d n_c), read through the
-// electron-exchange symmetry R^k(ab;dc) = R^k(ba;cd); angD/angX: K1 factors of the (bi,bj)
-// pair (exchange already multiplied by (-1)^(lc+ld+L)).  The pointers may refer to global
-// memory (row kernel) or to the staged site window in shared memory (site kernel).
+
+// k ranges of a pair in packed form: direct terms k = dlo + 2i, i < nkd; exchange likewise
+struct PairK { int dlo, nkd, xlo, nkx; };
+BS2E_HD PairK pair_k(KRange kr)
+{
+    PairK p;
+    p.dlo = kr.dlo;
+    p.nkd = kr.dhi >= kr.dlo ? (kr.dhi - kr.dlo) / 2 + 1 : 0;
+    p.xlo = kr.xlo;
+    p.nkx = kr.xhi >= kr.xlo ? (kr.xhi - kr.xlo) / 2 + 1 : 0;
+    return p;
+}
+
+// sum_i rp[i*stride] * wa[i] in ascending order (the k sum of r_12_tens, mat_els.f90:566-570)
+template <int NK>
+BS2E_HD double k_dot_n(const double* rp, int stride, const double* wa)
+{
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NK; ++i) acc += rp[i * stride] * wa[i];
+    return acc;
+}
+BS2E_HD double k_dot(const double* rp, int stride, const double* wa, int nk)
+{
+    switch (nk) {  // nk is uniform over a (row, column block) pair
+    case 0: return 0.0;
+    case 1: return k_dot_n<1>(rp, stride, wa);
+    case 2: return k_dot_n<2>(rp, stride, wa);
+    case 3: return k_dot_n<3>(rp, stride, wa);
+    case 4: return k_dot_n<4>(rp, stride, wa);
+    case 5: return k_dot_n<5>(rp, stride, wa);
+    case 6: return k_dot_n<6>(rp, stride, wa);
+    case 7: return k_dot_n<7>(rp, stride, wa);
+    case 8: return k_dot_n<8>(rp, stride, wa);
+    default: break;
+    }
+    double acc = k_dot_n<8>(rp, stride, wa);
+    for (int i = 8; i < nk; ++i) acc += rp[i * stride] * wa[i];
+    return acc;
+}
+
+// one-body and overlap part of an entry whose column block equals the row block
+// (H_1p_neq, S_mat_neq); lc, ld = l values of the column block (= those of the row)
+BS2E_HD void one_body_terms(const Geom& g, const Plan& pl, const OneBody& ob, const RowInfo& r,
+                            bool same, bool samex, int lc, int ld, int nc, int nd, Cplx* hout,
+                            Cplx* sout)
+{
+    Cplx h = Cplx{0.0, 0.0}, s = Cplx{0.0, 0.0};
+    if (same) {
+        const Cplx Sbd = band_S(g, ob, r.nb, nd), Sac = band_S(g, ob, r.na, nc);
+        h = cadd(h, cmul(band_H(g, ob, r.la, r.na, nc), Sbd));
+        h = cadd(h, cmul(band_H(g, ob, r.lb, r.nb, nd), Sac));
+        s = cadd(s, cmul(Sac, Sbd));
+    }
+    if (samex) {
+        const double sgn = ((pl.L + lc + ld) & 1) ? -1.0 : 1.0;
+        const Cplx Sbc = band_S(g, ob, r.nb, nc), Sad = band_S(g, ob, r.na, nd);
+        Cplx hx = cadd(cmul(band_H(g, ob, r.la, r.na, nd), Sbc),
+                       cmul(band_H(g, ob, r.lb, r.nb, nc), Sad));
+        h = cadd(h, Cplx{hx.re * sgn, hx.im * sgn});
+        Cplx sx2 = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
+        s = cadd(s, sx2);
+    }
+    *hout = h;
+    *sout = s;
+}
+
+// value of the (i,j) entry, j = (bj, nc, nd).
+// Rd[i*sd], i < pk.nkd : R^k(n_a n_b; n_c n_d) for k = pk.dlo + 2i;
+// Rx[i*sx], i < pk.nkx : R^k(n_a n_b; n_d n_c), read through the electron-exchange
+// symmetry R^k(ab;dc) = R^k(ba;cd); wa_d / wa_x: the matching angular factors of the
+// (bi,bj) pair (exchange already multiplied by (-1)^(lc+ld+L)).  The pointers may refer
+// to global memory (row kernel) or to the staged site window in shared memory.
 BS2E_HD Element element_value_at(const Geom& g, const Plan& pl, const OneBody& ob,
-                                 const double* Rd, size_t sd, const double* Rx, size_t sx,
-                                 const double* angD, const double* angX, KRange kr,
+                                 const double* Rd, int sd, const double* Rx, int sx,
+                                 const double* wa_d, const double* wa_x, PairK pk,
                                  const RowInfo& r, const Coupling& c, int bj, int nc, int nd,
                                  bool sup, bool sup_ex)
 {
@@ -437,14 +506,50 @@ BS2E_HD Element element_value_at(const Geom& g, const Plan& pl, const OneBody& o
     const bool allowed = (sup && c.dirany) || (sup_ex && c.exany);
     if (allowed) {
         double res = 0.0;
-        if (sup) {  // sum_k ang_k R^k(n_a n_b; n_c n_d)
+        if (sup) res += k_dot(Rd, sd, wa_d, pk.nkd);
+        if (sup_ex) res += k_dot(Rx, sx, wa_x, pk.nkx);
+        e.H.re = res;
+    }
+    e.storeS = (sup && c.same) || (sup_ex && c.samex);
+    if (e.storeS) {
+        const BlockDesc bc = pl.blk[bj];
+        Cplx h, s;
+        one_body_terms(g, pl, ob, r, c.same, c.samex, bc.l1, bc.l2, nc, nd, &h, &s);
+        e.H = cadd(e.H, h);
+        e.S = s;
+    }
+    return e;
+}
+
+// the same with R^k gathered from the global tensor R[k][p1][p2] (row kernel); the
+// stride between consecutive terms of one parity is two planes
+BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
+                              const double* R, const RowInfo& r, const Coupling& c,
+                              int bj, int nc, int nd, bool sup, bool sup_ex)
+{
+    const size_t plane = (size_t)g.P * g.ldP;
+    const size_t cpl = ((size_t)r.bi * pl.nblk + bj);
+    const PairK pk = pair_k(pl.krange[cpl]);
+    const double* Rd = R;
+    const double* Rx = R;
+    if (sup) Rd = R + (size_t)pair_index(g, r.na, nc) * g.ldP + pair_index(g, r.nb, nd) + pk.dlo * plane;
+    if (sup_ex) Rx = R + (size_t)pair_index(g, r.nb, nc) * g.ldP + pair_index(g, r.na, nd) + pk.xlo * plane;
+    const double* ad = pl.angD + cpl * g.K1;
+    const double* ax = pl.angX + cpl * g.K1;
+    Element e;
+    e.H = Cplx{0.0, 0.0};
+    e.S = Cplx{0.0, 0.0};
+    const bool allowed = (sup && c.dirany) || (sup_ex && c.exany);
+    if (allowed) {
+        double res = 0.0;
+        if (sup) {
             double acc = 0.0;
-            for (int k = kr.dlo; k <= kr.dhi; k += 2) acc += Rd[k * sd] * angD[k];
+            for (int i = 0; i < pk.nkd; ++i) acc += Rd[(size_t)(2 * i) * plane] * ad[pk.dlo + 2 * i];
             res += acc;
         }
-        if (sup_ex) {  // (-1)^(lc+ld+L) sum_k ang^ex_k R^k(n_a n_b; n_d n_c)
+        if (sup_ex) {
             double acc = 0.0;
-            for (int k = kr.xlo; k <= kr.xhi; k += 2) acc += Rx[k * sx] * angX[k];
+            for (int i = 0; i < pk.nkx; ++i) acc += Rx[(size_t)(2 * i) * plane] * ax[pk.xlo + 2 * i];
             res += acc;
         }
         e.H.re = res;
@@ -452,42 +557,12 @@ BS2E_HD Element element_value_at(const Geom& g, const Plan& pl, const OneBody& o
     e.storeS = (sup && c.same) || (sup_ex && c.samex);
     if (e.storeS) {
         const BlockDesc bc = pl.blk[bj];
-        const int lc = bc.l1, ld = bc.l2;
-        Cplx h = Cplx{0.0, 0.0}, s = Cplx{0.0, 0.0};
-        if (c.same) {
-            const Cplx Sbd = band_S(g, ob, r.nb, nd), Sac = band_S(g, ob, r.na, nc);
-            h = cadd(h, cmul(band_H(g, ob, r.la, r.na, nc), Sbd));
-            h = cadd(h, cmul(band_H(g, ob, r.lb, r.nb, nd), Sac));
-            s = cadd(s, cmul(Sac, Sbd));
-        }
-        if (c.samex) {
-            const double sgn = ((pl.L + lc + ld) & 1) ? -1.0 : 1.0;
-            const Cplx Sbc = band_S(g, ob, r.nb, nc), Sad = band_S(g, ob, r.na, nd);
-            Cplx hx = cadd(cmul(band_H(g, ob, r.la, r.na, nd), Sbc),
-                           cmul(band_H(g, ob, r.lb, r.nb, nc), Sad));
-            h = cadd(h, Cplx{hx.re * sgn, hx.im * sgn});
-            Cplx sx2 = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
-            s = cadd(s, sx2);
-        }
+        Cplx h, s;
+        one_body_terms(g, pl, ob, r, c.same, c.samex, bc.l1, bc.l2, nc, nd, &h, &s);
         e.H = cadd(e.H, h);
         e.S = s;
     }
     return e;
-}
-
-// the same with R^k gathered from the global tensor R[k][p1][p2]
-BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
-                              const double* R, const RowInfo& r, const Coupling& c,
-                              int bj, int nc, int nd, bool sup, bool sup_ex)
-{
-    const size_t plane = (size_t)g.P * g.ldP;
-    const size_t cpl = ((size_t)r.bi * pl.nblk + bj);
-    const double* Rd = R;
-    const double* Rx = R;
-    if (sup) Rd = R + (size_t)pair_index(g, r.na, nc) * g.ldP + pair_index(g, r.nb, nd);
-    if (sup_ex) Rx = R + (size_t)pair_index(g, r.nb, nc) * g.ldP + pair_index(g, r.na, nd);
-    return element_value_at(g, pl, ob, Rd, plane, Rx, plane, pl.angD + cpl * g.K1,
-                            pl.angX + cpl * g.K1, pl.krange[cpl], r, c, bj, nc, nd, sup, sup_ex);
 }
 
 }  // namespace bs2e

@@ -181,4 +181,155 @@ BS2E_HD int search_top(int nnc)
     return top;
 }
 
+// ---- one stored entry of a (row, column block) pair --------------------------
+// Everything that is uniform over the pair.  Pointers into shared memory in the
+// kernel, into plain arrays in the CPU checker.
+struct PairCtx {
+    const SiteEntry* Tb;        // [nnc] clipped windows of the column block
+    const unsigned short* hpq;  // [nnc+1] prefix of stored H entries over the n_c slots
+    const unsigned short* spq;  // [nnc]   same for S (diagonal pair only)
+    const double* Rv;           // staged R^k values, Rv[k*nsmax + slot]
+    const double* wa_d;         // packed direct factors, k = pk.dlo + 2i
+    const double* wa_x;         // packed exchange factors
+    int nsmax;
+    PairK pk;
+    int bj;
+    int win;                    // single-window form: kModeD or kModeX; else kModeDX
+    bool diag;                  // column block == row block: one-body terms and S
+    bool dirany, exany, samex, cut;
+    long long hbase, sbase;     // first H entry of the pair / first S entry of the row
+};
+
+// How a pair is walked: with one window only (all entries of the other window are
+// clipped away for this site and column block, or the mode stores one window) the
+// n_c slots hold <= 2w+1 consecutive n_d; otherwise the union of both windows.
+BS2E_HD int pair_window(int mode, int totD, int totX)
+{
+    if (mode == kModeD || mode == kModeX) return mode;
+    if (totX == 0) return kModeD;
+    if (totD == 0) return kModeX;
+    return kModeDX;
+}
+
+// position of n_c value v in the ascending union of the two n_c ranges
+BS2E_HD int union_pos(const Site& s, int v)
+{
+    return below(s.cDlo, s.cDhi, v) + below(s.cXlo, s.cXhi, v) -
+           below(imax(s.cDlo, s.cXlo), imin(s.cDhi, s.cXhi), v);
+}
+
+// A pair is walked in <= 3 segments of consecutive n_c slots [q0,q1): slots that lie in
+// one n_c range only hold one window (win = kModeD / kModeX, <= 2w+1 consecutive n_d);
+// slots in both ranges (|n_a - n_b| <= 2w) hold the union (win = kModeDX).
+struct Seg { int q0, q1, win; };
+struct Segs { Seg a, b, c; };  // ascending n_c; empty segments have q1 <= q0
+BS2E_HD Seg segs_at(const Segs& g3, int t) { return t == 0 ? g3.a : (t == 1 ? g3.b : g3.c); }
+
+BS2E_HD Seg seg_of_range(const Site& s, int lo, int hi, int win)
+{
+    Seg r;
+    r.q0 = union_pos(s, lo);
+    r.q1 = hi >= lo ? union_pos(s, hi) + 1 : r.q0;
+    r.win = win;
+    return r;
+}
+
+BS2E_HD Segs pair_segments(const Site& s, int win, bool cut)
+{
+    Segs o;
+    o.a = o.b = o.c = Seg{0, 0, kModeD};
+    if (win == kModeD) {
+        o.a = seg_of_range(s, s.cDlo, s.cDhi, kModeD);
+    } else if (win == kModeX) {
+        o.a = seg_of_range(s, s.cXlo, s.cXhi, kModeX);
+    } else {
+        const int ilo = imax(s.cDlo, s.cXlo), ihi = imin(s.cDhi, s.cXhi);
+        const bool dlow = s.cDlo <= s.cXlo, dhigh = s.cDhi > s.cXhi;
+        if (ihi < ilo) {  // disjoint n_c ranges
+            o.a = seg_of_range(s, dlow ? s.cDlo : s.cXlo, dlow ? s.cDhi : s.cXhi, dlow ? kModeD : kModeX);
+            o.c = seg_of_range(s, dlow ? s.cXlo : s.cDlo, dlow ? s.cXhi : s.cDhi, dlow ? kModeX : kModeD);
+        } else {
+            o.a = seg_of_range(s, imin(s.cDlo, s.cXlo), ilo - 1, dlow ? kModeD : kModeX);
+            o.b = seg_of_range(s, ilo, ihi, kModeDX);
+            o.c = seg_of_range(s, ihi + 1, imax(s.cDhi, s.cXhi), dhigh ? kModeD : kModeX);
+        }
+    }
+    if (cut) {  // slots with n_c < n_a are cut away (j >= i)
+        const int qc = union_pos(s, s.na);
+        o.a.q0 = imax(o.a.q0, qc);
+        o.b.q0 = imax(o.b.q0, qc);
+        o.c.q0 = imax(o.c.q0, qc);
+    }
+    return o;
+}
+
+// entry number idx (ascending n_d) of n_c slot q.  WIDE = false: one window (win);
+// WIDE = true: union of both windows, cnt = number of entries of the slot.
+template <bool WIDE>
+BS2E_HD void site_lane(const Geom& g, const Plan& pl, const OneBody& ob, const Site& s,
+                       const RowInfo& r, const PairCtx& pc, int win, int q, int idx, int cnt,
+                       long long* Hidx, double* Hdat, long long* Sidx, double* Sdat)
+{
+    SiteEntry e = pc.Tb[q];
+    const int nc = site_nc(s, q);
+    if (pc.cut) e = entry_cut(e, s, nc);
+    int nd;
+    if (!WIDE) {
+        const int lo = win == kModeD ? (int)e.dlo : (int)e.xlo;
+        const int hi = win == kModeD ? (int)e.dhi : (int)e.xhi;
+        nd = lo + idx;
+        if (nd > hi) return;
+    } else {
+        if (idx >= cnt) return;
+        nd = entry_nd(e, true, true, idx);
+    }
+    // inside the stored set the clipping is common to both windows
+    const bool sup = site_nc_inD(s, nc) && nd >= s.dDlo && nd <= s.dDhi;
+    const bool sup_ex = site_nc_inX(s, nc) && nd >= s.dXlo && nd <= s.dXhi;
+    const int stride = 2 * pc.nsmax;
+    double re = 0.0, im = 0.0;
+    const bool allowed = (sup && pc.dirany) || (sup_ex && pc.exany);
+    if (allowed) {
+        double res = 0.0;
+        if (sup) res += k_dot(pc.Rv + pc.pk.dlo * pc.nsmax + site_slotD(s, nc, nd), stride, pc.wa_d, pc.pk.nkd);
+        if (sup_ex) res += k_dot(pc.Rv + pc.pk.xlo * pc.nsmax + site_slotX(s, nc, nd), stride, pc.wa_x, pc.pk.nkx);
+        re = res;
+    }
+    const long long j = (long long)e.jbase + nd;
+    if (pc.diag) {
+        const bool storeS = sup || (sup_ex && pc.samex);
+        if (storeS) {
+            const BlockDesc bc = pl.blk[pc.bj];
+            Cplx h, sv;
+            one_body_terms(g, pl, ob, r, true, pc.samex, bc.l1, bc.l2, nc, nd, &h, &sv);
+            re += h.re;
+            im += h.im;
+            const long long pos =
+                pc.sbase + pc.spq[q] + union_below(true, e.dlo, e.dhi, pc.samex, e.xlo, e.xhi, nd);
+            Sidx[pos] = j;
+            Sdat[2 * pos] = sv.re;
+            Sdat[2 * pos + 1] = sv.im;
+        }
+    }
+    const long long pos = pc.hbase + pc.hpq[q] + idx;
+    Hidx[pos] = j;
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<double2*>(Hdat + 2 * pos) = make_double2(re, im);
+#else
+    Hdat[2 * pos] = re;
+    Hdat[2 * pos + 1] = im;
+#endif
+}
+
+// storage mode that the pair effectively stores: a D+X pair whose exchange
+// (direct) windows are all empty for this site and column block is a pure D (X) pair
+BS2E_HD int effective_mode(int mode, int totD, int totX)
+{
+    if (mode == kModeDX) {
+        if (totX == 0) return kModeD;
+        if (totD == 0) return kModeX;
+    }
+    return mode;
+}
+
 }  // namespace bs2e

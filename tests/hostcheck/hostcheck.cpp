@@ -228,16 +228,19 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
         const double* R = c->R.data();
         const int K1 = g.K1, nsmax = site_max_slots(g), ncmax = site_max_nc(g), nblk = pl.nblk;
         const size_t plane = (size_t)g.P * g.ldP;
+        int lpw = 1;
+        while (lpw < 2 * g.w + 1) lpw *= 2;
+        if (lpw > 32) throw std::logic_error("site kernel needs 2w+1 <= 32");
+        const int spi = 32 / lpw;
         std::vector<double> Rv((size_t)nsmax * K1);
         std::vector<SiteEntry> T((size_t)nblk * ncmax);
         std::vector<unsigned short> hp((size_t)nblk * kModes * (ncmax + 1)), sp((size_t)nblk * (ncmax + 1));
-        std::vector<long long> written_H(row_hi - row_lo + 1, 0), written_S(row_hi - row_lo + 1, 0);
         const int nsites = (int)hp_.site_key.size();
         long long rows_seen = 0;
         for (int sidx = 0; sidx < nsites; ++sidx) {
             const unsigned key = hp_.site_key[sidx];
             const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
-            const int nnc = s.nnc, top = search_top(nnc);
+            const int nnc = s.nnc;
             if (nnc > ncmax || s.nD + s.nX > nsmax) throw std::logic_error("site exceeds smem bounds");
             // phase 1
             for (int bj = 0; bj < nblk; ++bj)
@@ -271,44 +274,65 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                 if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
                 const long long wrow = rowi - row_lo;
                 int offrun = 0;  // phase 3 (running form of the scan over column blocks)
+                std::vector<double> wang(2 * K1);
                 for (int bj = 0; bj < nblk; ++bj) {
-                    const int mode = pair_mode(pl, r, bj);
+                    int mode = pair_mode(pl, r, bj);
                     if (mode < 0) continue;
-                    const unsigned short* hpq = hp.data() + ((size_t)bj * kModes + mode) * (ncmax + 1);
-                    const int total = hpq[nnc];
+                    const unsigned short* hb = hp.data() + (bj * kModes) * (ncmax + 1) + nnc;
+                    mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
+                    const int total = hb[mode * (ncmax + 1)];
                     if (total == 0) continue;
                     // phase 4
-                    const Coupling cp = coupling(pl, r, bj);
-                    const bool useD = mode_useD(mode), useX = mode_useX(mode);
-                    const bool cut = mode == kModeDiag && !pl.full;
-                    const size_t cpl = (size_t)r.bi * nblk + bj;
-                    const long long hbase = H_ptr[wrow] - 1 + offrun, sbase = S_ptr[wrow] - 1;
-                    for (int o = 0; o < total; ++o) {
-                        const int q = prefix_search(hpq, nnc, top, o);
-                        const int nc = site_nc(s, q);
-                        SiteEntry e = T[bj * ncmax + q];
-                        if (cut) e = entry_cut(e, s, nc);
-                        const int nd = entry_nd(e, useD, useX, o - (int)hpq[q]);
-                        const bool sup = nd >= (int)e.dlo && nd <= (int)e.dhi;
-                        const bool sup_ex = nd >= (int)e.xlo && nd <= (int)e.xhi;
-                        if (!sup && !sup_ex) throw std::logic_error("output position maps outside both windows");
-                        const Element el = element_value_at(
-                            g, pl, ob, Rv.data() + (sup ? site_slotD(s, nc, nd) : 0), (size_t)nsmax,
-                            Rv.data() + (sup_ex ? site_slotX(s, nc, nd) : 0), (size_t)nsmax,
-                            pl.angD + cpl * K1, pl.angX + cpl * K1, pl.krange[cpl], r, cp, bj, nc, nd, sup,
-                            sup_ex);
-                        const long long j = (long long)e.jbase + nd;
-                        H_idx[hbase + o] = j;
-                        H_dat[2 * (hbase + o)] = el.H.re;
-                        H_dat[2 * (hbase + o) + 1] = el.H.im;
-                        ++written_H[wrow];
-                        if (el.storeS) {
-                            const long long pos = sbase + sp[(size_t)bj * (ncmax + 1) + q] +
-                                                  union_below(true, e.dlo, e.dhi, cp.samex, e.xlo, e.xhi, nd);
-                            S_idx[pos] = j;
-                            S_dat[2 * pos] = el.S.re;
-                            S_dat[2 * pos + 1] = el.S.im;
-                            ++written_S[wrow];
+                    const int cpl = r.bi * nblk + bj;
+                    const unsigned char fl = pl.flags[cpl];
+                    const PairK pk = pair_k(pl.krange[cpl]);
+                    for (int i = 0; i < pk.nkd; ++i) wang[i] = pl.angD[(size_t)cpl * K1 + pk.dlo + 2 * i];
+                    for (int i = 0; i < pk.nkx; ++i) wang[K1 + i] = pl.angX[(size_t)cpl * K1 + pk.xlo + 2 * i];
+                    PairCtx pc;
+                    pc.Tb = T.data() + bj * ncmax;
+                    pc.hpq = hp.data() + (bj * kModes + mode) * (ncmax + 1);
+                    pc.spq = sp.data() + bj * (ncmax + 1);
+                    pc.Rv = Rv.data();
+                    pc.wa_d = wang.data();
+                    pc.wa_x = wang.data() + K1;
+                    pc.nsmax = nsmax;
+                    pc.pk = pk;
+                    pc.bj = bj;
+                    pc.diag = mode == kModeDiag;
+                    pc.dirany = (fl & kDirAny) != 0;
+                    pc.exany = (fl & kExAny) != 0;
+                    pc.samex = pc.diag && r.la == r.lb;
+                    pc.cut = pc.diag && !pl.full;
+                    pc.win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
+                    pc.hbase = H_ptr[wrow] - 1 + offrun;
+                    pc.sbase = S_ptr[wrow] - 1;
+                    long long* Hi = reinterpret_cast<long long*>(H_idx);
+                    long long* Si = reinterpret_cast<long long*>(S_idx);
+                    const Segs segs = pair_segments(s, pc.win, pc.cut);
+                    const int nseg = 3;
+                    Seg seg[3] = {segs_at(segs, 0), segs_at(segs, 1), segs_at(segs, 2)};
+                    for (int q = 0; q < nnc; ++q) {  // slots outside the segments must be empty
+                        bool covered = false;
+                        for (int t = 0; t < nseg; ++t) covered = covered || (q >= seg[t].q0 && q < seg[t].q1);
+                        if (!covered && pc.hpq[q + 1] != pc.hpq[q])
+                            throw std::logic_error("pair_segments misses a populated n_c slot");
+                    }
+                    for (int t = 0; t < nseg; ++t) {
+                        const int q0 = seg[t].q0, q1 = seg[t].q1, win = seg[t].win;
+                        if (win != kModeDX) {
+                            for (int qb = q0; qb < q1; qb += spi)
+                                for (int lane = 0; lane < 32; ++lane) {
+                                    const int sub = lane / lpw, idx1 = lane - sub * lpw, q = qb + sub;
+                                    if (q < q1)
+                                        site_lane<false>(g, pl, ob, s, r, pc, win, q, idx1, 0, Hi, H_dat, Si, S_dat);
+                                }
+                        } else {
+                            for (int q = q0; q < q1; ++q) {
+                                const int cnt = (int)pc.hpq[q + 1] - (int)pc.hpq[q];
+                                for (int lane = 0; lane < 64; ++lane)
+                                    if (lane < 32 || cnt > 32)
+                                        site_lane<true>(g, pl, ob, s, r, pc, win, q, lane, cnt, Hi, H_dat, Si, S_dat);
+                            }
                         }
                     }
                     offrun += total;
@@ -318,9 +342,6 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
             }
         }
         if (rows_seen != row_hi - row_lo + 1) throw std::logic_error("site list does not cover the rows");
-        for (long long q = 0; q <= row_hi - row_lo; ++q)
-            if (written_H[q] != H_ptr[q + 1] - H_ptr[q] || written_S[q] != S_ptr[q + 1] - S_ptr[q])
-                throw std::logic_error("site fill wrote a different number of entries than counted");
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();
