@@ -24,6 +24,8 @@
 #include <set>
 #include <unordered_map>
 
+#include <cuda.h>
+
 #include "ctx.h"
 #include "plan.h"
 #include "site_core.h"
@@ -118,11 +120,9 @@ struct alignas(16) RowCache {  // per row of the site: what a pair needs to know
 };
 
 struct SiteSmem {   // element counts of the dynamic shared memory carve-up
-    int nsmax;      // slots (stride of Rv over k)
+    int nsmax;      // slots (stride of Rv over k) = entries of list DX at most
     int ncmax;      // n_c slots
     int cap;        // (row, column block) pairs per group
-    int lanes_per_slot;  // power of two >= 2w+1 (<= 32)
-    int wide_two_pass;   // 2*(2w+1) > 32
     size_t bytes;
 };
 
@@ -130,11 +130,13 @@ __host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int n
 {
     const size_t nsmax = (size_t)site_max_slots(g), ncmax = (size_t)site_max_nc(g);
     size_t b = 0;
-    b += sizeof(double) * nsmax * g.K1;                               // Rv
+    b += sizeof(double) * 2 * (size_t)site_win_doubles(g);             // Rv: D and X windows
     b += sizeof(double) * (size_t)nw * 2 * g.K1;                       // wang
     b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                     // T
-    b += sizeof(int2) * (size_t)cap;                                   // plist
     b += sizeof(RowCache) * (size_t)nblk;                              // rcache
+    b += sizeof(Cand) * 2 * nsmax;                                     // listD + listX (half each), listDX
+    b += sizeof(int2) * (size_t)cap;                                   // plist
+    b += sizeof(int) * (ncmax + 1);                                    // cprefix
     b += sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1);  // hp
     b += sizeof(unsigned short) * (size_t)nblk * (ncmax + 1);           // sp
     return b + 16;
@@ -156,23 +158,28 @@ constexpr size_t kSiteSmemLimit = 200 * 1024;
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, kSiteMinBlocks)
-site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, SiteList sl, SiteSmem lay,
+site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay,
                  long long row_lo, const long long* __restrict__ Hptr,
                  const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
                  double2* __restrict__ Hdat, long long* __restrict__ Sidx,
                  double2* __restrict__ Sdat)
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     const int K1 = g.K1, nsmax = lay.nsmax, ncmax = lay.ncmax, cap = lay.cap;
     const int nblk = pl.nblk;
     double* Rv = reinterpret_cast<double*>(smraw);
-    double* wang_all = Rv + (size_t)nsmax * K1;
+    double* wang_all = Rv + 2 * (size_t)site_win_doubles(g);
     SiteEntry* T = reinterpret_cast<SiteEntry*>(wang_all + (size_t)NW * 2 * K1);
     RowCache* rcache = reinterpret_cast<RowCache*>(T + (size_t)nblk * ncmax);  // rows of the group
-    int2* plist = reinterpret_cast<int2*>(rcache + nblk);                       // coupled pairs of the group
-    unsigned short* hp = reinterpret_cast<unsigned short*>(plist + cap);
+    Cand* listD = reinterpret_cast<Cand*>(rcache + nblk);
+    Cand* listX = listD + nsmax / 2;
+    Cand* listDX = listX + nsmax / 2;
+    int2* plist = reinterpret_cast<int2*>(listDX + nsmax);                     // coupled pairs of the group
+    int* cprefix = reinterpret_cast<int*>(plist + cap);
+    unsigned short* hp = reinterpret_cast<unsigned short*>(cprefix + ncmax + 1);
     unsigned short* sp = hp + (size_t)nblk * kModes * (ncmax + 1);
     __shared__ int s_next, s_npairs;
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sidx = blockIdx.x;
@@ -182,29 +189,56 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
     const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
     const int nnc = s.nnc;
 
-    // ---- phase 1: clipped windows per column block; stage both R^k windows ----
-    for (int q = lane; q < nnc; q += 32)
-        for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
-    {
-        const int ns = s.nD + s.nX;
-        const size_t plane = (size_t)g.P * g.ldP;
-        for (int slot = tid; slot < ns; slot += NW * 32) {
-            const double* src = R + site_slot_source(g, s, slot);
-            int k = 0;
-            for (; k + 4 <= K1; k += 4) {
-                const double v0 = __ldg(src + (size_t)k * plane);
-                const double v1 = __ldg(src + (size_t)(k + 1) * plane);
-                const double v2 = __ldg(src + (size_t)(k + 2) * plane);
-                const double v3 = __ldg(src + (size_t)(k + 3) * plane);
-                Rv[(size_t)k * nsmax + slot] = v0;
-                Rv[(size_t)(k + 1) * nsmax + slot] = v1;
-                Rv[(size_t)(k + 2) * nsmax + slot] = v2;
-                Rv[(size_t)(k + 3) * nsmax + slot] = v3;
-            }
-            for (; k < K1; ++k) Rv[(size_t)k * nsmax + slot] = __ldg(src + (size_t)k * plane);
+    // ---- phase 0: both R^k windows of the site, [K1][2w+1][cpad] boxes of the tensor
+    //      R[k][p1][p2], dropped into shared memory by two TMA tile loads ----
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const bool wantX = s.dXlo <= pl.max_nd;  // else every exchange window is clipped away
+        const unsigned box_bytes = (unsigned)(K1 * s.kst * sizeof(double));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"(wantX ? 2 * box_bytes : box_bytes)
+                     : "memory");
+        const unsigned dstD = (unsigned)__cvta_generic_to_shared(Rv);
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dstD),
+            "l"(&tmapR), "r"(site_colD(g, s)), "r"(site_rowD(g, s)), "r"(0), "r"(bar)
+            : "memory");
+        if (wantX) {
+            const unsigned dstX = (unsigned)__cvta_generic_to_shared(Rv + s.xoff);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dstX),
+                "l"(&tmapR), "r"(site_colX(g, s)), "r"(site_rowX(g, s)), "r"(0), "r"(bar)
+                : "memory");
         }
     }
+    // ---- phase 1a: clipped windows per column block, candidate lists D and X,
+    //      slot prefix of list DX ----
+    if (warp == NW - 1) {
+        int run = 0;
+        for (int q0 = 0; q0 < nnc; q0 += 32) {
+            const int q = q0 + lane;
+            const int c = q < nnc ? site_cand_DX_count(s, q) : 0;
+            const int inc = warp_incl_scan(c, lane);
+            if (q < nnc) cprefix[q] = run + inc - c;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) cprefix[nnc] = run;
+    }
+    for (int q = lane; q < nnc; q += 32)
+        for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+    for (int t = tid; t < s.nD; t += NW * 32) listD[t] = site_cand_D(s, t);
+    for (int t = tid; t < s.nX; t += NW * 32) listX[t] = site_cand_X(s, t);
     __syncthreads();
+    // ---- phase 1b: list DX (CSR order over both windows) ----
+    for (int q = warp; q < nnc; q += NW) {
+        const int n = cprefix[q + 1] - cprefix[q], base = cprefix[q];
+        for (int idx = lane; idx < n; idx += 32) listDX[base + idx] = site_cand_DX(s, q, idx);
+    }
     // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode);
     //      one thread per (bj, mode), serial over the slots ----
     for (int task = tid; task < nblk * kModes; task += NW * 32) {
@@ -232,8 +266,9 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
     const int G = cap / nblk;  // rows per group (host guarantees >= 1)
     double* const Hd = reinterpret_cast<double*>(Hdat);
     double* const Sd = reinterpret_cast<double*>(Sdat);
-    const int lpw = lay.lanes_per_slot;          // lanes per n_c slot in the single-window modes
-    const int sub = lane / lpw, idx1 = lane - sub * lpw, spi = 32 / lpw;
+    // first live candidate of each list when n_c < n_a is cut away (diagonal pair, j >= i)
+    const int cutD = (s.na - s.cDlo) * s.dw;
+    const int cutX = imin(s.nX, imax(0, s.na - s.cXlo) * s.xw);
 
     for (int g0 = 0; g0 < nr; g0 += G) {
         const int gr = imin(G, nr - g0);
@@ -274,6 +309,15 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
         }
         __syncthreads();
         const int npairs = s_npairs;
+        if (g0 == 0) {  // the staged windows must have landed
+            unsigned done = 0;
+            while (!done)
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(done)
+                    : "r"(bar)
+                    : "memory");
+        }
         // ---- phase 4: fill ----
         for (;;) {
             int p = 0;
@@ -304,38 +348,27 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, Site
             pc.Rv = Rv;
             pc.wa_d = wang;
             pc.wa_x = wang + K1;
-            pc.nsmax = nsmax;
+            pc.kst = s.kst;
             pc.bj = bj;
             pc.diag = mode == kModeDiag;
             pc.dirany = (fl & kDirAny) != 0;
             pc.exany = (fl & kExAny) != 0;
             pc.samex = pc.diag && r.la == r.lb;
             pc.cut = pc.diag && !pl.full;
-            {
-                const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
-                pc.win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
-            }
             pc.hbase = rc.hbase + pe.y;
             pc.sbase = rc.sbase;
-            const Segs segs = pair_segments(s, pc.win, pc.cut);
-            for (int t = 0; t < 3; ++t) {
-                const Seg sg = segs_at(segs, t);
-                const int q0 = sg.q0, q1 = sg.q1, win = sg.win;
-                if (win != kModeDX) {
-                    // one window: lpw lanes per n_c slot, 32/lpw slots per step
-                    for (int qb = q0; qb < q1; qb += spi) {
-                        const int q = qb + sub;
-                        if (q < q1) site_lane<false>(g, pl, ob, s, r, pc, win, q, idx1, 0, Hidx, Hd, Sidx, Sd);
-                    }
-                } else {
-                    // union of both windows: one slot per step, <= 2*(2w+1) <= 64 entries
-                    for (int q = q0; q < q1; ++q) {
-                        const int cnt = (int)pc.hpq[q + 1] - (int)pc.hpq[q];
-                        if (cnt == 0) continue;
-                        site_lane<true>(g, pl, ob, s, r, pc, win, q, lane, cnt, Hidx, Hd, Sidx, Sd);
-                        if (cnt > 32) site_lane<true>(g, pl, ob, s, r, pc, win, q, lane + 32, cnt, Hidx, Hd, Sidx, Sd);
-                    }
-                }
+            const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
+            const int win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
+            if (win == kModeD) {
+                for (int t = (pc.cut ? cutD : 0) + lane; t < s.nD; t += 32)
+                    site_item<kModeD>(g, pl, ob, s, r, pc, listD[t], Hidx, Hd, Sidx, Sd);
+            } else if (win == kModeX) {
+                for (int t = (pc.cut ? cutX : 0) + lane; t < s.nX; t += 32)
+                    site_item<kModeX>(g, pl, ob, s, r, pc, listX[t], Hidx, Hd, Sidx, Sd);
+            } else {
+                const int ncand = cprefix[nnc];
+                for (int t = (pc.cut ? cprefix[union_pos(s, s.na)] : 0) + lane; t < ncand; t += 32)
+                    site_item<kModeDX>(g, pl, ob, s, r, pc, listDX[t], Hidx, Hd, Sidx, Sd);
             }
         }
     }
@@ -437,6 +470,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         pl.row_n1 = b->d_row_n1;
         pl.row_n2 = b->d_row_n2;
         pl.row_blk = b->d_row_blk;
+        pl.max_nd = hp.max_nd;
 
         const long long nrows = row_hi - row_lo + 1;
         b->d_cntH = dev_alloc<long long>(nrows + 1);
@@ -473,13 +507,10 @@ void block_assemble(bs2e_block* b)
     constexpr int NW = kSiteWarps;
     const Geom& g = c->dg;
     const char* mode = getenv("BS2E_FILL");
-    bool use_site = b->nsites > 0 && !(mode && strcmp(mode, "row") == 0) && 2 * g.w + 1 <= 32;
+    bool use_site = b->nsites > 0 && c->have_tmap && !(mode && strcmp(mode, "row") == 0) && site_max_nc(g) <= 255;
     SiteSmem lay{};
     if (use_site) {
         lay.nsmax = site_max_slots(g);
-        lay.lanes_per_slot = 1;
-        while (lay.lanes_per_slot < 2 * g.w + 1) lay.lanes_per_slot *= 2;
-        lay.wide_two_pass = 2 * (2 * g.w + 1) > 32;
         lay.ncmax = site_max_nc(g);
         const int cap_want = std::max(b->dplan.nblk, std::min(2048, b->dplan.nblk * b->dplan.nblk));
         lay.cap = cap_want;
@@ -488,14 +519,15 @@ void block_assemble(bs2e_block* b)
             lay.cap = b->dplan.nblk;
             lay.bytes = site_smem_bytes(g, b->dplan.nblk, NW, lay.cap);
         }
-        if (lay.bytes > kSiteSmemLimit || 2 * site_max_slots(g) > 65535 || b->dplan.nblk > 4095) use_site = false;
+        if (lay.bytes > kSiteSmemLimit || 2 * site_win_doubles(g) + site_kst(g) > 65535 || b->dplan.nblk > 4095)
+            use_site = false;
     }
     if (use_site) {
         BS2E_CUDA(cudaFuncSetAttribute(site_fill_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)lay.bytes));
         const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
         site_fill_kernel<NW><<<(unsigned)b->nsites, NW * 32, lay.bytes, c->stream>>>(
-            c->dg, b->dplan, c->one_body(), c->d_R, sl, lay, b->row_lo, b->d_Hptr, b->d_Sptr, b->d_Hidx,
+            c->tmapR, c->dg, b->dplan, c->one_body(), sl, lay, b->row_lo, b->d_Hptr, b->d_Sptr, b->d_Hidx,
             reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
     } else {
         block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,

@@ -235,6 +235,7 @@ struct Plan {
     int n_config;
     int full;
     int L;
+    int max_nd;                  // largest n_2 of any configuration of the block list
     const BlockDesc* blk;        // [nblk]
     const NcRow* ncrow;          // [nblk][nb+1], index n_c
     const unsigned char* flags;  // [nblk][nblk]

@@ -178,6 +178,8 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
     hp.n_config = n_config;
     hp.lmax = 0;
     for (auto& d : blocks) hp.lmax = d.l1 > hp.lmax ? d.l1 : hp.lmax;
+    hp.max_nd = 0;
+    for (auto v : rn2) hp.max_nd = v > hp.max_nd ? v : hp.max_nd;
     hp.blocks = std::move(blocks);
     hp.ncrow = std::move(ncrow);
     hp.flags = std::move(flags);
@@ -197,6 +199,7 @@ Plan HostPlan::view() const
     pl.n_config = (int)n_config;
     pl.full = full;
     pl.L = L;
+    pl.max_nd = max_nd;
     pl.blk = blocks.data();
     pl.ncrow = ncrow.data();
     pl.flags = flags.data();

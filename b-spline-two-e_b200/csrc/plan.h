@@ -8,7 +8,7 @@
 namespace bs2e {
 
 struct HostPlan {
-    int nblk = 0, L = 0, full = 0, lmax = 0;
+    int nblk = 0, L = 0, full = 0, lmax = 0, max_nd = 0;
     long long n_config = 0;
     std::vector<BlockDesc> blocks;
     std::vector<NcRow> ncrow;

@@ -21,9 +21,20 @@ struct Site {
     int na, nb;
     Union2 ncu;  // n_c values of the candidates (union of the two n_c windows)
     int nnc;     // number of n_c slots
-    int cDlo, cDhi, dDlo, dDhi, dw, nD;  // D window: n_c range, n_d range, width, slots
+    int cDlo, cDhi, dDlo, dDhi, dw, nD;  // D window: n_c range, n_d range, width, entries
     int cXlo, cXhi, dXlo, dXhi, xw, nX;  // X window
+    // staged R^k values: Rv[win*xoff + k*kst + r*cpad + c], r = n_c - first n_c of the
+    // window, c = n_d - first n_d (the box a TMA tile load drops into shared memory)
+    // The first column of a TMA box must be 16-byte aligned, so a box starts at the even
+    // column below the window and shD / shX (0 or 1) is the window's offset inside it.
+    int cpad, kst, xoff, shD, shX;
 };
+
+// padded column count of a staged window (TMA: inner box extent must be a multiple of 16 B)
+BS2E_HD int site_cpad(const Geom& g) { return 2 * g.w + 2; }  // 2w+1 columns + 1 for the alignment shift
+BS2E_HD int site_kst(const Geom& g) { return (2 * g.w + 1) * site_cpad(g); }
+// doubles per staged window, rounded so that the second window stays 128-byte aligned
+BS2E_HD int site_win_doubles(const Geom& g) { return (g.K1 * site_kst(g) + 15) & ~15; }
 
 BS2E_HD Site make_site(const Geom& g, int na, int nb)
 {
@@ -38,6 +49,11 @@ BS2E_HD Site make_site(const Geom& g, int na, int nb)
     s.xw = s.dXhi - s.dXlo + 1;
     s.nD = (s.cDhi - s.cDlo + 1) * s.dw;
     s.nX = (s.cXhi - s.cXlo + 1) * s.xw;
+    s.cpad = site_cpad(g);
+    s.kst = site_kst(g);
+    s.xoff = site_win_doubles(g);
+    s.shD = pair_index(g, nb, s.dDlo) & 1;
+    s.shX = pair_index(g, na, s.dXlo) & 1;
     s.ncu = union2(s.cDlo, s.cDhi, s.cXlo, s.cXhi);
     s.nnc = union2_count(s.ncu);
     return s;
@@ -65,20 +81,16 @@ BS2E_HD Union2 site_nd_union(const Site& s, int nc)
 }
 
 // slot of a column (n_c,n_d) in the staged D / X window (caller guarantees membership)
-BS2E_HD int site_slotD(const Site& s, int nc, int nd) { return (nc - s.cDlo) * s.dw + (nd - s.dDlo); }
-BS2E_HD int site_slotX(const Site& s, int nc, int nd) { return s.nD + (nc - s.cXlo) * s.xw + (nd - s.dXlo); }
+BS2E_HD int site_slotD(const Site& s, int nc, int nd) { return (nc - s.cDlo) * s.cpad + (nd - s.dDlo) + s.shD; }
+BS2E_HD int site_slotX(const Site& s, int nc, int nd) { return s.xoff + (nc - s.cXlo) * s.cpad + (nd - s.dXlo) + s.shX; }
 
-// address of the R^k(k=0) value that fills a slot; add k*P*ldP for multipole k
-BS2E_HD size_t site_slot_source(const Geom& g, const Site& s, int slot)
-{
-    if (slot < s.nD) {
-        const int nc = s.cDlo + slot / s.dw, nd = s.dDlo + slot % s.dw;
-        return (size_t)pair_index(g, s.na, nc) * g.ldP + pair_index(g, s.nb, nd);
-    }
-    const int t = slot - s.nD;
-    const int nc = s.cXlo + t / s.xw, nd = s.dXlo + t % s.xw;
-    return (size_t)pair_index(g, s.nb, nc) * g.ldP + pair_index(g, s.na, nd);
-}
+// first row / column of R (pair indices) of the staged windows: window D holds
+// R^k[pair(n_a,n_c)][pair(n_b,n_d)], window X holds R^k[pair(n_b,n_c)][pair(n_a,n_d)]
+// (the exchange integral read through R^k(ab;dc) = R^k(ba;cd))
+BS2E_HD int site_rowD(const Geom& g, const Site& s) { return pair_index(g, s.na, s.cDlo); }
+BS2E_HD int site_colD(const Geom& g, const Site& s) { return pair_index(g, s.nb, s.dDlo) & ~1; }
+BS2E_HD int site_rowX(const Geom& g, const Site& s) { return pair_index(g, s.nb, s.cXlo); }
+BS2E_HD int site_colX(const Geom& g, const Site& s) { return pair_index(g, s.na, s.dXlo) & ~1; }
 
 // ---- per (site, column block) tables ---------------------------------------
 // Clipping of the two windows by the configurations that exist in column block
@@ -156,53 +168,75 @@ BS2E_HD int entry_count(const SiteEntry& e, bool useD, bool useX)
     return union_below(useD, e.dlo, e.dhi, useX, e.xlo, e.xhi, 0x7fffffff);
 }
 
-// rho-th (0-based, ascending) stored n_d of the entry
-BS2E_HD int entry_nd(const SiteEntry& e, bool useD, bool useX, int rho)
+// position of n_c value v in the ascending union of the two n_c ranges
+BS2E_HD int union_pos(const Site& s, int v)
 {
-    const Union2 u = union2(useD ? (int)e.dlo : 1, useD ? (int)e.dhi : 0,
-                            useX ? (int)e.xlo : 1, useX ? (int)e.xhi : 0);
-    return union2_at(u, rho);
+    return below(s.cDlo, s.cDhi, v) + below(s.cXlo, s.cXhi, v) -
+           below(imax(s.cDlo, s.cXlo), imin(s.cDhi, s.cXhi), v);
 }
 
-// largest q in [0,nnc) with prefix[q] <= o  (prefix ascending, prefix[0] = 0)
-BS2E_HD int prefix_search(const unsigned short* prefix, int nnc, int top, int o)
+// ---- candidate lists of a site ------------------------------------------------
+// The columns (n_c,n_d) a row of the site can couple to, in CSR order (n_c, then
+// n_d ascending), independent of the column block: list D = direct window, list X =
+// exchange window, list DX = union.  One entry: a = q | n_d << 8,
+// b = slotD | slotX << 16 (0xffff: the column is not in that window).
+struct alignas(8) Cand { unsigned a, b; };
+constexpr unsigned kNoSlot = 0xffffu;
+
+BS2E_HD Cand site_cand(const Site& s, int q, int nc, int nd)
 {
-    int q = 0;
-    for (int st = top; st > 0; st >>= 1) {
-        const int m = q + st;
-        if (m < nnc && (int)prefix[m] <= o) q = m;
-    }
-    return q;
+    Cand c;
+    c.a = (unsigned)q | ((unsigned)nd << 8);
+    unsigned sd = kNoSlot, sx = kNoSlot;
+    if (site_nc_inD(s, nc) && nd >= s.dDlo && nd <= s.dDhi) sd = (unsigned)site_slotD(s, nc, nd);
+    if (site_nc_inX(s, nc) && nd >= s.dXlo && nd <= s.dXhi) sx = (unsigned)site_slotX(s, nc, nd);
+    c.b = sd | (sx << 16);
+    return c;
 }
-BS2E_HD int search_top(int nnc)
+BS2E_HD int cand_q(const Cand& c) { return (int)(c.a & 0xffu); }
+BS2E_HD int cand_nd(const Cand& c) { return (int)(c.a >> 8); }
+BS2E_HD unsigned cand_slotD(const Cand& c) { return c.b & 0xffffu; }
+BS2E_HD unsigned cand_slotX(const Cand& c) { return c.b >> 16; }
+
+// entry t of list D / list X (row-major over the window = slot order)
+BS2E_HD Cand site_cand_D(const Site& s, int t)
 {
-    int top = 1;
-    while (top * 2 < nnc) top *= 2;
-    return top;
+    const int nc = s.cDlo + t / s.dw, nd = s.dDlo + t % s.dw;
+    return site_cand(s, union_pos(s, nc), nc, nd);
+}
+BS2E_HD Cand site_cand_X(const Site& s, int t)
+{
+    const int nc = s.cXlo + t / s.xw, nd = s.dXlo + t % s.xw;
+    return site_cand(s, union_pos(s, nc), nc, nd);
+}
+// number of entries of n_c slot q in list DX, and its idx-th entry
+BS2E_HD int site_cand_DX_count(const Site& s, int q) { return union2_count(site_nd_union(s, site_nc(s, q))); }
+BS2E_HD Cand site_cand_DX(const Site& s, int q, int idx)
+{
+    const int nc = site_nc(s, q);
+    return site_cand(s, q, nc, union2_at(site_nd_union(s, nc), idx));
 }
 
-// ---- one stored entry of a (row, column block) pair --------------------------
+// ---- one (row, column block) pair ---------------------------------------------
 // Everything that is uniform over the pair.  Pointers into shared memory in the
 // kernel, into plain arrays in the CPU checker.
 struct PairCtx {
     const SiteEntry* Tb;        // [nnc] clipped windows of the column block
     const unsigned short* hpq;  // [nnc+1] prefix of stored H entries over the n_c slots
     const unsigned short* spq;  // [nnc]   same for S (diagonal pair only)
-    const double* Rv;           // staged R^k values, Rv[k*nsmax + slot]
+    const double* Rv;           // staged R^k values, Rv[k*kst + slot]
     const double* wa_d;         // packed direct factors, k = pk.dlo + 2i
     const double* wa_x;         // packed exchange factors
-    int nsmax;
+    int kst;
     PairK pk;
     int bj;
-    int win;                    // single-window form: kModeD or kModeX; else kModeDX
     bool diag;                  // column block == row block: one-body terms and S
     bool dirany, exany, samex, cut;
     long long hbase, sbase;     // first H entry of the pair / first S entry of the row
 };
 
-// How a pair is walked: with one window only (all entries of the other window are
-// clipped away for this site and column block, or the mode stores one window) the
-// n_c slots hold <= 2w+1 consecutive n_d; otherwise the union of both windows.
+// Which list a pair walks: one window when the mode stores one window or when the
+// other window is clipped away completely for this site and column block.
 BS2E_HD int pair_window(int mode, int totD, int totX)
 {
     if (mode == kModeD || mode == kModeX) return mode;
@@ -211,88 +245,36 @@ BS2E_HD int pair_window(int mode, int totD, int totX)
     return kModeDX;
 }
 
-// position of n_c value v in the ascending union of the two n_c ranges
-BS2E_HD int union_pos(const Site& s, int v)
+// One candidate of the pair's list.  LIST = kModeD / kModeX: every stored entry lies
+// in that window; LIST = kModeDX: union of both windows.
+template <int LIST>
+BS2E_HD void site_item(const Geom& g, const Plan& pl, const OneBody& ob, const Site& s,
+                       const RowInfo& r, const PairCtx& pc, Cand cd, long long* Hidx, double* Hdat,
+                       long long* Sidx, double* Sdat)
 {
-    return below(s.cDlo, s.cDhi, v) + below(s.cXlo, s.cXhi, v) -
-           below(imax(s.cDlo, s.cXlo), imin(s.cDhi, s.cXhi), v);
-}
-
-// A pair is walked in <= 3 segments of consecutive n_c slots [q0,q1): slots that lie in
-// one n_c range only hold one window (win = kModeD / kModeX, <= 2w+1 consecutive n_d);
-// slots in both ranges (|n_a - n_b| <= 2w) hold the union (win = kModeDX).
-struct Seg { int q0, q1, win; };
-struct Segs { Seg a, b, c; };  // ascending n_c; empty segments have q1 <= q0
-BS2E_HD Seg segs_at(const Segs& g3, int t) { return t == 0 ? g3.a : (t == 1 ? g3.b : g3.c); }
-
-BS2E_HD Seg seg_of_range(const Site& s, int lo, int hi, int win)
-{
-    Seg r;
-    r.q0 = union_pos(s, lo);
-    r.q1 = hi >= lo ? union_pos(s, hi) + 1 : r.q0;
-    r.win = win;
-    return r;
-}
-
-BS2E_HD Segs pair_segments(const Site& s, int win, bool cut)
-{
-    Segs o;
-    o.a = o.b = o.c = Seg{0, 0, kModeD};
-    if (win == kModeD) {
-        o.a = seg_of_range(s, s.cDlo, s.cDhi, kModeD);
-    } else if (win == kModeX) {
-        o.a = seg_of_range(s, s.cXlo, s.cXhi, kModeX);
-    } else {
-        const int ilo = imax(s.cDlo, s.cXlo), ihi = imin(s.cDhi, s.cXhi);
-        const bool dlow = s.cDlo <= s.cXlo, dhigh = s.cDhi > s.cXhi;
-        if (ihi < ilo) {  // disjoint n_c ranges
-            o.a = seg_of_range(s, dlow ? s.cDlo : s.cXlo, dlow ? s.cDhi : s.cXhi, dlow ? kModeD : kModeX);
-            o.c = seg_of_range(s, dlow ? s.cXlo : s.cDlo, dlow ? s.cXhi : s.cDhi, dlow ? kModeX : kModeD);
-        } else {
-            o.a = seg_of_range(s, imin(s.cDlo, s.cXlo), ilo - 1, dlow ? kModeD : kModeX);
-            o.b = seg_of_range(s, ilo, ihi, kModeDX);
-            o.c = seg_of_range(s, ihi + 1, imax(s.cDhi, s.cXhi), dhigh ? kModeD : kModeX);
-        }
-    }
-    if (cut) {  // slots with n_c < n_a are cut away (j >= i)
-        const int qc = union_pos(s, s.na);
-        o.a.q0 = imax(o.a.q0, qc);
-        o.b.q0 = imax(o.b.q0, qc);
-        o.c.q0 = imax(o.c.q0, qc);
-    }
-    return o;
-}
-
-// entry number idx (ascending n_d) of n_c slot q.  WIDE = false: one window (win);
-// WIDE = true: union of both windows, cnt = number of entries of the slot.
-template <bool WIDE>
-BS2E_HD void site_lane(const Geom& g, const Plan& pl, const OneBody& ob, const Site& s,
-                       const RowInfo& r, const PairCtx& pc, int win, int q, int idx, int cnt,
-                       long long* Hidx, double* Hdat, long long* Sidx, double* Sdat)
-{
+    const int q = cand_q(cd), nd = cand_nd(cd);
     SiteEntry e = pc.Tb[q];
-    const int nc = site_nc(s, q);
-    if (pc.cut) e = entry_cut(e, s, nc);
-    int nd;
-    if (!WIDE) {
-        const int lo = win == kModeD ? (int)e.dlo : (int)e.xlo;
-        const int hi = win == kModeD ? (int)e.dhi : (int)e.xhi;
-        nd = lo + idx;
-        if (nd > hi) return;
+    if (pc.cut) e = entry_cut(e, s, site_nc(s, q));
+    const bool sup = nd >= (int)e.dlo && nd <= (int)e.dhi;
+    const bool sup_ex = nd >= (int)e.xlo && nd <= (int)e.xhi;
+    int rank;
+    if (LIST == kModeD) {
+        if (!sup) return;
+        rank = nd - (int)e.dlo;
+    } else if (LIST == kModeX) {
+        if (!sup_ex) return;
+        rank = nd - (int)e.xlo;
     } else {
-        if (idx >= cnt) return;
-        nd = entry_nd(e, true, true, idx);
+        if (!sup && !sup_ex) return;
+        rank = union_below(true, e.dlo, e.dhi, true, e.xlo, e.xhi, nd);
     }
-    // inside the stored set the clipping is common to both windows
-    const bool sup = site_nc_inD(s, nc) && nd >= s.dDlo && nd <= s.dDhi;
-    const bool sup_ex = site_nc_inX(s, nc) && nd >= s.dXlo && nd <= s.dXhi;
-    const int stride = 2 * pc.nsmax;
+    const int stride = 2 * pc.kst;
     double re = 0.0, im = 0.0;
     const bool allowed = (sup && pc.dirany) || (sup_ex && pc.exany);
     if (allowed) {
         double res = 0.0;
-        if (sup) res += k_dot(pc.Rv + pc.pk.dlo * pc.nsmax + site_slotD(s, nc, nd), stride, pc.wa_d, pc.pk.nkd);
-        if (sup_ex) res += k_dot(pc.Rv + pc.pk.xlo * pc.nsmax + site_slotX(s, nc, nd), stride, pc.wa_x, pc.pk.nkx);
+        if (sup) res += k_dot(pc.Rv + pc.pk.dlo * pc.kst + cand_slotD(cd), stride, pc.wa_d, pc.pk.nkd);
+        if (sup_ex) res += k_dot(pc.Rv + pc.pk.xlo * pc.kst + cand_slotX(cd), stride, pc.wa_x, pc.pk.nkx);
         re = res;
     }
     const long long j = (long long)e.jbase + nd;
@@ -301,7 +283,7 @@ BS2E_HD void site_lane(const Geom& g, const Plan& pl, const OneBody& ob, const S
         if (storeS) {
             const BlockDesc bc = pl.blk[pc.bj];
             Cplx h, sv;
-            one_body_terms(g, pl, ob, r, true, pc.samex, bc.l1, bc.l2, nc, nd, &h, &sv);
+            one_body_terms(g, pl, ob, r, true, pc.samex, bc.l1, bc.l2, site_nc(s, q), nd, &h, &sv);
             re += h.re;
             im += h.im;
             const long long pos =
@@ -311,7 +293,7 @@ BS2E_HD void site_lane(const Geom& g, const Plan& pl, const OneBody& ob, const S
             Sdat[2 * pos + 1] = sv.im;
         }
     }
-    const long long pos = pc.hbase + pc.hpq[q] + idx;
+    const long long pos = pc.hbase + pc.hpq[q] + rank;
     Hidx[pos] = j;
 #if defined(__CUDA_ARCH__)
     *reinterpret_cast<double2*>(Hdat + 2 * pos) = make_double2(re, im);

@@ -228,45 +228,66 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
         const double* R = c->R.data();
         const int K1 = g.K1, nsmax = site_max_slots(g), ncmax = site_max_nc(g), nblk = pl.nblk;
         const size_t plane = (size_t)g.P * g.ldP;
-        int lpw = 1;
-        while (lpw < 2 * g.w + 1) lpw *= 2;
-        if (lpw > 32) throw std::logic_error("site kernel needs 2w+1 <= 32");
-        const int spi = 32 / lpw;
-        std::vector<double> Rv((size_t)nsmax * K1);
+        std::vector<double> Rv(2 * (size_t)site_win_doubles(g)), wang(2 * K1);
         std::vector<SiteEntry> T((size_t)nblk * ncmax);
+        std::vector<Cand> listD(nsmax / 2), listX(nsmax / 2), listDX(nsmax);
+        std::vector<int> cprefix(ncmax + 1);
         std::vector<unsigned short> hp((size_t)nblk * kModes * (ncmax + 1)), sp((size_t)nblk * (ncmax + 1));
+        long long* Hi = reinterpret_cast<long long*>(H_idx);
+        long long* Si = reinterpret_cast<long long*>(S_idx);
         const int nsites = (int)hp_.site_key.size();
         long long rows_seen = 0;
         for (int sidx = 0; sidx < nsites; ++sidx) {
             const unsigned key = hp_.site_key[sidx];
             const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
             const int nnc = s.nnc;
-            if (nnc > ncmax || s.nD + s.nX > nsmax) throw std::logic_error("site exceeds smem bounds");
+            if (nnc > ncmax || s.nD + s.nX > nsmax || s.nD > nsmax / 2 || s.nX > nsmax / 2)
+                throw std::logic_error("site exceeds smem bounds");
             // phase 1
+            int run = 0;
+            for (int q = 0; q < nnc; ++q) { cprefix[q] = run; run += site_cand_DX_count(s, q); }
+            cprefix[nnc] = run;
+            if (run > nsmax) throw std::logic_error("list DX exceeds smem bound");
             for (int bj = 0; bj < nblk; ++bj)
                 for (int q = 0; q < nnc; ++q) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+            for (int t = 0; t < s.nD; ++t) listD[t] = site_cand_D(s, t);
+            for (int t = 0; t < s.nX; ++t) listX[t] = site_cand_X(s, t);
+            for (int q = 0; q < nnc; ++q)
+                for (int idx = 0; idx < cprefix[q + 1] - cprefix[q]; ++idx)
+                    listDX[cprefix[q] + idx] = site_cand_DX(s, q, idx);
+            // phase 0: the two boxes a TMA tile load delivers (zero fill outside the tensor)
             std::fill(Rv.begin(), Rv.end(), -9.0);
-            for (int slot = 0; slot < s.nD + s.nX; ++slot)
+            for (int win = 0; win < 2; ++win) {
+                const int row0 = win ? site_rowX(g, s) : site_rowD(g, s);
+                const int col0 = win ? site_colX(g, s) : site_colD(g, s);
                 for (int k = 0; k < K1; ++k)
-                    Rv[(size_t)k * nsmax + slot] = R[site_slot_source(g, s, slot) + (size_t)k * plane];
+                    for (int rr = 0; rr < 2 * g.w + 1; ++rr)
+                        for (int cc = 0; cc < s.cpad; ++cc) {
+                            const bool in = row0 + rr < g.P && col0 + cc < g.ldP;
+                            Rv[(size_t)win * s.xoff + (size_t)k * s.kst + rr * s.cpad + cc] =
+                                in ? R[(size_t)k * plane + (size_t)(row0 + rr) * g.ldP + col0 + cc] : 0.0;
+                        }
+            }
             // phase 2
             for (int task = 0; task < nblk * kModes; ++task) {
                 const int bj = task / kModes, mode = task - bj * kModes;
                 const bool useD = mode_useD(mode), useX = mode_useX(mode), diag = mode == kModeDiag;
                 const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
-                int run = 0, srun = 0;
+                int hrun = 0, srun = 0;
                 for (int q = 0; q < nnc; ++q) {
                     SiteEntry e = T[bj * ncmax + q];
                     if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
-                    hp[(size_t)task * (ncmax + 1) + q] = (unsigned short)run;
-                    run += entry_count(e, useD, useX);
+                    hp[(size_t)task * (ncmax + 1) + q] = (unsigned short)hrun;
+                    hrun += entry_count(e, useD, useX);
                     if (diag) {
                         sp[(size_t)bj * (ncmax + 1) + q] = (unsigned short)srun;
                         srun += entry_count(e, true, samex);
                     }
                 }
-                hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)run;
+                hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)hrun;
             }
+            const int cutD = (s.na - s.cDlo) * s.dw;
+            const int cutX = imin(s.nX, imax(0, s.na - s.cXlo) * s.xw);
             for (int ri = hp_.site_ptr[sidx]; ri < hp_.site_ptr[sidx + 1]; ++ri) {
                 const int rowi = hp_.site_rows[ri];
                 ++rows_seen;
@@ -274,7 +295,6 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                 if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
                 const long long wrow = rowi - row_lo;
                 int offrun = 0;  // phase 3 (running form of the scan over column blocks)
-                std::vector<double> wang(2 * K1);
                 for (int bj = 0; bj < nblk; ++bj) {
                     int mode = pair_mode(pl, r, bj);
                     if (mode < 0) continue;
@@ -285,55 +305,35 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                     // phase 4
                     const int cpl = r.bi * nblk + bj;
                     const unsigned char fl = pl.flags[cpl];
-                    const PairK pk = pair_k(pl.krange[cpl]);
-                    for (int i = 0; i < pk.nkd; ++i) wang[i] = pl.angD[(size_t)cpl * K1 + pk.dlo + 2 * i];
-                    for (int i = 0; i < pk.nkx; ++i) wang[K1 + i] = pl.angX[(size_t)cpl * K1 + pk.xlo + 2 * i];
                     PairCtx pc;
+                    pc.pk = pair_k(pl.krange[cpl]);
+                    for (int i = 0; i < pc.pk.nkd; ++i) wang[i] = pl.angD[(size_t)cpl * K1 + pc.pk.dlo + 2 * i];
+                    for (int i = 0; i < pc.pk.nkx; ++i) wang[K1 + i] = pl.angX[(size_t)cpl * K1 + pc.pk.xlo + 2 * i];
                     pc.Tb = T.data() + bj * ncmax;
                     pc.hpq = hp.data() + (bj * kModes + mode) * (ncmax + 1);
                     pc.spq = sp.data() + bj * (ncmax + 1);
                     pc.Rv = Rv.data();
                     pc.wa_d = wang.data();
                     pc.wa_x = wang.data() + K1;
-                    pc.nsmax = nsmax;
-                    pc.pk = pk;
+                    pc.kst = s.kst;
                     pc.bj = bj;
                     pc.diag = mode == kModeDiag;
                     pc.dirany = (fl & kDirAny) != 0;
                     pc.exany = (fl & kExAny) != 0;
                     pc.samex = pc.diag && r.la == r.lb;
                     pc.cut = pc.diag && !pl.full;
-                    pc.win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
                     pc.hbase = H_ptr[wrow] - 1 + offrun;
                     pc.sbase = S_ptr[wrow] - 1;
-                    long long* Hi = reinterpret_cast<long long*>(H_idx);
-                    long long* Si = reinterpret_cast<long long*>(S_idx);
-                    const Segs segs = pair_segments(s, pc.win, pc.cut);
-                    const int nseg = 3;
-                    Seg seg[3] = {segs_at(segs, 0), segs_at(segs, 1), segs_at(segs, 2)};
-                    for (int q = 0; q < nnc; ++q) {  // slots outside the segments must be empty
-                        bool covered = false;
-                        for (int t = 0; t < nseg; ++t) covered = covered || (q >= seg[t].q0 && q < seg[t].q1);
-                        if (!covered && pc.hpq[q + 1] != pc.hpq[q])
-                            throw std::logic_error("pair_segments misses a populated n_c slot");
-                    }
-                    for (int t = 0; t < nseg; ++t) {
-                        const int q0 = seg[t].q0, q1 = seg[t].q1, win = seg[t].win;
-                        if (win != kModeDX) {
-                            for (int qb = q0; qb < q1; qb += spi)
-                                for (int lane = 0; lane < 32; ++lane) {
-                                    const int sub = lane / lpw, idx1 = lane - sub * lpw, q = qb + sub;
-                                    if (q < q1)
-                                        site_lane<false>(g, pl, ob, s, r, pc, win, q, idx1, 0, Hi, H_dat, Si, S_dat);
-                                }
-                        } else {
-                            for (int q = q0; q < q1; ++q) {
-                                const int cnt = (int)pc.hpq[q + 1] - (int)pc.hpq[q];
-                                for (int lane = 0; lane < 64; ++lane)
-                                    if (lane < 32 || cnt > 32)
-                                        site_lane<true>(g, pl, ob, s, r, pc, win, q, lane, cnt, Hi, H_dat, Si, S_dat);
-                            }
-                        }
+                    const int win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
+                    if (win == kModeD) {
+                        for (int t = pc.cut ? cutD : 0; t < s.nD; ++t)
+                            site_item<kModeD>(g, pl, ob, s, r, pc, listD[t], Hi, H_dat, Si, S_dat);
+                    } else if (win == kModeX) {
+                        for (int t = pc.cut ? cutX : 0; t < s.nX; ++t)
+                            site_item<kModeX>(g, pl, ob, s, r, pc, listX[t], Hi, H_dat, Si, S_dat);
+                    } else {
+                        for (int t = pc.cut ? cprefix[union_pos(s, s.na)] : 0; t < cprefix[nnc]; ++t)
+                            site_item<kModeDX>(g, pl, ob, s, r, pc, listDX[t], Hi, H_dat, Si, S_dat);
                     }
                     offrun += total;
                 }
