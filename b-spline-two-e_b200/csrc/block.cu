@@ -192,11 +192,12 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
     // ---- phase 0: both R^k windows of the site, [K1][2w+1][cpad] boxes of the tensor
     //      R[k][p1][p2], dropped into shared memory by two TMA tile loads ----
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    // if n_a - w exceeds every n_2 of the basis, all exchange windows of the site are clipped away
+    const bool wantX = s.dXlo <= pl.max_nd;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const bool wantX = s.dXlo <= pl.max_nd;  // else every exchange window is clipped away
         const unsigned box_bytes = (unsigned)(K1 * s.kst * sizeof(double));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
                      "r"(wantX ? 2 * box_bytes : box_bytes)
@@ -218,7 +219,7 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
     }
     // ---- phase 1a: clipped windows per column block, candidate lists D and X,
     //      slot prefix of list DX ----
-    if (warp == NW - 1) {
+    if (warp == NW - 1 && wantX) {
         int run = 0;
         for (int q0 = 0; q0 < nnc; q0 += 32) {
             const int q = q0 + lane;
@@ -232,10 +233,11 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
     for (int q = lane; q < nnc; q += 32)
         for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
     for (int t = tid; t < s.nD; t += NW * 32) listD[t] = site_cand_D(s, t);
-    for (int t = tid; t < s.nX; t += NW * 32) listX[t] = site_cand_X(s, t);
+    if (wantX)
+        for (int t = tid; t < s.nX; t += NW * 32) listX[t] = site_cand_X(s, t);
     __syncthreads();
     // ---- phase 1b: list DX (CSR order over both windows) ----
-    for (int q = warp; q < nnc; q += NW) {
+    for (int q = warp; wantX && q < nnc; q += NW) {
         const int n = cprefix[q + 1] - cprefix[q], base = cprefix[q];
         for (int idx = lane; idx < n; idx += 32) listDX[base + idx] = site_cand_DX(s, q, idx);
     }
@@ -243,6 +245,7 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
     //      one thread per (bj, mode), serial over the slots ----
     for (int task = tid; task < nblk * kModes; task += NW * 32) {
         const int bj = task / kModes, mode = task - bj * kModes;
+        if (!wantX && (mode == kModeX || mode == kModeDX)) continue;  // never read, see tot_of()
         const bool useD = mode_useD(mode), useX = mode_useX(mode);
         const bool diag = mode == kModeDiag;
         const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
@@ -291,8 +294,8 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
                     mode = pair_mode(pl, r, bj);
                     if (mode >= 0) {
                         const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
-                        mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
-                        c = hb[mode * (ncmax + 1)];
+                        mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
+                        c = (wantX || mode != kModeX) ? hb[mode * (ncmax + 1)] : 0;
                     }
                 }
                 const int inc = warp_incl_scan(c, lane);
@@ -358,7 +361,7 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
             pc.hbase = rc.hbase + pe.y;
             pc.sbase = rc.sbase;
             const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
-            const int win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
+            const int win = pair_window(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
             if (win == kModeD) {
                 for (int t = (pc.cut ? cutD : 0) + lane; t < s.nD; t += 32)
                     site_item<kModeD>(g, pl, ob, s, r, pc, listD[t], Hidx, Hd, Sidx, Sd);
