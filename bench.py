@@ -253,14 +253,14 @@ def run_ours(args):
     value = total_elems * K / (tC * 1e-3)
     rk_per_s = n_rk * K / ((tA + tB) * 1e-3)
 
-    # ---- roofline of the dominant kernel (block_fill_kernel), this rank ----
+    # ---- roofline of the dominant kernel (site_fill_kernel), this rank ----
     fill_total_ms = sum(sum(x) for x in fill_ms)
     n_fill = K * len(blocks)
     alg_bytes_per_launch = 24.0 * my_elems / len(blocks)       # 16 B data + 8 B index per element
     avg_fill_ms = fill_total_ms / n_fill
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_per_launch / (avg_fill_ms * 1e-3) / 1e9
-    roofline = {"kernel": "block_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "site_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_fill_ms, "share_of_stage_C": fill_total_ms / max(tC, 1e-9),
