@@ -1,5 +1,9 @@
 // abi.cu -- the extern "C" surface declared in include/bs2e.h.
+#include <sched.h>
+
+#include <cctype>
 #include <complex>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <tuple>
@@ -377,11 +381,63 @@ int bs2e_block_fill(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
     });
 }
 
+// Pinned pages are placed by the kernel's local-allocation policy on the NUMA
+// node of the calling thread.  A buffer on the socket the GPU is not attached
+// to halves the D2H rate (every byte crosses the inter-socket link), so the
+// calling thread is moved onto the CPUs of the GPU's node for the duration of
+// the allocation.  Best effort: any failure leaves the default placement.
+namespace {
+bool gpu_node_cpus(cpu_set_t* set)
+{
+    int dev = 0;
+    char bus[32] = {0};
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) return false;
+    for (char* q = bus; *q; ++q) *q = (char)tolower(*q);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    CPU_ZERO(set);
+    int a = 0, b = 0, n = 0;
+    for (;;) {  // "0-15,32-47"
+        if (fscanf(f, "%d", &a) != 1) break;
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') {
+            if (fscanf(f, "%d", &b) != 1) break;
+            ch = fgetc(f);
+        }
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; ++cpu) { CPU_SET(cpu, set); ++n; }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    return n > 0;
+}
+}  // namespace
+
 int bs2e_host_alloc(int64_t bytes, void** ptr)
 {
     return guarded("bs2e_host_alloc", [&] {
         if (!ptr || bytes < 0) throw Error("bad argument");
-        BS2E_CUDA(cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));
+        cpu_set_t saved, want;
+        const bool have_saved = sched_getaffinity(0, sizeof(saved), &saved) == 0;
+        bool moved = false;
+        if (have_saved && gpu_node_cpus(&want)) {
+            cpu_set_t both;
+            CPU_AND(&both, &want, &saved);  // stay inside the CPUs this process may use
+            if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof(both), &both) == 0;
+        }
+        const cudaError_t e = cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault);
+        if (moved) sched_setaffinity(0, sizeof(saved), &saved);
+        BS2E_CUDA(e);
     });
 }
 

@@ -125,7 +125,8 @@ int bs2e_block_download(bs2e_block *blk, int64_t *H_ptr, int64_t *H_idx, double 
 int bs2e_block_checksum(bs2e_block *blk, uint64_t *sum_H, uint64_t *sum_S);
 int bs2e_block_free(bs2e_block *blk);
 
-/* Pinned host memory for callers that want full-speed transfers. */
+/* Pinned host memory for callers that want full-speed transfers; the pages are
+ * placed on the NUMA node the current CUDA device is attached to.           */
 int bs2e_host_alloc(int64_t bytes, void **ptr);
 int bs2e_host_free(void *ptr);
 
