@@ -96,16 +96,21 @@ block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, lon
 
 // ---------------------------------------------------------------------------
 // site-centric fill: one CTA per radial site (n_a,n_b), see site_core.h.
-//   phase 1  per column block bj and n_c slot: clipped windows T[bj][q];
-//            R^k values of both windows -> shared memory, Rv[k][slot]
+// All rows (l_a,l_b; n_a,n_b) of the site read the same R^k values; only the
+// angular factors and the clipping by the column block differ.
+//   phase 1  per column block bj and n_c slot: clipped windows T[bj][q]
 //   phase 2  per (bj, storage mode): prefix over the n_c slots of the number of
 //            stored entries, hp[bj][mode][q] (mode: D, X, D+X, diagonal pair)
-//   phase 3  per row of the site: offsets of its column blocks inside the row
-//   phase 4  warps grab (row, column block) pairs from a shared counter and
-//            walk the OUTPUT positions of the pair 32 at a time (all lanes
-//            busy): n_c slot by binary search in hp, n_d by interval
-//            arithmetic, sum_k ang_k R^k from shared memory, coalesced stores
-// Nothing is computed per pair except the copy of its 2*K1 angular factors.
+//   phase 3  per row of the site: storage mode, k parity and offset inside the
+//            row of each of its column blocks (pm); per (bj, mode) the bit mask
+//            of the rows that store that list (gmask)
+//   phase 4  THREAD t OWNS CANDIDATE COLUMN t of the site: it loads the R^k
+//            values of the column for all multipoles into registers once (both
+//            windows) and then walks the column blocks; per (bj, mode) it works
+//            out once whether / where the column is stored, then for every row
+//            of the mask sum_k ang_k R^k with the packed factors read as
+//            broadcast loads -- per stored element ~K1/2 FP64 FMAs, K1/4 loads,
+//            two stores.  R^k is read from HBM exactly once per site.
 // ---------------------------------------------------------------------------
 struct SiteList {
     const unsigned* key;  // [nsites]  n_a << 16 | n_b
@@ -114,29 +119,37 @@ struct SiteList {
     int nsites;
 };
 
-struct alignas(16) RowCache {  // per row of the site: what a pair needs to know about its row
+struct alignas(16) RowCache {  // per row of the group
     long long hbase, sbase;    // 0-based position of the first H / S entry of the row
     int bi, la, lb, pad;
 };
 
+struct alignas(16) RowRec {    // one (row, column block) pair of the group, filed under (bj, mode)
+    long long hpos;            // 0-based position of the pair's first H entry
+    int cf;                    // index of the pair's packed factors (units of 2*NKP doubles)
+    int meta;                  // pd | ri << 8
+};
+
+constexpr int kSiteThreads = 128;
+
 struct SiteSmem {   // element counts of the dynamic shared memory carve-up
-    int nsmax;      // slots (stride of Rv over k) = entries of list DX at most
     int ncmax;      // n_c slots
-    int cap;        // (row, column block) pairs per group
+    int G;          // rows per group (<= 32)
+    int cfsm;       // packed factors of the group's pairs staged in shared memory
     size_t bytes;
 };
 
-__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int nw, int cap)
+__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G, int nkp, bool cfsm)
 {
-    const size_t nsmax = (size_t)site_max_slots(g), ncmax = (size_t)site_max_nc(g);
+    const size_t ncmax = (size_t)site_max_nc(g);
     size_t b = 0;
-    b += sizeof(double) * 2 * (size_t)site_win_doubles(g);             // Rv: D and X windows
-    b += sizeof(double) * (size_t)nw * 2 * g.K1;                       // wang
-    b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                     // T
-    b += sizeof(RowCache) * (size_t)nblk;                              // rcache
-    b += sizeof(Cand) * 2 * nsmax;                                     // listD + listX (half each), listDX
-    b += sizeof(int2) * (size_t)cap;                                   // plist
-    b += sizeof(int) * (ncmax + 1);                                    // cprefix
+    b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                      // T
+    b += sizeof(RowRec) * (size_t)nblk * G;                             // rlist
+    b += sizeof(RowCache) * (size_t)G;                                  // rcache
+    if (cfsm) b += sizeof(double) * (size_t)G * nblk * 2 * nkp;         // cfs
+    b += sizeof(uchar4) * (size_t)((nblk + 3) & ~3);                    // gcnt
+    b += sizeof(unsigned) * (size_t)((G * nblk + 3) & ~3);              // pm
+    b += sizeof(int) * ((ncmax + 1 + 3) & ~3);                          // cprefix
     b += sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1);  // hp
     b += sizeof(unsigned short) * (size_t)nblk * (ncmax + 1);           // sp
     return b + 16;
@@ -152,73 +165,58 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
-constexpr int kSiteWarps = 8;
-constexpr int kSiteMinBlocks = 4;
-constexpr size_t kSiteSmemLimit = 200 * 1024;
+constexpr size_t kSiteSmemLimit = 160 * 1024;
+constexpr size_t kSiteCoefSmem = 48 * 1024;  // stage the packed factors when they fit this
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, kSiteMinBlocks)
-site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay,
+// the packed factors of one (row block, column block) pair and window: NKP doubles
+template <int NKP, bool SM>
+__device__ __forceinline__ void load_coefs(const double* __restrict__ cf, double* out)
+{
+#pragma unroll
+    for (int i = 0; i < NKP; i += 2) {
+        const double2 v = SM ? *reinterpret_cast<const double2*>(cf + i)
+                             : __ldg(reinterpret_cast<const double2*>(cf + i));
+        out[i] = v.x;
+        out[i + 1] = v.y;
+    }
+}
+
+// WX: the sites of this launch have exchange windows (site_wants_X); the sites that
+// have none run a leaner instantiation (no exchange registers, half the n_c slots).
+template <int NT, int KMAX, bool CFSM, bool WX>
+__global__ void __launch_bounds__(NT, KMAX <= 13 ? (WX ? 512 : 768) / NT : 256 / NT)
+site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int site_off, const double* __restrict__ R,
                  long long row_lo, const long long* __restrict__ Hptr,
                  const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
                  double2* __restrict__ Hdat, long long* __restrict__ Sidx,
                  double2* __restrict__ Sdat)
 {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    const int K1 = g.K1, nsmax = lay.nsmax, ncmax = lay.ncmax, cap = lay.cap;
+    constexpr int NW = NT / 32;
+    constexpr int NKP = (((KMAX + 1) / 2) + 1) & ~1;  // = site_nkp(KMAX)
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int K1 = g.K1, ncmax = lay.ncmax, G = lay.G;
     const int nblk = pl.nblk;
-    double* Rv = reinterpret_cast<double*>(smraw);
-    double* wang_all = Rv + 2 * (size_t)site_win_doubles(g);
-    SiteEntry* T = reinterpret_cast<SiteEntry*>(wang_all + (size_t)NW * 2 * K1);
-    RowCache* rcache = reinterpret_cast<RowCache*>(T + (size_t)nblk * ncmax);  // rows of the group
-    Cand* listD = reinterpret_cast<Cand*>(rcache + nblk);
-    Cand* listX = listD + nsmax / 2;
-    Cand* listDX = listX + nsmax / 2;
-    int2* plist = reinterpret_cast<int2*>(listDX + nsmax);                     // coupled pairs of the group
-    int* cprefix = reinterpret_cast<int*>(plist + cap);
-    unsigned short* hp = reinterpret_cast<unsigned short*>(cprefix + ncmax + 1);
+    SiteEntry* T = reinterpret_cast<SiteEntry*>(smraw);
+    RowRec* rlist = reinterpret_cast<RowRec*>(T + (size_t)nblk * ncmax);
+    RowCache* rcache = reinterpret_cast<RowCache*>(rlist + (size_t)nblk * G);
+    double* cfs = reinterpret_cast<double*>(rcache + G);
+    uchar4* gcnt = reinterpret_cast<uchar4*>(cfs + (CFSM ? (size_t)G * nblk * 2 * NKP : 0));
+    unsigned* pm = reinterpret_cast<unsigned*>(gcnt + ((nblk + 3) & ~3));
+    int* cprefix = reinterpret_cast<int*>(pm + ((G * nblk + 3) & ~3));
+    unsigned short* hp = reinterpret_cast<unsigned short*>(cprefix + ((ncmax + 1 + 3) & ~3));
     unsigned short* sp = hp + (size_t)nblk * kModes * (ncmax + 1);
-    __shared__ int s_next, s_npairs;
-    __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int sidx = blockIdx.x;
+    const int sidx = blockIdx.x + site_off;
     const unsigned key = sl.key[sidx];
-    const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
+    const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), WX);
     const int* srows = sl.rows + sl.ptr[sidx];
     const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
     const int nnc = s.nnc;
+    constexpr bool wantX = WX;
+    const size_t plane = (size_t)g.P * g.ldP;
 
-    // ---- phase 0: both R^k windows of the site, [K1][2w+1][cpad] boxes of the tensor
-    //      R[k][p1][p2], dropped into shared memory by two TMA tile loads ----
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
-    // if n_a - w exceeds every n_2 of the basis, all exchange windows of the site are clipped away
-    const bool wantX = s.dXlo <= pl.max_nd;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const unsigned box_bytes = (unsigned)(K1 * s.kst * sizeof(double));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"(wantX ? 2 * box_bytes : box_bytes)
-                     : "memory");
-        const unsigned dstD = (unsigned)__cvta_generic_to_shared(Rv);
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-            " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dstD),
-            "l"(&tmapR), "r"(site_colD(g, s)), "r"(site_rowD(g, s)), "r"(0), "r"(bar)
-            : "memory");
-        if (wantX) {
-            const unsigned dstX = (unsigned)__cvta_generic_to_shared(Rv + s.xoff);
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-                " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dstX),
-                "l"(&tmapR), "r"(site_colX(g, s)), "r"(site_rowX(g, s)), "r"(0), "r"(bar)
-                : "memory");
-        }
-    }
-    // ---- phase 1a: clipped windows per column block, candidate lists D and X,
-    //      slot prefix of list DX ----
+    // ---- phase 1: clipped windows per column block; slot prefix of the candidate list ----
     if (warp == NW - 1 && wantX) {
         int run = 0;
         for (int q0 = 0; q0 < nnc; q0 += 32) {
@@ -232,20 +230,12 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
     }
     for (int q = lane; q < nnc; q += 32)
         for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
-    for (int t = tid; t < s.nD; t += NW * 32) listD[t] = site_cand_D(s, t);
-    if (wantX)
-        for (int t = tid; t < s.nX; t += NW * 32) listX[t] = site_cand_X(s, t);
     __syncthreads();
-    // ---- phase 1b: list DX (CSR order over both windows) ----
-    for (int q = warp; wantX && q < nnc; q += NW) {
-        const int n = cprefix[q + 1] - cprefix[q], base = cprefix[q];
-        for (int idx = lane; idx < n; idx += 32) listDX[base + idx] = site_cand_DX(s, q, idx);
-    }
     // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode);
     //      one thread per (bj, mode), serial over the slots ----
-    for (int task = tid; task < nblk * kModes; task += NW * 32) {
+    for (int task = tid; task < nblk * kModes; task += NT) {
         const int bj = task / kModes, mode = task - bj * kModes;
-        if (!wantX && (mode == kModeX || mode == kModeDX)) continue;  // never read, see tot_of()
+        if (!wantX && (mode == kModeX || mode == kModeDX)) continue;  // never read
         const bool useD = mode_useD(mode), useX = mode_useX(mode);
         const bool diag = mode == kModeDiag;
         const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
@@ -265,20 +255,13 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
         hpq[nnc] = (unsigned short)run;
     }
 
-    double* wang = wang_all + warp * 2 * K1;
-    const int G = cap / nblk;  // rows per group (host guarantees >= 1)
     double* const Hd = reinterpret_cast<double*>(Hdat);
     double* const Sd = reinterpret_cast<double*>(Sdat);
-    // first live candidate of each list when n_c < n_a is cut away (diagonal pair, j >= i)
-    const int cutD = (s.na - s.cDlo) * s.dw;
-    const int cutX = imin(s.nX, imax(0, s.na - s.cXlo) * s.xw);
 
     for (int g0 = 0; g0 < nr; g0 += G) {
         const int gr = imin(G, nr - g0);
         __syncthreads();  // phase 2 / previous group finished
-        if (tid == 0) { s_next = 0; s_npairs = 0; }
-        __syncthreads();
-        // ---- phase 3: coupled pairs of each row and their offsets inside the row ----
+        // ---- phase 3a: coupled column blocks of each row and their offsets inside the row ----
         for (int ri = warp; ri < gr; ri += NW) {
             const int rowi = srows[g0 + ri];
             const RowInfo r = row_info(pl, rowi);
@@ -299,79 +282,142 @@ site_fill_kernel(const __grid_constant__ CUtensorMap tmapR, Geom g, Plan pl, One
                     }
                 }
                 const int inc = warp_incl_scan(c, lane);
-                const unsigned live = __ballot_sync(0xffffffffu, c > 0);
-                int base = 0;
-                if (lane == 0 && live) base = atomicAdd(&s_npairs, __popc(live));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (c > 0) {
-                    const int slot = base + __popc(live & ((1u << lane) - 1u));
-                    plist[slot] = make_int2(ri | (bj << 12) | (mode << 24), run + inc - c);
-                }
+                if (bj < nblk)
+                    pm[ri * nblk + bj] = c > 0 ? pm_pack(run + inc - c, mode, (r.la + pl.blk[bj].l1) & 1) : 0u;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
         __syncthreads();
-        const int npairs = s_npairs;
-        if (g0 == 0) {  // the staged windows must have landed
-            unsigned done = 0;
-            while (!done)
-                asm volatile(
-                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                    : "=r"(done)
-                    : "r"(bar)
-                    : "memory");
+        // ---- phase 3b: the pairs of each column block, filed by storage mode ----
+        for (int bj = tid; bj < nblk; bj += NT) {
+            int cnt[kModes] = {0, 0, 0, 0};
+            for (int ri = 0; ri < gr; ++ri) {
+                const unsigned v = pm[ri * nblk + bj];
+                if (pm_valid(v)) ++cnt[pm_mode(v)];
+            }
+            gcnt[bj] = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2],
+                                   (unsigned char)cnt[3]);
+            int pos[kModes] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+            for (int ri = 0; ri < gr; ++ri) {
+                const unsigned v = pm[ri * nblk + bj];
+                if (!pm_valid(v)) continue;
+                const int mode = pm_mode(v);
+                int where = 0;  // pos[mode]++ without dynamic indexing of a register array
+#pragma unroll
+                for (int q = 0; q < kModes; ++q)
+                    if (q == mode) where = pos[q]++;
+                const RowCache rc = rcache[ri];
+                rlist[bj * G + where] = RowRec{rc.hbase + pm_off(v), CFSM ? ri * nblk + bj : rc.bi * nblk + bj,
+                                               pm_pd(v) | (ri << 8)};
+            }
         }
+        if (CFSM) {  // packed factors of the group's pairs -> shared memory (16-byte units)
+            const int per = NKP;  // double2 per pair
+            for (int idx = tid; idx < gr * nblk * per; idx += NT) {
+                const int pair = idx / per, l = idx - pair * per;
+                const int ri = pair / nblk, bj = pair - ri * nblk;
+                if (!pm_valid(pm[pair])) continue;
+                const double2* src = reinterpret_cast<const double2*>(
+                    pl.angP + ((size_t)rcache[ri].bi * nblk + bj) * (2 * NKP));
+                reinterpret_cast<double2*>(cfs)[(size_t)pair * per + l] = __ldg(src + l);
+            }
+        }
+        __syncthreads();
         // ---- phase 4: fill ----
-        for (;;) {
-            int p = 0;
-            if (lane == 0) p = atomicAdd(&s_next, 1);
-            p = __shfl_sync(0xffffffffu, p, 0);
-            if (p >= npairs) break;
-            const int2 pe = plist[p];
-            const int ri = pe.x & 0xfff, bj = (pe.x >> 12) & 0xfff, mode = pe.x >> 24;
-            const RowCache rc = rcache[ri];
-            RowInfo r;
-            r.i = 0;
-            r.bi = rc.bi;
-            r.na = s.na;
-            r.nb = s.nb;
-            r.la = rc.la;
-            r.lb = rc.lb;
-            const int cpl = r.bi * nblk + bj;
-            const unsigned fl = pl.flags[cpl];
-            PairCtx pc;
-            pc.pk = pair_k(pl.krange[cpl]);
-            __syncwarp();
-            for (int i = lane; i < pc.pk.nkd; i += 32) wang[i] = pl.angD[(size_t)cpl * K1 + pc.pk.dlo + 2 * i];
-            for (int i = lane; i < pc.pk.nkx; i += 32) wang[K1 + i] = pl.angX[(size_t)cpl * K1 + pc.pk.xlo + 2 * i];
-            __syncwarp();
-            pc.Tb = T + bj * ncmax;
-            pc.hpq = hp + (bj * kModes + mode) * (ncmax + 1);
-            pc.spq = sp + bj * (ncmax + 1);
-            pc.Rv = Rv;
-            pc.wa_d = wang;
-            pc.wa_x = wang + K1;
-            pc.kst = s.kst;
-            pc.bj = bj;
-            pc.diag = mode == kModeDiag;
-            pc.dirany = (fl & kDirAny) != 0;
-            pc.exany = (fl & kExAny) != 0;
-            pc.samex = pc.diag && r.la == r.lb;
-            pc.cut = pc.diag && !pl.full;
-            pc.hbase = rc.hbase + pe.y;
-            pc.sbase = rc.sbase;
-            const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
-            const int win = pair_window(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
-            if (win == kModeD) {
-                for (int t = (pc.cut ? cutD : 0) + lane; t < s.nD; t += 32)
-                    site_item<kModeD>(g, pl, ob, s, r, pc, listD[t], Hidx, Hd, Sidx, Sd);
-            } else if (win == kModeX) {
-                for (int t = (pc.cut ? cutX : 0) + lane; t < s.nX; t += 32)
-                    site_item<kModeX>(g, pl, ob, s, r, pc, listX[t], Hidx, Hd, Sidx, Sd);
-            } else {
-                const int ncand = cprefix[nnc];
-                for (int t = (pc.cut ? cprefix[union_pos(s, s.na)] : 0) + lane; t < ncand; t += 32)
-                    site_item<kModeDX>(g, pl, ob, s, r, pc, listDX[t], Hidx, Hd, Sidx, Sd);
+        const double* const cfbase = CFSM ? cfs : pl.angP;
+        const int nc_all = site_num_cand(s, cprefix, wantX);
+        for (int t0 = 0; t0 < nc_all; t0 += NT) {
+            const int t = t0 + tid;
+            const bool act = t < nc_all;
+            const OwnCand c = site_own_cand(g, s, cprefix, wantX, act ? t : 0);
+            double Rd[KMAX], Rx[WX ? KMAX : 1];
+            {
+                const double* pD = R + (size_t)c.rowD * g.ldP + c.colD;
+                const double* pX = R + (size_t)c.rowX * g.ldP + c.colX;
+                const bool onD = act && c.inD, onX = act && c.inX;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {   // read once, streaming
+                    Rd[k] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
+                    if constexpr (WX) Rx[k] = (onX && k < K1) ? __ldcs(pX + (size_t)k * plane) : 0.0;
+                }
+                if constexpr (!WX) Rx[0] = 0.0;
+            }
+            if (__ballot_sync(0xffffffffu, act) == 0u) continue;  // warp without candidates
+            for (int bj = 0; bj < nblk; ++bj) {
+                const uchar4 gc = gcnt[bj];
+                if ((gc.x | gc.y | gc.z | gc.w) == 0) continue;
+                const SiteEntry e = T[bj * ncmax + c.q];
+                const BlockDesc bc = pl.blk[bj];
+                const int lpar = (bc.l1 + bc.l2) & 1;
+                const RowRec* rl = rlist + bj * G;
+#pragma unroll
+                for (int mode = 0; mode < kModes; ++mode) {
+                    if (!WX && (mode == kModeX || mode == kModeDX)) continue;  // no such pairs without exchange windows
+                    const int nrow = mode == 0 ? gc.x : mode == 1 ? gc.y : mode == 2 ? gc.z : gc.w;
+                    if (nrow == 0) continue;
+                    const RowRec* rm = rl;
+                    rl += nrow;
+                    const bool diag = mode == kModeDiag;
+                    const ModeSlot ms = site_mode_slot(s, c, e, hp + (bj * kModes + mode) * (ncmax + 1), mode,
+                                                       diag && !pl.full);
+                    const bool stored = act && (ms.sup || ms.sup_ex);
+                    if (__ballot_sync(0xffffffffu, stored) == 0u) continue;
+                    const long long jcol = ms.jcol;
+                    if (!diag) {
+#pragma unroll 2
+                        for (int i = 0; i < nrow; ++i) {
+                            const RowRec rec = rm[i];
+                            const int pd = rec.meta & 1, px = pd ^ lpar;
+                            const double* cf = cfbase + (size_t)rec.cf * (2 * NKP);
+                            double res = 0.0;
+                            if (mode != kModeX) {
+                                double cD[NKP];
+                                load_coefs<NKP, CFSM>(cf, cD);
+                                const double d = site_dot_par<KMAX>(cD, Rd, pd);
+                                res += ms.sup ? d : 0.0;
+                            }
+                            if constexpr (WX) {
+                                if (mode != kModeD) {
+                                    double cX[NKP];
+                                    load_coefs<NKP, CFSM>(cf + NKP, cX);
+                                    const double x = site_dot_par<KMAX>(cX, Rx, px);
+                                    res += ms.sup_ex ? x : 0.0;
+                                }
+                            }
+                            if (stored) {
+                                const long long pos = rec.hpos + ms.rank;
+                                Hidx[pos] = jcol;
+                                *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(res, 0.0);
+                            }
+                        }
+                    } else {  // exactly one row: the row whose own block is bj
+                        const RowRec rec = rm[0];
+                        const RowCache rc = rcache[rec.meta >> 8];
+                        const int pd = rec.meta & 1, px = pd ^ lpar;
+                        const double* cf = cfbase + (size_t)rec.cf * (2 * NKP);
+                        double cD[NKP];
+                        load_coefs<NKP, CFSM>(cf, cD);
+                        const double d = site_dot_par<KMAX>(cD, Rd, pd);
+                        double res = 0.0;
+                        res += ms.sup ? d : 0.0;
+                        if constexpr (WX) {
+                            double cX[NKP];
+                            load_coefs<NKP, CFSM>(cf + NKP, cX);
+                            const double x = site_dot_par<KMAX>(cX, Rx, px);
+                            res += ms.sup_ex ? x : 0.0;
+                        }
+                        if (stored) {
+                            RowInfo r;
+                            r.i = 0; r.bi = rc.bi; r.na = s.na; r.nb = s.nb; r.la = rc.la; r.lb = rc.lb;
+                            double re = res, im = 0.0;
+                            site_diag_terms(g, pl, ob, r, c, ms, r.la == r.lb, sp + bj * (ncmax + 1), rc.sbase,
+                                            &re, &im, Sidx, Sd);
+                            const long long pos = rec.hpos + ms.rank;
+                            Hidx[pos] = jcol;
+                            *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(re, im);
+                        }
+                    }
+                }
             }
         }
     }
@@ -450,10 +496,12 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         b->d_krange = dev_upload(hp.krange, st);
         b->d_angD = dev_upload(hp.angD, st);
         b->d_angX = dev_upload(hp.angX, st);
+        if (hp.nkp > 0) b->d_angP = dev_upload(hp.angP, st);
         b->d_row_n1 = dev_upload(hp.row_n1, st);
         b->d_row_n2 = dev_upload(hp.row_n2, st);
         b->d_row_blk = dev_upload(hp.row_blk, st);
         b->nsites = (int)hp.site_key.size();
+        b->nsites_x = hp.nsites_x;
         if (b->nsites > 0) {
             b->d_site_key = dev_upload(hp.site_key, st);
             b->d_site_ptr = dev_upload(hp.site_ptr, st);
@@ -470,6 +518,8 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         pl.krange = b->d_krange;
         pl.angD = b->d_angD;
         pl.angX = b->d_angX;
+        pl.angP = b->d_angP;
+        pl.nkp = hp.nkp;
         pl.row_n1 = b->d_row_n1;
         pl.row_n2 = b->d_row_n2;
         pl.row_blk = b->d_row_blk;
@@ -505,41 +555,58 @@ void block_assemble(bs2e_block* b)
         b->d_Sdat = dev_alloc<double>(2 * (size_t)b->nnzS);
     }
     const long long nrows = b->row_hi - b->row_lo + 1;
-    // site kernel unless its shared-memory windows do not fit (large k_s * max_k)
-    // or BS2E_FILL=row asks for the row kernel (kept for A/B measurements)
-    constexpr int NW = kSiteWarps;
+    // site kernel unless max_k exceeds its largest instantiation or its tables do
+    // not fit shared memory; BS2E_FILL=row asks for the row kernel (A/B measurements)
     const Geom& g = c->dg;
     const char* mode = getenv("BS2E_FILL");
-    bool use_site = b->nsites > 0 && c->have_tmap && !(mode && strcmp(mode, "row") == 0) && site_max_nc(g) <= 255;
+    const int nblk = b->dplan.nblk;
+    const int kmax = site_kmax_for(g.K1);
+    bool use_site = b->nsites > 0 && b->d_angP && !(mode && strcmp(mode, "row") == 0) && kmax > 0 &&
+                    site_max_slots(g) <= 65535 && (size_t)nblk * site_max_slots(g) < (1u << 24);
     SiteSmem lay{};
     if (use_site) {
-        lay.nsmax = site_max_slots(g);
+        const int nkp = site_nkp(kmax);
         lay.ncmax = site_max_nc(g);
-        const int cap_want = std::max(b->dplan.nblk, std::min(2048, b->dplan.nblk * b->dplan.nblk));
-        lay.cap = cap_want;
-        lay.bytes = site_smem_bytes(g, b->dplan.nblk, NW, lay.cap);
-        if (lay.bytes > kSiteSmemLimit) {  // shrink the pair group before giving up
-            lay.cap = b->dplan.nblk;
-            lay.bytes = site_smem_bytes(g, b->dplan.nblk, NW, lay.cap);
-        }
-        if (lay.bytes > kSiteSmemLimit || 2 * site_win_doubles(g) + site_kst(g) > 65535 || b->dplan.nblk > 4095)
-            use_site = false;
+        lay.G = std::min(32, nblk);   // a site has at most one row per (l1,l2) block
+        lay.cfsm = sizeof(double) * (size_t)lay.G * nblk * 2 * nkp <= kSiteCoefSmem;
+        lay.bytes = site_smem_bytes(g, nblk, lay.G, nkp, lay.cfsm != 0);
+        if (lay.bytes > kSiteSmemLimit) use_site = false;
     }
     if (use_site) {
-        BS2E_CUDA(cudaFuncSetAttribute(site_fill_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)lay.bytes));
         const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
-        site_fill_kernel<NW><<<(unsigned)b->nsites, NW * 32, lay.bytes, c->stream>>>(
-            c->tmapR, c->dg, b->dplan, c->one_body(), sl, lay, b->row_lo, b->d_Hptr, b->d_Sptr, b->d_Hidx,
-            reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
+        auto launch = [&](auto kern, int nt, int first, int count) {
+            if (count <= 0) return;
+            BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+            kern<<<(unsigned)count, nt, lay.bytes, c->stream>>>(
+                c->dg, b->dplan, c->one_body(), sl, lay, first, c->d_R, b->row_lo, b->d_Hptr, b->d_Sptr,
+                b->d_Hidx, reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
+            BS2E_LAUNCHED();
+        };
+        constexpr int NT = kSiteThreads;
+        const int nx = b->nsites_x, nd = b->nsites - b->nsites_x;
+#define BS2E_SITE(KM)                                                          \
+    case KM:                                                                   \
+        if (lay.cfsm) {                                                        \
+            launch(site_fill_kernel<NT, KM, true, true>, NT, 0, nx);           \
+            launch(site_fill_kernel<NT, KM, true, false>, NT, nx, nd);         \
+        } else {                                                               \
+            launch(site_fill_kernel<NT, KM, false, true>, NT, 0, nx);          \
+            launch(site_fill_kernel<NT, KM, false, false>, NT, nx, nd);        \
+        }                                                                      \
+        break;
+        switch (kmax) {
+            BS2E_SITE(7) BS2E_SITE(13) BS2E_SITE(21) BS2E_SITE(31)
+        default: throw Error("block_assemble: no site kernel for this max_k");
+        }
+#undef BS2E_SITE
     } else {
         block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,
                             c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, b->row_lo, nrows,
                                          b->d_Hptr, b->d_Sptr, b->d_Hidx,
                                          reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx,
                                          reinterpret_cast<double2*>(b->d_Sdat));
+        BS2E_LAUNCHED();
     }
-    BS2E_LAUNCHED();
     b->assembled = true;
 }
 
@@ -601,7 +668,7 @@ void block_free(bs2e_block* b)
 {
     if (!b) return;
     cudaFree(b->d_blk); cudaFree(b->d_ncrow); cudaFree(b->d_flags); cudaFree(b->d_krange);
-    cudaFree(b->d_angD); cudaFree(b->d_angX);
+    cudaFree(b->d_angD); cudaFree(b->d_angX); cudaFree(b->d_angP);
     cudaFree(b->d_row_n1); cudaFree(b->d_row_n2); cudaFree(b->d_row_blk);
     cudaFree(b->d_site_key); cudaFree(b->d_site_ptr); cudaFree(b->d_site_rows);
     cudaFree(b->d_cntH); cudaFree(b->d_cntS); cudaFree(b->d_Hptr); cudaFree(b->d_Sptr);

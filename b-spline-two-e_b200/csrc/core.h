@@ -242,6 +242,8 @@ struct Plan {
     const KRange* krange;        // [nblk][nblk]
     const double* angD;          // [nblk][nblk][K1]   direct, |.|<5e-16 zeroed
     const double* angX;          // [nblk][nblk][K1]   exchange * (-1)^(lc+ld+L)
+    const double* angP;          // [nblk][nblk][2*nkp] the same packed by parity (site_core.h)
+    int nkp;
     const unsigned short* row_n1;   // [n_config]
     const unsigned short* row_n2;   // [n_config]
     const unsigned short* row_blk;  // [n_config]

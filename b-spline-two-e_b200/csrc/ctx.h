@@ -102,12 +102,12 @@ struct bs2e_block {
     bs2e::NcRow* d_ncrow = nullptr;
     unsigned char* d_flags = nullptr;
     bs2e::KRange* d_krange = nullptr;
-    double *d_angD = nullptr, *d_angX = nullptr;
+    double *d_angD = nullptr, *d_angX = nullptr, *d_angP = nullptr;
     unsigned short *d_row_n1 = nullptr, *d_row_n2 = nullptr, *d_row_blk = nullptr;
     // rows grouped by radial site (site kernel)
     unsigned* d_site_key = nullptr;
     int *d_site_ptr = nullptr, *d_site_rows = nullptr;
-    int nsites = 0;
+    int nsites = 0, nsites_x = 0;
     // CSR fragment (device)
     long long *d_cntH = nullptr, *d_cntS = nullptr;  // [nrows+1] counts
     long long *d_Hptr = nullptr, *d_Sptr = nullptr;  // [nrows+1] 1-based

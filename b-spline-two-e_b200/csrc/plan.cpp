@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <unordered_map>
 
+#include "site_core.h"
 #include "wigner.h"
 
 namespace bs2e {
@@ -128,23 +129,51 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
             krange[o] = kr;
         }
 
+    // the same factors packed by multipole parity for the site kernel
+    const int kmax = site_kmax_for(K1);
+    const int nkp = kmax > 0 ? site_nkp(kmax) : 0;
+    std::vector<double> angP((size_t)nblk * nblk * 2 * nkp, 0.0);
+    if (nkp > 0)
+        for (int bi = 0; bi < nblk; ++bi)
+            for (int bj = 0; bj < nblk; ++bj) {
+                const size_t o = (size_t)bi * nblk + bj;
+                const int pd = (blocks[bi].l1 + blocks[bj].l1) & 1, px = (blocks[bi].l1 + blocks[bj].l2) & 1;
+                for (int k = 0; k < K1; ++k) {
+                    if (angD[o * K1 + k] != 0.0) {
+                        if ((k ^ pd) & 1) throw std::logic_error("block_plan: direct factor off parity");
+                        angP[o * 2 * nkp + (k - pd) / 2] = angD[o * K1 + k];
+                    }
+                    if (angX[o * K1 + k] != 0.0) {
+                        if ((k ^ px) & 1) throw std::logic_error("block_plan: exchange factor off parity");
+                        angP[o * 2 * nkp + nkp + (k - px) / 2] = angX[o * K1 + k];
+                    }
+                }
+            }
+
     // rows of the requested range grouped by radial site (counting sort on the
     // site key, then sites ordered by descending row count so that the heaviest
     // CTAs of the site kernel start first)
     std::vector<unsigned> site_key;
     std::vector<int> site_ptr, site_rows;
+    int nsites_x = 0;
     if ((size_t)stride * stride <= ((size_t)1 << 26)) {  // else: no site list, the row kernel is used
         const long long nrows = row_hi - row_lo + 1;
         const size_t nkeys = (size_t)stride * stride;
         std::vector<int> kcount(nkeys + 1, 0);
         for (long long i = row_lo - 1; i < row_hi; ++i) ++kcount[(size_t)rn1[i] * stride + rn2[i] + 1];
-        // distinct sites, bucketed by their number of rows
-        std::vector<int> per_n(nblk + 2, 0);
+        // distinct sites, bucketed by (has exchange windows, number of rows)
+        int max_nd_all = 0;
+        for (auto v : rn2) max_nd_all = v > max_nd_all ? v : max_nd_all;
+        auto cls = [&](size_t kq) { return site_wants_X(hg, max_nd_all, (int)(kq / stride)) ? 0 : 1; };
+        std::vector<int> per_n(2 * (nblk + 2), 0);
         for (size_t kq = 0; kq < nkeys; ++kq)
-            if (kcount[kq + 1] > 0) ++per_n[kcount[kq + 1]];
-        std::vector<int> first_of_n(nblk + 2, 0);  // first site index holding n rows
+            if (kcount[kq + 1] > 0) ++per_n[cls(kq) * (nblk + 2) + kcount[kq + 1]];
+        std::vector<int> first_of_n(2 * (nblk + 2), 0);  // first site index of (class, n rows)
         int nsites = 0;
-        for (int n = nblk; n >= 1; --n) { first_of_n[n] = nsites; nsites += per_n[n]; }
+        for (int cl = 0; cl < 2; ++cl) {
+            for (int n = nblk; n >= 1; --n) { first_of_n[cl * (nblk + 2) + n] = nsites; nsites += per_n[cl * (nblk + 2) + n]; }
+            if (cl == 0) nsites_x = nsites;
+        }
         site_key.resize(nsites);
         site_ptr.assign(nsites + 1, 0);
         std::vector<int> site_of_key(nkeys, -1);
@@ -153,7 +182,7 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
             for (size_t kq = 0; kq < nkeys; ++kq) {
                 const int n = kcount[kq + 1];
                 if (n <= 0) continue;
-                const int sidx = fill[n]++;
+                const int sidx = fill[cls(kq) * (nblk + 2) + n]++;
                 site_of_key[kq] = sidx;
                 site_key[sidx] = ((unsigned)(kq / stride) << 16) | (unsigned)(kq % stride);
                 site_ptr[sidx + 1] = n;
@@ -172,6 +201,7 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
     hp.site_key = std::move(site_key);
     hp.site_ptr = std::move(site_ptr);
     hp.site_rows = std::move(site_rows);
+    hp.nsites_x = nsites_x;
     hp.nblk = nblk;
     hp.L = L;
     hp.full = full ? 1 : 0;
@@ -186,6 +216,8 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
     hp.krange = std::move(krange);
     hp.angD = std::move(angD);
     hp.angX = std::move(angX);
+    hp.angP = std::move(angP);
+    hp.nkp = nkp;
     hp.row_n1 = std::move(rn1);
     hp.row_n2 = std::move(rn2);
     hp.row_blk = std::move(rblk);
@@ -206,6 +238,8 @@ Plan HostPlan::view() const
     pl.krange = krange.data();
     pl.angD = angD.data();
     pl.angX = angX.data();
+    pl.angP = angP.data();
+    pl.nkp = nkp;
     pl.row_n1 = row_n1.data();
     pl.row_n2 = row_n2.data();
     pl.row_blk = row_blk.data();

@@ -15,11 +15,15 @@ struct HostPlan {
     std::vector<unsigned char> flags;
     std::vector<KRange> krange;
     std::vector<double> angD, angX;
+    std::vector<double> angP;  // packed by parity for the site kernel, [nblk][nblk][2*nkp]
+    int nkp = 0;
     std::vector<unsigned short> row_n1, row_n2, row_blk;
-    // rows row_lo..row_hi grouped by radial site (n1,n2), sites with most rows first
+    // rows row_lo..row_hi grouped by radial site (n1,n2): sites with exchange windows
+    // first, inside each class the sites with most rows first
     std::vector<unsigned> site_key;  // n1 << 16 | n2
     std::vector<int> site_ptr;       // [nsites+1]
     std::vector<int> site_rows;      // 1-based row indices, ascending inside a site
+    int nsites_x = 0;                // sites 0..nsites_x-1 have exchange windows (site_wants_X), the rest do not
     Plan view() const;  // Plan over the HOST arrays
 };
 

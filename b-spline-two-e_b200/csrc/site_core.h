@@ -36,15 +36,25 @@ BS2E_HD int site_kst(const Geom& g) { return (2 * g.w + 1) * site_cpad(g); }
 // doubles per staged window, rounded so that the second window stays 128-byte aligned
 BS2E_HD int site_win_doubles(const Geom& g) { return (g.K1 * site_kst(g) + 15) & ~15; }
 
-BS2E_HD Site make_site(const Geom& g, int na, int nb)
+// wantX = false: every exchange window of the site is clipped away by the basis
+// (n_a - w exceeds the largest n_2 of any configuration), the site is treated as if
+// it had the direct window only (half the n_c slots, no exchange values to load)
+BS2E_HD bool site_wants_X(const Geom& g, int max_nd, int na) { return imax(1, na - g.w) <= max_nd; }
+
+BS2E_HD Site make_site(const Geom& g, int na, int nb, bool wantX)
 {
     Site s;
     s.na = na;
     s.nb = nb;
     s.cDlo = imax(1, na - g.w); s.cDhi = imin(g.nb, na + g.w);
     s.dDlo = imax(1, nb - g.w); s.dDhi = imin(g.nb, nb + g.w);
-    s.cXlo = s.dDlo; s.cXhi = s.dDhi;
-    s.dXlo = s.cDlo; s.dXhi = s.cDhi;
+    if (wantX) {
+        s.cXlo = s.dDlo; s.cXhi = s.dDhi;
+        s.dXlo = s.cDlo; s.dXhi = s.cDhi;
+    } else {
+        s.cXlo = 1; s.cXhi = 0;
+        s.dXlo = 1; s.dXhi = 0;
+    }
     s.dw = s.dDhi - s.dDlo + 1;
     s.xw = s.dXhi - s.dXlo + 1;
     s.nD = (s.cDhi - s.cDlo + 1) * s.dw;
@@ -53,7 +63,7 @@ BS2E_HD Site make_site(const Geom& g, int na, int nb)
     s.kst = site_kst(g);
     s.xoff = site_win_doubles(g);
     s.shD = pair_index(g, nb, s.dDlo) & 1;
-    s.shX = pair_index(g, na, s.dXlo) & 1;
+    s.shX = wantX ? (pair_index(g, na, s.dXlo) & 1) : 0;
     s.ncu = union2(s.cDlo, s.cDhi, s.cXlo, s.cXhi);
     s.nnc = union2_count(s.ncu);
     return s;
@@ -175,132 +185,153 @@ BS2E_HD int union_pos(const Site& s, int v)
            below(imax(s.cDlo, s.cXlo), imin(s.cDhi, s.cXhi), v);
 }
 
-// ---- candidate lists of a site ------------------------------------------------
-// The columns (n_c,n_d) a row of the site can couple to, in CSR order (n_c, then
-// n_d ascending), independent of the column block: list D = direct window, list X =
-// exchange window, list DX = union.  One entry: a = q | n_d << 8,
-// b = slotD | slotX << 16 (0xffff: the column is not in that window).
-struct alignas(8) Cand { unsigned a, b; };
-constexpr unsigned kNoSlot = 0xffffu;
+// ---- per (row, column block) pair: storage mode, k parity, offset in the row ----
+// One 32-bit word per pair of the row group: offset of the pair's first H entry
+// inside its row, the storage mode (after effective_mode) and the parity of the
+// multipoles of the direct term, pd = (l_a + l_c) & 1 (wigner_tools.f90:131: the
+// factor vanishes unless l_a+k+l_c is even).  The exchange parity follows from
+// the column block alone: px = pd ^ ((l_c + l_d) & 1).
+constexpr unsigned kPmValid = 0x80000000u;
+BS2E_HD unsigned pm_pack(int off, int mode, int pd) { return kPmValid | ((unsigned)(mode | (pd << 2)) << 24) | (unsigned)off; }
+BS2E_HD bool pm_valid(unsigned v) { return (v & kPmValid) != 0; }
+BS2E_HD int pm_off(unsigned v) { return (int)(v & 0xffffffu); }
+BS2E_HD int pm_mode(unsigned v) { return (int)((v >> 24) & 3u); }
+BS2E_HD int pm_pd(unsigned v) { return (int)((v >> 26) & 1u); }
 
-BS2E_HD Cand site_cand(const Site& s, int q, int nc, int nd)
+// rows of a group are addressed by bit masks (<= 32 rows per group)
+BS2E_HD int popc32(unsigned m)
 {
-    Cand c;
-    c.a = (unsigned)q | ((unsigned)nd << 8);
-    unsigned sd = kNoSlot, sx = kNoSlot;
-    if (site_nc_inD(s, nc) && nd >= s.dDlo && nd <= s.dDhi) sd = (unsigned)site_slotD(s, nc, nd);
-    if (site_nc_inX(s, nc) && nd >= s.dXlo && nd <= s.dXhi) sx = (unsigned)site_slotX(s, nc, nd);
-    c.b = sd | (sx << 16);
-    return c;
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
 }
-BS2E_HD int cand_q(const Cand& c) { return (int)(c.a & 0xffu); }
-BS2E_HD int cand_nd(const Cand& c) { return (int)(c.a >> 8); }
-BS2E_HD unsigned cand_slotD(const Cand& c) { return c.b & 0xffffu; }
-BS2E_HD unsigned cand_slotX(const Cand& c) { return c.b >> 16; }
+BS2E_HD int lowest_bit(unsigned m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
 
-// entry t of list D / list X (row-major over the window = slot order)
-BS2E_HD Cand site_cand_D(const Site& s, int t)
-{
-    const int nc = s.cDlo + t / s.dw, nd = s.dDlo + t % s.dw;
-    return site_cand(s, union_pos(s, nc), nc, nd);
-}
-BS2E_HD Cand site_cand_X(const Site& s, int t)
-{
-    const int nc = s.cXlo + t / s.xw, nd = s.dXlo + t % s.xw;
-    return site_cand(s, union_pos(s, nc), nc, nd);
-}
-// number of entries of n_c slot q in list DX, and its idx-th entry
+// ---- candidate columns of a site ------------------------------------------------
+// The columns (n_c,n_d) a row of the site can couple to, in CSR order (n_c, then n_d
+// ascending), independent of the column block: the union of the two windows (list
+// DX), or the direct window alone when every exchange window of the site is clipped
+// away.  Thread t of the site's CTA OWNS candidate t for the whole site: it loads the
+// candidate's R^k values for all multipoles into registers once and then walks every
+// (column block, row) pair of the site.
 BS2E_HD int site_cand_DX_count(const Site& s, int q) { return union2_count(site_nd_union(s, site_nc(s, q))); }
-BS2E_HD Cand site_cand_DX(const Site& s, int q, int idx)
+
+// largest q in [0,nnc) with prefix[q] <= p; the trip count depends on nnc only
+template <class T>
+BS2E_HD int prefix_slot(const T* prefix, int nnc, int p)
 {
-    const int nc = site_nc(s, q);
-    return site_cand(s, q, nc, union2_at(site_nd_union(s, nc), idx));
+    int lo = 0, n = nnc;  // the slot lies in [lo, lo+n)
+    while (n > 1) {
+        const int half = n >> 1;
+        if ((int)prefix[lo + half] <= p) lo += half;
+        n -= half;
+    }
+    return lo;
 }
 
-// ---- one (row, column block) pair ---------------------------------------------
-// Everything that is uniform over the pair.  Pointers into shared memory in the
-// kernel, into plain arrays in the CPU checker.
-struct PairCtx {
-    const SiteEntry* Tb;        // [nnc] clipped windows of the column block
-    const unsigned short* hpq;  // [nnc+1] prefix of stored H entries over the n_c slots
-    const unsigned short* spq;  // [nnc]   same for S (diagonal pair only)
-    const double* Rv;           // staged R^k values, Rv[k*kst + slot]
-    const double* wa_d;         // packed direct factors, k = pk.dlo + 2i
-    const double* wa_x;         // packed exchange factors
-    int kst;
-    PairK pk;
-    int bj;
-    bool diag;                  // column block == row block: one-body terms and S
-    bool dirany, exany, samex, cut;
-    long long hbase, sbase;     // first H entry of the pair / first S entry of the row
+struct OwnCand {
+    int q, nc, nd;
+    bool inD, inX;           // member of the direct / exchange window of the site
+    int rowD, colD;          // R^k(n_a n_b; n_c n_d) = R[k][rowD][colD]
+    int rowX, colX;          // R^k(n_a n_b; n_d n_c) = R[k][rowX][colX]  (= R^k(n_b n_a; n_c n_d))
 };
 
-// Which list a pair walks: one window when the mode stores one window or when the
-// other window is clipped away completely for this site and column block.
-BS2E_HD int pair_window(int mode, int totD, int totX)
+// candidate t of the site; cprefix[q] = number of list-DX entries of the n_c slots
+// before q (only read when wantX)
+BS2E_HD OwnCand site_own_cand(const Geom& g, const Site& s, const int* cprefix, bool wantX, int t)
 {
-    if (mode == kModeD || mode == kModeX) return mode;
-    if (totX == 0) return kModeD;
-    if (totD == 0) return kModeX;
-    return kModeDX;
+    OwnCand c;
+    if (wantX) {
+        c.q = prefix_slot(cprefix, s.nnc, t);
+        c.nc = site_nc(s, c.q);
+        c.nd = union2_at(site_nd_union(s, c.nc), t - cprefix[c.q]);
+    } else {
+        const int r = t / s.dw;
+        c.nc = s.cDlo + r;
+        c.nd = s.dDlo + (t - r * s.dw);
+        c.q = union_pos(s, c.nc);
+    }
+    c.inD = site_nc_inD(s, c.nc) && c.nd >= s.dDlo && c.nd <= s.dDhi;
+    c.inX = wantX && site_nc_inX(s, c.nc) && c.nd >= s.dXlo && c.nd <= s.dXhi;
+    c.rowD = c.colD = c.rowX = c.colX = 0;
+    if (c.inD) { c.rowD = pair_index(g, s.na, c.nc); c.colD = pair_index(g, s.nb, c.nd); }
+    if (c.inX) { c.rowX = pair_index(g, s.nb, c.nc); c.colX = pair_index(g, s.na, c.nd); }
+    return c;
+}
+BS2E_HD int site_num_cand(const Site& s, const int* cprefix, bool wantX) { return wantX ? cprefix[s.nnc] : s.nD; }
+
+// What candidate c is inside the column list of (column block, storage mode):
+// whether it is stored, through which window(s), at which rank and column index.
+struct ModeSlot {
+    bool sup, sup_ex;  // stored through the direct / exchange window
+    int rank;          // position inside the (column block, mode) list
+    int jcol;          // configuration index of the column, 1-based
+    SiteEntry e;       // clipped windows of the n_c slot (diagonal cut applied)
+};
+
+BS2E_HD ModeSlot site_mode_slot(const Site& s, const OwnCand& c, SiteEntry e, const unsigned short* hpq,
+                                int mode, bool cut)
+{
+    ModeSlot m;
+    if (cut) e = entry_cut(e, s, c.nc);
+    m.e = e;
+    const bool useD = mode_useD(mode), useX = mode_useX(mode);
+    m.sup = useD && c.nd >= (int)e.dlo && c.nd <= (int)e.dhi;
+    m.sup_ex = useX && c.nd >= (int)e.xlo && c.nd <= (int)e.xhi;
+    m.rank = (int)hpq[c.q] + union_below(useD, e.dlo, e.dhi, useX, e.xlo, e.xhi, c.nd);
+    m.jcol = e.jbase + c.nd;
+    return m;
 }
 
-// One candidate of the pair's list.  LIST = kModeD / kModeX: every stored entry lies
-// in that window; LIST = kModeDX: union of both windows.
-template <int LIST>
-BS2E_HD void site_item(const Geom& g, const Plan& pl, const OneBody& ob, const Site& s,
-                       const RowInfo& r, const PairCtx& pc, Cand cd, long long* Hidx, double* Hdat,
-                       long long* Sidx, double* Sdat)
+// ---- angular factors packed for the site kernel ----------------------------------
+// angP[(bi*nblk + bj)*2*nkp + l]: l < nkp: direct factor of k = pd + 2l, pd = (la+lc)&1;
+// nkp + l: exchange factor (times (-1)^(lc+ld+L)) of k = px + 2l, px = (la+ld)&1; zero
+// past max_k and where the reference skips the term (|ang| < 5e-16, mat_els.f90:568).
+// nkp is even so that both halves are 16-byte aligned.
+BS2E_HD int site_nkp(int kmax) { return (((kmax + 1) / 2) + 1) & ~1; }
+
+// sum over the multipoles of one parity in ascending order (mat_els.f90:566-570);
+// R[k] holds all multipoles of the candidate (zeros past max_k)
+template <int KMAX>
+BS2E_HD double site_dot_par(const double* cf, const double* R, int par)
 {
-    const int q = cand_q(cd), nd = cand_nd(cd);
-    SiteEntry e = pc.Tb[q];
-    if (pc.cut) e = entry_cut(e, s, site_nc(s, q));
-    const bool sup = nd >= (int)e.dlo && nd <= (int)e.dhi;
-    const bool sup_ex = nd >= (int)e.xlo && nd <= (int)e.xhi;
-    int rank;
-    if (LIST == kModeD) {
-        if (!sup) return;
-        rank = nd - (int)e.dlo;
-    } else if (LIST == kModeX) {
-        if (!sup_ex) return;
-        rank = nd - (int)e.xlo;
+    double acc = 0.0;
+    if (par == 0) {
+#pragma unroll
+        for (int i = 0; 2 * i < KMAX; ++i) acc += cf[i] * R[2 * i];
     } else {
-        if (!sup && !sup_ex) return;
-        rank = union_below(true, e.dlo, e.dhi, true, e.xlo, e.xhi, nd);
+#pragma unroll
+        for (int i = 0; 2 * i + 1 < KMAX; ++i) acc += cf[i] * R[2 * i + 1];
     }
-    const int stride = 2 * pc.kst;
-    double re = 0.0, im = 0.0;
-    const bool allowed = (sup && pc.dirany) || (sup_ex && pc.exany);
-    if (allowed) {
-        double res = 0.0;
-        if (sup) res += k_dot(pc.Rv + pc.pk.dlo * pc.kst + cand_slotD(cd), stride, pc.wa_d, pc.pk.nkd);
-        if (sup_ex) res += k_dot(pc.Rv + pc.pk.xlo * pc.kst + cand_slotX(cd), stride, pc.wa_x, pc.pk.nkx);
-        re = res;
-    }
-    const long long j = (long long)e.jbase + nd;
-    if (pc.diag) {
-        const bool storeS = sup || (sup_ex && pc.samex);
-        if (storeS) {
-            const BlockDesc bc = pl.blk[pc.bj];
-            Cplx h, sv;
-            one_body_terms(g, pl, ob, r, true, pc.samex, bc.l1, bc.l2, site_nc(s, q), nd, &h, &sv);
-            re += h.re;
-            im += h.im;
-            const long long pos =
-                pc.sbase + pc.spq[q] + union_below(true, e.dlo, e.dhi, pc.samex, e.xlo, e.xhi, nd);
-            Sidx[pos] = j;
-            Sdat[2 * pos] = sv.re;
-            Sdat[2 * pos + 1] = sv.im;
-        }
-    }
-    const long long pos = pc.hbase + pc.hpq[q] + rank;
-    Hidx[pos] = j;
-#if defined(__CUDA_ARCH__)
-    *reinterpret_cast<double2*>(Hdat + 2 * pos) = make_double2(re, im);
-#else
-    Hdat[2 * pos] = re;
-    Hdat[2 * pos + 1] = im;
-#endif
+    return acc;
+}
+
+// one-body and overlap part of a stored entry of the diagonal pair (column block ==
+// row block): adds H_1p to (re,im) and writes the S entry when one is stored
+BS2E_HD void site_diag_terms(const Geom& g, const Plan& pl, const OneBody& ob, const RowInfo& r,
+                             const OwnCand& c, const ModeSlot& m, bool samex, const unsigned short* spq,
+                             long long sbase, double* re, double* im, long long* Sidx, double* Sdat)
+{
+    const bool storeS = m.sup || (m.sup_ex && samex);
+    if (!storeS) return;
+    Cplx h, sv;
+    one_body_terms(g, pl, ob, r, true, samex, r.la, r.lb, c.nc, c.nd, &h, &sv);
+    *re += h.re;
+    *im += h.im;
+    const long long pos =
+        sbase + spq[c.q] + union_below(true, m.e.dlo, m.e.dhi, samex, m.e.xlo, m.e.xhi, c.nd);
+    Sidx[pos] = m.jcol;
+    Sdat[2 * pos] = sv.re;
+    Sdat[2 * pos + 1] = sv.im;
 }
 
 // storage mode that the pair effectively stores: a D+X pair whose exchange
@@ -312,6 +343,17 @@ BS2E_HD int effective_mode(int mode, int totD, int totX)
         if (totD == 0) return kModeX;
     }
     return mode;
+}
+
+// number of multipole registers the site kernel is instantiated for (0: none, the
+// row kernel is used)
+BS2E_HD int site_kmax_for(int K1)
+{
+    if (K1 <= 7) return 7;
+    if (K1 <= 13) return 13;
+    if (K1 <= 21) return 21;
+    if (K1 <= 31) return 31;
+    return 0;
 }
 
 }  // namespace bs2e

@@ -3,6 +3,8 @@
 // serial loops on the CPU, so the index logic of the GPU path can be checked
 // against the oracle in the GPU-less CI container.  Never linked into, loaded
 // by, or shipped with the product library.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -211,137 +213,211 @@ int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
     }
 }
 
-// emulates site_fill_kernel phase by phase: one "CTA" per radial site; warp
-// scans become serial prefix sums, everything lane-level comes from site_core.h
+}  // extern "C"
+
+// emulates site_fill_kernel<NT,KMAX> phase by phase: one "CTA" of nthreads threads per
+// radial site; warp scans / ballots become serial loops, everything lane-level comes
+// from site_core.h.  group_rows > 0 overrides the rows-per-group of the launcher (to
+// exercise the multi-group path on small bases).
+template <int KMAX>
+static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, long long row_hi,
+                              int group_rows, int nthreads, const int64_t* H_ptr, const int64_t* S_ptr,
+                              int64_t* H_idx, double* H_dat, int64_t* S_idx, double* S_dat)
+{
+    constexpr int NKP = (((KMAX + 1) / 2) + 1) & ~1;
+    const Geom& g = c->hg.g;
+    const Plan pl = hp_.view();
+    if (pl.nkp != NKP || site_nkp(KMAX) != NKP) throw std::logic_error("packed factor stride mismatch");
+    const OneBody ob{c->Hb.data(), c->Sb.data()};
+    const double* R = c->R.data();
+    const int K1 = g.K1, ncmax = site_max_nc(g), nblk = pl.nblk;
+    const int G = group_rows > 0 ? std::min(group_rows, 32) : std::min(32, nblk);
+    const int NT = nthreads;
+    const size_t plane = (size_t)g.P * g.ldP;
+    std::vector<SiteEntry> T((size_t)nblk * ncmax);
+    std::vector<unsigned short> hp((size_t)nblk * kModes * (ncmax + 1)), sp((size_t)nblk * (ncmax + 1));
+    struct Rec { long long hpos; int cf, meta; };
+    std::vector<unsigned> pm((size_t)G * nblk);
+    std::vector<int> gcnt((size_t)nblk * kModes);
+    std::vector<Rec> rlist((size_t)nblk * G);
+    std::vector<double> cfs((size_t)G * nblk * 2 * NKP);
+    std::vector<int> cprefix(ncmax + 1);
+    struct RowC { long long hbase, sbase; int bi, la, lb; };
+    std::vector<RowC> rcache(G);
+    long long* Hi = reinterpret_cast<long long*>(H_idx);
+    long long* Si = reinterpret_cast<long long*>(S_idx);
+    const int nsites = (int)hp_.site_key.size();
+    long long rows_seen = 0;
+    for (int sidx = 0; sidx < nsites; ++sidx) {
+        const unsigned key = hp_.site_key[sidx];
+        const bool wantX = site_wants_X(g, pl.max_nd, (int)(key >> 16));
+        if (wantX != (sidx < hp_.nsites_x)) throw std::logic_error("site filed in the wrong launch class");
+        const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), wantX);
+        const int nnc = s.nnc;
+        if (nnc > ncmax) throw std::logic_error("site exceeds smem bounds");
+        // phase 1
+        std::fill(cprefix.begin(), cprefix.end(), -12345);
+        if (wantX) {
+            int run = 0;
+            for (int q = 0; q < nnc; ++q) { cprefix[q] = run; run += site_cand_DX_count(s, q); }
+            cprefix[nnc] = run;
+            if (run > site_max_slots(g)) throw std::logic_error("candidate list exceeds its bound");
+        }
+        for (int bj = 0; bj < nblk; ++bj)
+            for (int q = 0; q < nnc; ++q) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+        // phase 2
+        std::fill(hp.begin(), hp.end(), (unsigned short)0xdead);
+        for (int task = 0; task < nblk * kModes; ++task) {
+            const int bj = task / kModes, mode = task - bj * kModes;
+            if (!wantX && (mode == kModeX || mode == kModeDX)) continue;
+            const bool useD = mode_useD(mode), useX = mode_useX(mode), diag = mode == kModeDiag;
+            const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
+            int hrun = 0, srun = 0;
+            for (int q = 0; q < nnc; ++q) {
+                SiteEntry e = T[bj * ncmax + q];
+                if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
+                hp[(size_t)task * (ncmax + 1) + q] = (unsigned short)hrun;
+                hrun += entry_count(e, useD, useX);
+                if (diag) {
+                    sp[(size_t)bj * (ncmax + 1) + q] = (unsigned short)srun;
+                    srun += entry_count(e, true, samex);
+                }
+            }
+            hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)hrun;
+        }
+        const int* srows = hp_.site_rows.data() + hp_.site_ptr[sidx];
+        const int nr = hp_.site_ptr[sidx + 1] - hp_.site_ptr[sidx];
+        for (int g0 = 0; g0 < nr; g0 += G) {
+            const int gr = std::min(G, nr - g0);
+            // phase 3a
+            for (int ri = 0; ri < gr; ++ri) {
+                const int rowi = srows[g0 + ri];
+                ++rows_seen;
+                const RowInfo r = row_info(pl, rowi);
+                if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
+                const long long wrow = rowi - row_lo;
+                rcache[ri] = RowC{H_ptr[wrow] - 1, S_ptr[wrow] - 1, r.bi, r.la, r.lb};
+                int run = 0;
+                for (int bj = 0; bj < nblk; ++bj) {
+                    int cnt = 0, mode = pair_mode(pl, r, bj);
+                    if (mode >= 0) {
+                        const unsigned short* hb = hp.data() + (bj * kModes) * (ncmax + 1) + nnc;
+                        mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
+                        cnt = (wantX || mode != kModeX) ? hb[mode * (ncmax + 1)] : 0;
+                    }
+                    pm[ri * nblk + bj] = cnt > 0 ? pm_pack(run, mode, (r.la + pl.blk[bj].l1) & 1) : 0u;
+                    run += cnt;
+                }
+                if (run != H_ptr[wrow + 1] - H_ptr[wrow])
+                    throw std::logic_error("site fill: row " + std::to_string(rowi) + " counted differently");
+            }
+            // phase 3b: the pairs of each column block, filed by storage mode
+            for (int bj = 0; bj < nblk; ++bj) {
+                int cnt[kModes] = {0, 0, 0, 0};
+                for (int ri = 0; ri < gr; ++ri) {
+                    const unsigned v = pm[ri * nblk + bj];
+                    if (pm_valid(v)) ++cnt[pm_mode(v)];
+                }
+                for (int mode = 0; mode < kModes; ++mode) gcnt[bj * kModes + mode] = cnt[mode];
+                if (cnt[kModeDiag] > 1) throw std::logic_error("diagonal pair with several rows");
+                int pos[kModes] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+                for (int ri = 0; ri < gr; ++ri) {
+                    const unsigned v = pm[ri * nblk + bj];
+                    if (!pm_valid(v)) continue;
+                    const int where = pos[pm_mode(v)]++;
+                    rlist[bj * G + where] = Rec{rcache[ri].hbase + pm_off(v), ri * nblk + bj, pm_pd(v) | (ri << 8)};
+                }
+            }
+            // packed factors of the group's pairs ("shared memory" copy)
+            std::fill(cfs.begin(), cfs.end(), std::nan(""));
+            for (int pair = 0; pair < gr * nblk; ++pair) {
+                if (!pm_valid(pm[pair])) continue;
+                const int ri = pair / nblk, bj = pair - ri * nblk;
+                const double* src = pl.angP + ((size_t)rcache[ri].bi * nblk + bj) * (2 * NKP);
+                std::copy(src, src + 2 * NKP, cfs.begin() + (size_t)pair * 2 * NKP);
+            }
+            // phase 4: thread t0+tid owns candidate column t
+            const int nc_all = site_num_cand(s, cprefix.data(), wantX);
+            for (int t0 = 0; t0 < nc_all; t0 += NT)
+                for (int tid = 0; tid < NT; ++tid) {
+                    const int t = t0 + tid;
+                    if (t >= nc_all) continue;
+                    const OwnCand cd = site_own_cand(g, s, cprefix.data(), wantX, t);
+                    double Rd[KMAX], Rx[KMAX];
+                    for (int k = 0; k < KMAX; ++k) {
+                        Rd[k] = (cd.inD && k < K1) ? R[(size_t)k * plane + (size_t)cd.rowD * g.ldP + cd.colD] : 0.0;
+                        Rx[k] = (cd.inX && k < K1) ? R[(size_t)k * plane + (size_t)cd.rowX * g.ldP + cd.colX] : 0.0;
+                    }
+                    for (int bj = 0; bj < nblk; ++bj) {
+                        const SiteEntry e = T[bj * ncmax + cd.q];
+                        const int lpar = (pl.blk[bj].l1 + pl.blk[bj].l2) & 1;
+                        const Rec* rl = rlist.data() + bj * G;
+                        for (int mode = 0; mode < kModes; ++mode) {
+                            const int nrow = gcnt[bj * kModes + mode];
+                            if (!nrow) continue;
+                            const Rec* rm = rl;
+                            rl += nrow;
+                            const bool diag = mode == kModeDiag;
+                            const ModeSlot ms = site_mode_slot(s, cd, e, hp.data() + (bj * kModes + mode) * (ncmax + 1),
+                                                               mode, diag && !pl.full);
+                            if (!(ms.sup || ms.sup_ex)) continue;
+                            for (int i = 0; i < nrow; ++i) {
+                                const Rec rec = rm[i];
+                                const RowC rc = rcache[rec.meta >> 8];
+                                const int pd = rec.meta & 1, px = pd ^ lpar;
+                                const double* cf = cfs.data() + (size_t)rec.cf * (2 * NKP);
+                                double res = 0.0;
+                                if (mode != kModeX) {
+                                    const double d = site_dot_par<KMAX>(cf, Rd, pd);
+                                    res += ms.sup ? d : 0.0;
+                                }
+                                if (mode != kModeD) {
+                                    const double x = site_dot_par<KMAX>(cf + NKP, Rx, px);
+                                    res += ms.sup_ex ? x : 0.0;
+                                }
+                                double re = res, im = 0.0;
+                                if (diag) {
+                                    if (rc.bi != bj) throw std::logic_error("diagonal pair on a foreign block");
+                                    RowInfo r;
+                                    r.i = 0; r.bi = rc.bi; r.na = s.na; r.nb = s.nb; r.la = rc.la; r.lb = rc.lb;
+                                    site_diag_terms(g, pl, ob, r, cd, ms, r.la == r.lb, sp.data() + bj * (ncmax + 1),
+                                                    rc.sbase, &re, &im, Si, S_dat);
+                                }
+                                const long long pos = rec.hpos + ms.rank;
+                                Hi[pos] = ms.jcol;
+                                H_dat[2 * pos] = re;
+                                H_dat[2 * pos + 1] = im;
+                            }
+                        }
+                    }
+                }
+        }
+    }
+    if (rows_seen != row_hi - row_lo + 1) throw std::logic_error("site list does not cover the rows");
+}
+
+extern "C" {
+
 int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                  const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
                  const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
-                 int64_t* S_idx, double* S_dat)
+                 int64_t* S_idx, double* S_dat, int64_t group_rows, int64_t nthreads)
 {
     try {
         const Geom& g = c->hg.g;
         HostPlan hp_ = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
         if (hp_.lmax > c->lmax_1p) throw std::invalid_argument("l exceeds max_l_1p");
         if (hp_.site_key.empty()) throw std::logic_error("no site list");
-        const Plan pl = hp_.view();
-        const OneBody ob{c->Hb.data(), c->Sb.data()};
-        const double* R = c->R.data();
-        const int K1 = g.K1, nsmax = site_max_slots(g), ncmax = site_max_nc(g), nblk = pl.nblk;
-        const size_t plane = (size_t)g.P * g.ldP;
-        std::vector<double> Rv(2 * (size_t)site_win_doubles(g)), wang(2 * K1);
-        std::vector<SiteEntry> T((size_t)nblk * ncmax);
-        std::vector<Cand> listD(nsmax / 2), listX(nsmax / 2), listDX(nsmax);
-        std::vector<int> cprefix(ncmax + 1);
-        std::vector<unsigned short> hp((size_t)nblk * kModes * (ncmax + 1)), sp((size_t)nblk * (ncmax + 1));
-        long long* Hi = reinterpret_cast<long long*>(H_idx);
-        long long* Si = reinterpret_cast<long long*>(S_idx);
-        const int nsites = (int)hp_.site_key.size();
-        long long rows_seen = 0;
-        for (int sidx = 0; sidx < nsites; ++sidx) {
-            const unsigned key = hp_.site_key[sidx];
-            const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu));
-            const int nnc = s.nnc;
-            if (nnc > ncmax || s.nD + s.nX > nsmax || s.nD > nsmax / 2 || s.nX > nsmax / 2)
-                throw std::logic_error("site exceeds smem bounds");
-            // phase 1
-            int run = 0;
-            for (int q = 0; q < nnc; ++q) { cprefix[q] = run; run += site_cand_DX_count(s, q); }
-            cprefix[nnc] = run;
-            if (run > nsmax) throw std::logic_error("list DX exceeds smem bound");
-            for (int bj = 0; bj < nblk; ++bj)
-                for (int q = 0; q < nnc; ++q) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
-            for (int t = 0; t < s.nD; ++t) listD[t] = site_cand_D(s, t);
-            for (int t = 0; t < s.nX; ++t) listX[t] = site_cand_X(s, t);
-            for (int q = 0; q < nnc; ++q)
-                for (int idx = 0; idx < cprefix[q + 1] - cprefix[q]; ++idx)
-                    listDX[cprefix[q] + idx] = site_cand_DX(s, q, idx);
-            // phase 0: the two boxes a TMA tile load delivers (zero fill outside the tensor)
-            std::fill(Rv.begin(), Rv.end(), -9.0);
-            for (int win = 0; win < 2; ++win) {
-                const int row0 = win ? site_rowX(g, s) : site_rowD(g, s);
-                const int col0 = win ? site_colX(g, s) : site_colD(g, s);
-                for (int k = 0; k < K1; ++k)
-                    for (int rr = 0; rr < 2 * g.w + 1; ++rr)
-                        for (int cc = 0; cc < s.cpad; ++cc) {
-                            const bool in = row0 + rr < g.P && col0 + cc < g.ldP;
-                            Rv[(size_t)win * s.xoff + (size_t)k * s.kst + rr * s.cpad + cc] =
-                                in ? R[(size_t)k * plane + (size_t)(row0 + rr) * g.ldP + col0 + cc] : 0.0;
-                        }
-            }
-            // phase 2
-            for (int task = 0; task < nblk * kModes; ++task) {
-                const int bj = task / kModes, mode = task - bj * kModes;
-                const bool useD = mode_useD(mode), useX = mode_useX(mode), diag = mode == kModeDiag;
-                const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
-                int hrun = 0, srun = 0;
-                for (int q = 0; q < nnc; ++q) {
-                    SiteEntry e = T[bj * ncmax + q];
-                    if (diag && !pl.full) e = entry_cut(e, s, site_nc(s, q));
-                    hp[(size_t)task * (ncmax + 1) + q] = (unsigned short)hrun;
-                    hrun += entry_count(e, useD, useX);
-                    if (diag) {
-                        sp[(size_t)bj * (ncmax + 1) + q] = (unsigned short)srun;
-                        srun += entry_count(e, true, samex);
-                    }
-                }
-                hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)hrun;
-            }
-            const int cutD = (s.na - s.cDlo) * s.dw;
-            const int cutX = imin(s.nX, imax(0, s.na - s.cXlo) * s.xw);
-            for (int ri = hp_.site_ptr[sidx]; ri < hp_.site_ptr[sidx + 1]; ++ri) {
-                const int rowi = hp_.site_rows[ri];
-                ++rows_seen;
-                const RowInfo r = row_info(pl, rowi);
-                if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
-                const long long wrow = rowi - row_lo;
-                int offrun = 0;  // phase 3 (running form of the scan over column blocks)
-                for (int bj = 0; bj < nblk; ++bj) {
-                    int mode = pair_mode(pl, r, bj);
-                    if (mode < 0) continue;
-                    const unsigned short* hb = hp.data() + (bj * kModes) * (ncmax + 1) + nnc;
-                    mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
-                    const int total = hb[mode * (ncmax + 1)];
-                    if (total == 0) continue;
-                    // phase 4
-                    const int cpl = r.bi * nblk + bj;
-                    const unsigned char fl = pl.flags[cpl];
-                    PairCtx pc;
-                    pc.pk = pair_k(pl.krange[cpl]);
-                    for (int i = 0; i < pc.pk.nkd; ++i) wang[i] = pl.angD[(size_t)cpl * K1 + pc.pk.dlo + 2 * i];
-                    for (int i = 0; i < pc.pk.nkx; ++i) wang[K1 + i] = pl.angX[(size_t)cpl * K1 + pc.pk.xlo + 2 * i];
-                    pc.Tb = T.data() + bj * ncmax;
-                    pc.hpq = hp.data() + (bj * kModes + mode) * (ncmax + 1);
-                    pc.spq = sp.data() + bj * (ncmax + 1);
-                    pc.Rv = Rv.data();
-                    pc.wa_d = wang.data();
-                    pc.wa_x = wang.data() + K1;
-                    pc.kst = s.kst;
-                    pc.bj = bj;
-                    pc.diag = mode == kModeDiag;
-                    pc.dirany = (fl & kDirAny) != 0;
-                    pc.exany = (fl & kExAny) != 0;
-                    pc.samex = pc.diag && r.la == r.lb;
-                    pc.cut = pc.diag && !pl.full;
-                    pc.hbase = H_ptr[wrow] - 1 + offrun;
-                    pc.sbase = S_ptr[wrow] - 1;
-                    const int win = pair_window(mode, hb[kModeD * (ncmax + 1)], hb[kModeX * (ncmax + 1)]);
-                    if (win == kModeD) {
-                        for (int t = pc.cut ? cutD : 0; t < s.nD; ++t)
-                            site_item<kModeD>(g, pl, ob, s, r, pc, listD[t], Hi, H_dat, Si, S_dat);
-                    } else if (win == kModeX) {
-                        for (int t = pc.cut ? cutX : 0; t < s.nX; ++t)
-                            site_item<kModeX>(g, pl, ob, s, r, pc, listX[t], Hi, H_dat, Si, S_dat);
-                    } else {
-                        for (int t = pc.cut ? cprefix[union_pos(s, s.na)] : 0; t < cprefix[nnc]; ++t)
-                            site_item<kModeDX>(g, pl, ob, s, r, pc, listDX[t], Hi, H_dat, Si, S_dat);
-                    }
-                    offrun += total;
-                }
-                if (offrun != H_ptr[wrow + 1] - H_ptr[wrow])
-                    throw std::logic_error("site fill: row " + std::to_string(rowi) + " counted differently");
-            }
+#define HC_SITE(KM)                                                                                  \
+    case KM:                                                                                         \
+        site_fill_emulate<KM>(c, hp_, row_lo, row_hi, (int)group_rows, (int)nthreads, H_ptr, S_ptr,  \
+                              H_idx, H_dat, S_idx, S_dat);                                           \
+        break;
+        switch (site_kmax_for(g.K1)) {
+            HC_SITE(7) HC_SITE(13) HC_SITE(21) HC_SITE(31)
+        default: throw std::logic_error("no site kernel instantiation for this max_k");
         }
-        if (rows_seen != row_hi - row_lo + 1) throw std::logic_error("site list does not cover the rows");
+#undef HC_SITE
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -89,6 +89,20 @@ def test_site_and_row_kernels_bit_identical(case):
                 assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
 
 
+def test_site_kernel_row_groups(case):
+    """sites whose rows do not fit one group of the site kernel (bit mask of <= 32 rows,
+    fewer when shared memory is short) are processed group by group"""
+    run, hc = case
+    hc.set_R(np.transpose(run.R, (2, 0, 1)))
+    hc.set_one_particle(run.H_vec, run.S)
+    s = max(run.syms, key=lambda q: q.n_config)
+    a = hc.block(s.l, s.conf_n, s.conf_l, True, kernel="site")
+    for group_rows, nthreads in ((1, 256), (2, 64), (3, 32)):   # few threads: several candidate passes
+        b = hc.block(s.l, s.conf_n, s.conf_l, True, kernel="site", group_rows=group_rows, nthreads=nthreads)
+        for (p1, i1, d1), (p2, i2, d2) in zip(a, b):
+            assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
+
+
 def test_row_range_fragments_concatenate(case):
     """sharding rows over GPUs: fragments of row ranges must tile the full CSR"""
     run, hc = case
