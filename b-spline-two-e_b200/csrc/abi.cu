@@ -83,6 +83,9 @@ int bs2e_ctx_create(int64_t k_spline, int64_t n_knots, const double* knots, int6
         if (prop.major < 10) throw Error("this library is built for sm_100a (B200) only");
         BS2E_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
+        BS2E_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         c->d_t = dev_upload(c->host.knots, c->stream);
         c->d_bp = dev_upload(c->host.bp, c->stream);
         c->d_glx = dev_upload(c->host.glx, c->stream);
@@ -111,6 +114,9 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         cudaFree(c->d_rowoff); cudaFree(c->d_pair);
         cudaFree(c->d_mom_rk); cudaFree(c->d_mom_rmk); cudaFree(c->d_pre); cudaFree(c->d_sufx);
         cudaFree(c->d_rd); cudaFree(c->d_R); cudaFree(c->d_Hb); cudaFree(c->d_Sb);
+        if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->ev_join) cudaEventDestroy(c->ev_join);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
     });

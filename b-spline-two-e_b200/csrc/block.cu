@@ -127,26 +127,29 @@ struct alignas(16) RowCache {  // per row of the group
 struct alignas(16) RowRec {    // one (row, column block) pair of the group, filed under (bj, mode)
     long long hpos;            // 0-based position of the pair's first H entry
     int cf;                    // index of the pair's packed factors (units of 2*NKP doubles)
-    int meta;                  // pd | ri << 8
+    int meta;                  // pd | px << 1 | ri << 8
 };
 
-constexpr int kSiteThreads = 128;
+constexpr int kSiteThreads = 128;   // sites with exchange windows
+constexpr int kSiteThreadsD = 256;  // sites without: one pass over the <= (2w+1)^2 candidates
 
 struct SiteSmem {   // element counts of the dynamic shared memory carve-up
     int ncmax;      // n_c slots
     int G;          // rows per group (<= 32)
     int cfsm;       // packed factors of the group's pairs staged in shared memory
+    int nl;         // l_max + 1 of the one-particle matrices
     size_t bytes;
 };
 
-__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G, int nkp, bool cfsm)
+__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G, int nkp, bool cfsm, int nl, bool wx)
 {
     const size_t ncmax = (size_t)site_max_nc(g);
     size_t b = 0;
+    b += sizeof(double) * (size_t)site_1p_doubles(g, nl);               // band rows of H_l and S
     b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                      // T
     b += sizeof(RowRec) * (size_t)nblk * G;                             // rlist
     b += sizeof(RowCache) * (size_t)G;                                  // rcache
-    if (cfsm) b += sizeof(double) * (size_t)G * nblk * 2 * nkp;         // cfs
+    if (cfsm) b += sizeof(double) * (size_t)G * nblk * (wx ? 2 : 1) * nkp;  // cfs (direct half only without X)
     b += sizeof(uchar4) * (size_t)((nblk + 3) & ~3);                    // gcnt
     b += sizeof(unsigned) * (size_t)((G * nblk + 3) & ~3);              // pm
     b += sizeof(int) * ((ncmax + 1 + 3) & ~3);                          // cprefix
@@ -196,11 +199,13 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     extern __shared__ __align__(16) unsigned char smraw[];
     const int K1 = g.K1, ncmax = lay.ncmax, G = lay.G;
     const int nblk = pl.nblk;
-    SiteEntry* T = reinterpret_cast<SiteEntry*>(smraw);
+    double* ob_s = reinterpret_cast<double*>(smraw);
+    SiteEntry* T = reinterpret_cast<SiteEntry*>(ob_s + site_1p_doubles(g, lay.nl));
     RowRec* rlist = reinterpret_cast<RowRec*>(T + (size_t)nblk * ncmax);
     RowCache* rcache = reinterpret_cast<RowCache*>(rlist + (size_t)nblk * G);
     double* cfs = reinterpret_cast<double*>(rcache + G);
-    uchar4* gcnt = reinterpret_cast<uchar4*>(cfs + (CFSM ? (size_t)G * nblk * 2 * NKP : 0));
+    constexpr int CFS = CFSM ? (WX ? 2 * NKP : NKP) : 2 * NKP;  // doubles per pair where the factors are read
+    uchar4* gcnt = reinterpret_cast<uchar4*>(cfs + (CFSM ? (size_t)G * nblk * CFS : 0));
     unsigned* pm = reinterpret_cast<unsigned*>(gcnt + ((nblk + 3) & ~3));
     int* cprefix = reinterpret_cast<int*>(pm + ((G * nblk + 3) & ~3));
     unsigned short* hp = reinterpret_cast<unsigned short*>(cprefix + ((ncmax + 1 + 3) & ~3));
@@ -216,6 +221,27 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     constexpr bool wantX = WX;
     const size_t plane = (size_t)g.P * g.ldP;
 
+    // The candidate column this thread owns and its R^k values (all multipoles, both
+    // windows), read once and streaming.  Without exchange windows the candidate list
+    // is known up front, so the loads of the first pass are issued here and complete
+    // behind phases 1-3.
+    OwnCand c;
+    double Rd[KMAX], Rx[WX ? KMAX : 1];
+    auto load_cand = [&](int t, bool act) {
+        c = site_own_cand(g, s, cprefix, wantX, act ? t : 0);
+        const double* pD = R + (size_t)c.rowD * g.ldP + c.colD;
+        const double* pX = R + (size_t)c.rowX * g.ldP + c.colX;
+        const bool onD = act && c.inD, onX = act && c.inX;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            Rd[k] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
+            if constexpr (WX) Rx[k] = (onX && k < K1) ? __ldcs(pX + (size_t)k * plane) : 0.0;
+        }
+        if constexpr (!WX) Rx[0] = 0.0;
+    };
+    const bool prefetched = !WX && s.nD <= NT && nr <= G;
+    if (prefetched) load_cand(tid, tid < s.nD);
+
     // ---- phase 1: clipped windows per column block; slot prefix of the candidate list ----
     if (warp == NW - 1 && wantX) {
         int run = 0;
@@ -230,6 +256,11 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     }
     for (int q = lane; q < nnc; q += 32)
         for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+    for (int idx = tid; idx < site_1p_doubles(g, lay.nl) / 2; idx += NT) {
+        const Cplx v = site_1p_source(g, ob, s, lay.nl, idx);
+        reinterpret_cast<double2*>(ob_s)[idx] = make_double2(v.re, v.im);
+    }
+    const SiteOneBody so{ob_s, ob_s + (size_t)lay.nl * 2 * (2 * g.w + 1) * 2};
     __syncthreads();
     // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode);
     //      one thread per (bj, mode), serial over the slots ----
@@ -307,12 +338,13 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                 for (int q = 0; q < kModes; ++q)
                     if (q == mode) where = pos[q]++;
                 const RowCache rc = rcache[ri];
+                const int px = pm_pd(v) ^ ((pl.blk[bj].l1 + pl.blk[bj].l2) & 1);
                 rlist[bj * G + where] = RowRec{rc.hbase + pm_off(v), CFSM ? ri * nblk + bj : rc.bi * nblk + bj,
-                                               pm_pd(v) | (ri << 8)};
+                                               pm_pd(v) | (px << 1) | (ri << 8)};
             }
         }
         if (CFSM) {  // packed factors of the group's pairs -> shared memory (16-byte units)
-            const int per = NKP;  // double2 per pair
+            const int per = CFS / 2;  // double2 per pair
             for (int idx = tid; idx < gr * nblk * per; idx += NT) {
                 const int pair = idx / per, l = idx - pair * per;
                 const int ri = pair / nblk, bj = pair - ri * nblk;
@@ -329,26 +361,12 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
         for (int t0 = 0; t0 < nc_all; t0 += NT) {
             const int t = t0 + tid;
             const bool act = t < nc_all;
-            const OwnCand c = site_own_cand(g, s, cprefix, wantX, act ? t : 0);
-            double Rd[KMAX], Rx[WX ? KMAX : 1];
-            {
-                const double* pD = R + (size_t)c.rowD * g.ldP + c.colD;
-                const double* pX = R + (size_t)c.rowX * g.ldP + c.colX;
-                const bool onD = act && c.inD, onX = act && c.inX;
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) {   // read once, streaming
-                    Rd[k] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
-                    if constexpr (WX) Rx[k] = (onX && k < K1) ? __ldcs(pX + (size_t)k * plane) : 0.0;
-                }
-                if constexpr (!WX) Rx[0] = 0.0;
-            }
+            if (!(prefetched && t0 == 0)) load_cand(t, act);
             if (__ballot_sync(0xffffffffu, act) == 0u) continue;  // warp without candidates
             for (int bj = 0; bj < nblk; ++bj) {
                 const uchar4 gc = gcnt[bj];
                 if ((gc.x | gc.y | gc.z | gc.w) == 0) continue;
                 const SiteEntry e = T[bj * ncmax + c.q];
-                const BlockDesc bc = pl.blk[bj];
-                const int lpar = (bc.l1 + bc.l2) & 1;
                 const RowRec* rl = rlist + bj * G;
 #pragma unroll
                 for (int mode = 0; mode < kModes; ++mode) {
@@ -367,8 +385,8 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
 #pragma unroll 2
                         for (int i = 0; i < nrow; ++i) {
                             const RowRec rec = rm[i];
-                            const int pd = rec.meta & 1, px = pd ^ lpar;
-                            const double* cf = cfbase + (size_t)rec.cf * (2 * NKP);
+                            const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
+                            const double* cf = cfbase + (size_t)rec.cf * CFS;
                             double res = 0.0;
                             if (mode != kModeX) {
                                 double cD[NKP];
@@ -393,8 +411,8 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                     } else {  // exactly one row: the row whose own block is bj
                         const RowRec rec = rm[0];
                         const RowCache rc = rcache[rec.meta >> 8];
-                        const int pd = rec.meta & 1, px = pd ^ lpar;
-                        const double* cf = cfbase + (size_t)rec.cf * (2 * NKP);
+                        const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
+                        const double* cf = cfbase + (size_t)rec.cf * CFS;
                         double cD[NKP];
                         load_coefs<NKP, CFSM>(cf, cD);
                         const double d = site_dot_par<KMAX>(cD, Rd, pd);
@@ -407,11 +425,9 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                             res += ms.sup_ex ? x : 0.0;
                         }
                         if (stored) {
-                            RowInfo r;
-                            r.i = 0; r.bi = rc.bi; r.na = s.na; r.nb = s.nb; r.la = rc.la; r.lb = rc.lb;
                             double re = res, im = 0.0;
-                            site_diag_terms(g, pl, ob, r, c, ms, r.la == r.lb, sp + bj * (ncmax + 1), rc.sbase,
-                                            &re, &im, Sidx, Sd);
+                            site_diag_terms(g, pl, so, s, rc.la, rc.lb, c, ms, rc.la == rc.lb, sp + bj * (ncmax + 1),
+                                            rc.sbase, &re, &im, Sidx, Sd);
                             const long long pos = rec.hpos + ms.rank;
                             Hidx[pos] = jcol;
                             *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(re, im);
@@ -569,29 +585,39 @@ void block_assemble(bs2e_block* b)
         lay.ncmax = site_max_nc(g);
         lay.G = std::min(32, nblk);   // a site has at most one row per (l1,l2) block
         lay.cfsm = sizeof(double) * (size_t)lay.G * nblk * 2 * nkp <= kSiteCoefSmem;
-        lay.bytes = site_smem_bytes(g, nblk, lay.G, nkp, lay.cfsm != 0);
+        lay.nl = c->lmax_1p + 1;
+        lay.bytes = site_smem_bytes(g, nblk, lay.G, nkp, lay.cfsm != 0, lay.nl, true);
         if (lay.bytes > kSiteSmemLimit) use_site = false;
     }
     if (use_site) {
         const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
-        auto launch = [&](auto kern, int nt, int first, int count) {
+        // the launch without exchange windows goes to the side stream so that it fills
+        // the SMs the other launch leaves idle in its last wave
+        const bool fork = b->nsites_x > 0 && b->nsites_x < b->nsites;
+        if (fork) {
+            BS2E_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+            BS2E_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        }
+        auto launch = [&](auto kern, int nt, bool wx, int first, int count) {
             if (count <= 0) return;
-            BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
-            kern<<<(unsigned)count, nt, lay.bytes, c->stream>>>(
+            cudaStream_t st = (fork && !wx) ? c->side : c->stream;
+            const size_t bytes = site_smem_bytes(g, nblk, lay.G, site_nkp(kmax), lay.cfsm != 0, lay.nl, wx);
+            BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            kern<<<(unsigned)count, nt, bytes, st>>>(
                 c->dg, b->dplan, c->one_body(), sl, lay, first, c->d_R, b->row_lo, b->d_Hptr, b->d_Sptr,
                 b->d_Hidx, reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
             BS2E_LAUNCHED();
         };
-        constexpr int NT = kSiteThreads;
+        constexpr int NT = kSiteThreads, NTD = kSiteThreadsD;
         const int nx = b->nsites_x, nd = b->nsites - b->nsites_x;
 #define BS2E_SITE(KM)                                                          \
     case KM:                                                                   \
         if (lay.cfsm) {                                                        \
-            launch(site_fill_kernel<NT, KM, true, true>, NT, 0, nx);           \
-            launch(site_fill_kernel<NT, KM, true, false>, NT, nx, nd);         \
+            launch(site_fill_kernel<NT, KM, true, true>, NT, true, 0, nx);           \
+            launch(site_fill_kernel<NTD, KM, true, false>, NTD, false, nx, nd);         \
         } else {                                                               \
-            launch(site_fill_kernel<NT, KM, false, true>, NT, 0, nx);          \
-            launch(site_fill_kernel<NT, KM, false, false>, NT, nx, nd);        \
+            launch(site_fill_kernel<NT, KM, false, true>, NT, true, 0, nx);          \
+            launch(site_fill_kernel<NTD, KM, false, false>, NTD, false, nx, nd);        \
         }                                                                      \
         break;
         switch (kmax) {
@@ -599,6 +625,10 @@ void block_assemble(bs2e_block* b)
         default: throw Error("block_assemble: no site kernel for this max_k");
         }
 #undef BS2E_SITE
+        if (fork) {
+            BS2E_CUDA(cudaEventRecord(c->ev_join, c->side));
+            BS2E_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        }
     } else {
         block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,
                             c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, b->row_lo, nrows,

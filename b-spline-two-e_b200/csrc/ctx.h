@@ -55,6 +55,9 @@ struct bs2e_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // side stream + events: the two site-kernel launches of a block run concurrently
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int max_k = 0;
 
     // host copy of the basis geometry

@@ -287,7 +287,10 @@ BS2E_HD ModeSlot site_mode_slot(const Site& s, const OwnCand& c, SiteEntry e, co
     const bool useD = mode_useD(mode), useX = mode_useX(mode);
     m.sup = useD && c.nd >= (int)e.dlo && c.nd <= (int)e.dhi;
     m.sup_ex = useX && c.nd >= (int)e.xlo && c.nd <= (int)e.xhi;
-    m.rank = (int)hpq[c.q] + union_below(useD, e.dlo, e.dhi, useX, e.xlo, e.xhi, c.nd);
+    // only read for stored columns: inside a single window the rank is the distance from its start
+    if (!useX) m.rank = (int)hpq[c.q] + (c.nd - (int)e.dlo);
+    else if (!useD) m.rank = (int)hpq[c.q] + (c.nd - (int)e.xlo);
+    else m.rank = (int)hpq[c.q] + union_below(true, e.dlo, e.dhi, true, e.xlo, e.xhi, c.nd);
     m.jcol = e.jbase + c.nd;
     return m;
 }
@@ -315,16 +318,63 @@ BS2E_HD double site_dot_par(const double* cf, const double* R, int par)
     return acc;
 }
 
+// ---- one-particle matrices of the site ----------------------------------------------
+// The diagonal pair of a row needs H_l(n_a,.), H_l(n_b,.), S(n_a,.), S(n_b,.) inside the
+// band only; the CTA copies those 2(l_max+2) band rows to shared memory once:
+//   Hs[(l*2 + r)*(2w+1) + d], Ss[r*(2w+1) + d], r = 0: n = n_a, r = 1: n = n_b,
+//   d = n' - n + w, complex interleaved.
+struct SiteOneBody { const double* Hs; const double* Ss; };
+BS2E_HD int site_1p_doubles(const Geom& g, int nl) { return (nl + 1) * 2 * (2 * g.w + 1) * 2; }
+// element idx of the copy (idx < site_1p_doubles / 2 complex numbers, H rows first)
+BS2E_HD Cplx site_1p_source(const Geom& g, const OneBody& ob, const Site& s, int nl, int idx)
+{
+    const int bw = 2 * g.w + 1;
+    const int row = idx / bw, d = idx - row * bw;
+    const int n = (row & 1) ? s.nb : s.na;
+    const int np = n + d - g.w;
+    if (np < 1 || np > g.nb) return Cplx{0.0, 0.0};
+    return row < 2 * nl ? band_H(g, ob, row >> 1, n, np) : band_S(g, ob, n, np);
+}
+BS2E_HD Cplx site_S(const Geom& g, const SiteOneBody& so, int r, int n, int np)
+{
+    const int d = np - n + g.w;
+    if (d < 0 || d > 2 * g.w) return Cplx{0.0, 0.0};
+    const double* q = so.Ss + (r * (2 * g.w + 1) + d) * 2;
+    return Cplx{q[0], q[1]};
+}
+BS2E_HD Cplx site_H(const Geom& g, const SiteOneBody& so, int l, int r, int n, int np)
+{
+    const int d = np - n + g.w;
+    if (d < 0 || d > 2 * g.w) return Cplx{0.0, 0.0};
+    const double* q = so.Hs + ((l * 2 + r) * (2 * g.w + 1) + d) * 2;
+    return Cplx{q[0], q[1]};
+}
+
 // one-body and overlap part of a stored entry of the diagonal pair (column block ==
-// row block): adds H_1p to (re,im) and writes the S entry when one is stored
-BS2E_HD void site_diag_terms(const Geom& g, const Plan& pl, const OneBody& ob, const RowInfo& r,
+// row block): adds H_1p to (re,im) and writes the S entry when one is stored.  Same
+// statements as one_body_terms (core.h) with the band rows read from the site's copy.
+BS2E_HD void site_diag_terms(const Geom& g, const Plan& pl, const SiteOneBody& so, const Site& s, int la, int lb,
                              const OwnCand& c, const ModeSlot& m, bool samex, const unsigned short* spq,
                              long long sbase, double* re, double* im, long long* Sidx, double* Sdat)
 {
     const bool storeS = m.sup || (m.sup_ex && samex);
     if (!storeS) return;
-    Cplx h, sv;
-    one_body_terms(g, pl, ob, r, true, samex, r.la, r.lb, c.nc, c.nd, &h, &sv);
+    const int nc = c.nc, nd = c.nd;
+    Cplx h = Cplx{0.0, 0.0}, sv = Cplx{0.0, 0.0};
+    {
+        const Cplx Sbd = site_S(g, so, 1, s.nb, nd), Sac = site_S(g, so, 0, s.na, nc);
+        h = cadd(h, cmul(site_H(g, so, la, 0, s.na, nc), Sbd));
+        h = cadd(h, cmul(site_H(g, so, lb, 1, s.nb, nd), Sac));
+        sv = cadd(sv, cmul(Sac, Sbd));
+    }
+    if (samex) {
+        const double sgn = ((pl.L + la + lb) & 1) ? -1.0 : 1.0;
+        const Cplx Sbc = site_S(g, so, 1, s.nb, nc), Sad = site_S(g, so, 0, s.na, nd);
+        Cplx hx = cadd(cmul(site_H(g, so, la, 0, s.na, nd), Sbc), cmul(site_H(g, so, lb, 1, s.nb, nc), Sad));
+        h = cadd(h, Cplx{hx.re * sgn, hx.im * sgn});
+        Cplx sx2 = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
+        sv = cadd(sv, sx2);
+    }
     *re += h.re;
     *im += h.im;
     const long long pos =

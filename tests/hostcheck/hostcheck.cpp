@@ -256,6 +256,14 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
         const int nnc = s.nnc;
         if (nnc > ncmax) throw std::logic_error("site exceeds smem bounds");
         // phase 1
+        const int nl = c->lmax_1p + 1;
+        std::vector<double> ob_s(site_1p_doubles(g, nl));
+        for (int idx = 0; idx < site_1p_doubles(g, nl) / 2; ++idx) {
+            const Cplx v = site_1p_source(g, ob, s, nl, idx);
+            ob_s[2 * idx] = v.re;
+            ob_s[2 * idx + 1] = v.im;
+        }
+        const SiteOneBody so{ob_s.data(), ob_s.data() + (size_t)nl * 2 * (2 * g.w + 1) * 2};
         std::fill(cprefix.begin(), cprefix.end(), -12345);
         if (wantX) {
             int run = 0;
@@ -325,7 +333,8 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
                     const unsigned v = pm[ri * nblk + bj];
                     if (!pm_valid(v)) continue;
                     const int where = pos[pm_mode(v)]++;
-                    rlist[bj * G + where] = Rec{rcache[ri].hbase + pm_off(v), ri * nblk + bj, pm_pd(v) | (ri << 8)};
+                    const int px = pm_pd(v) ^ ((pl.blk[bj].l1 + pl.blk[bj].l2) & 1);
+                    rlist[bj * G + where] = Rec{rcache[ri].hbase + pm_off(v), ri * nblk + bj, pm_pd(v) | (px << 1) | (ri << 8)};
                 }
             }
             // packed factors of the group's pairs ("shared memory" copy)
@@ -350,7 +359,6 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
                     }
                     for (int bj = 0; bj < nblk; ++bj) {
                         const SiteEntry e = T[bj * ncmax + cd.q];
-                        const int lpar = (pl.blk[bj].l1 + pl.blk[bj].l2) & 1;
                         const Rec* rl = rlist.data() + bj * G;
                         for (int mode = 0; mode < kModes; ++mode) {
                             const int nrow = gcnt[bj * kModes + mode];
@@ -364,7 +372,7 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
                             for (int i = 0; i < nrow; ++i) {
                                 const Rec rec = rm[i];
                                 const RowC rc = rcache[rec.meta >> 8];
-                                const int pd = rec.meta & 1, px = pd ^ lpar;
+                                const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
                                 const double* cf = cfs.data() + (size_t)rec.cf * (2 * NKP);
                                 double res = 0.0;
                                 if (mode != kModeX) {
@@ -378,10 +386,8 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
                                 double re = res, im = 0.0;
                                 if (diag) {
                                     if (rc.bi != bj) throw std::logic_error("diagonal pair on a foreign block");
-                                    RowInfo r;
-                                    r.i = 0; r.bi = rc.bi; r.na = s.na; r.nb = s.nb; r.la = rc.la; r.lb = rc.lb;
-                                    site_diag_terms(g, pl, ob, r, cd, ms, r.la == r.lb, sp.data() + bj * (ncmax + 1),
-                                                    rc.sbase, &re, &im, Si, S_dat);
+                                    site_diag_terms(g, pl, so, s, rc.la, rc.lb, cd, ms, rc.la == rc.lb,
+                                                    sp.data() + bj * (ncmax + 1), rc.sbase, &re, &im, Si, S_dat);
                                 }
                                 const long long pos = rec.hpos + ms.rank;
                                 Hi[pos] = ms.jcol;
