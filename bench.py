@@ -122,27 +122,13 @@ def ncu_traffic_per_launch(workload):
 
 
 # ---------------------------------------------------------------------------
-# row partition for N>1: contiguous ranges with equal stored-element counts
-# ---------------------------------------------------------------------------
-def balanced_ranges(weights, parts):
-    cum = np.concatenate([[0], np.cumsum(weights, dtype=np.float64)])
-    n = len(weights)
-    cuts = [0]
-    for r in range(1, parts):
-        cuts.append(int(np.searchsorted(cum, cum[-1] * r / parts)))
-    cuts.append(n)
-    for q in range(1, len(cuts)):           # keep every range non-empty
-        cuts[q] = min(max(cuts[q], cuts[q - 1] + 1), n - (parts - q))
-    return [(cuts[r] + 1, cuts[r + 1]) for r in range(parts)]
-
-
-# ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import bs2e
+    from bs2e.sharding import balanced_ranges
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus:

@@ -3,6 +3,10 @@
 
     python scripts/ncu_summary.py launches gpurun_out/rXX/launches.csv
     python scripts/ncu_summary.py full     gpurun_out/rXX/full.ncu-rep
+    python scripts/ncu_summary.py traffic  gpurun_out/rXX/full.ncu-rep cfg3 5 > profiles/ncu_fill_traffic.json
+        (DRAM bytes of the fill kernels of one captured step divided by the number of
+         symmetry blocks = per "launch" of bench.py's roofline, which times the two
+         concurrent site_fill launches of a block as one)
 """
 import collections
 import csv
@@ -60,5 +64,25 @@ def full(path):
         print(f"| {short(r[kn])} | " + " | ".join(vals) + " |")
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def traffic(path, workload, nblocks):
+    import json
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    kn = hdr.index("Kernel Name")
+    rd, wr, tm = (hdr.index(m) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
+    fills = [r for r in data if "site_fill" in r[kn] or "block_fill" in r[kn]]
+    tot_r = sum(float(r[rd].replace(",", "")) * UNIT[units[rd]] for r in fills)
+    tot_w = sum(float(r[wr].replace(",", "")) * UNIT[units[wr]] for r in fills)
+    print(json.dumps({workload: {"dram_bytes_per_launch": (tot_r + tot_w) / int(nblocks),
+                                 "dram_read_bytes_per_launch": tot_r / int(nblocks),
+                                 "dram_write_bytes_per_launch": tot_w / int(nblocks),
+                                 "fill_kernel_launches_captured": len(fills), "blocks": int(nblocks),
+                                 "source": path}}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -1,0 +1,119 @@
+"""N>1 logic on CPU: two processes (torch.distributed, gloo backend) shard the
+rows of every symmetry block the way bench.py does on N GPUs -- nnz-balanced
+contiguous row ranges from the count pass, no data-path collective, fragments
+concatenated in row order -- with the CPU emulation of the kernels
+(tests/hostcheck) standing in for the device.  The concatenated CSR must equal
+the oracle's."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from bs2e.sharding import balanced_ranges, concat_fragments
+from conftest import SMALL_CASES
+
+
+def test_balanced_ranges_cover_and_balance():
+    rng = np.random.default_rng(3)
+    w = rng.integers(0, 50, size=1000)
+    for parts in (1, 2, 3, 8):
+        r = balanced_ranges(w, parts)
+        assert r[0][0] == 1 and r[-1][1] == len(w)
+        assert all(r[q][1] + 1 == r[q + 1][0] for q in range(parts - 1))
+        assert all(hi >= lo for lo, hi in r)
+        loads = [w[lo - 1:hi].sum() for lo, hi in r]
+        assert max(loads) - min(loads) <= 2 * w.max()
+    # degenerate weights: ranges stay non-empty
+    r = balanced_ranges(np.zeros(5), 5)
+    assert r == [(1, 1), (2, 2), (3, 3), (4, 4), (5, 5)]
+    r = balanced_ranges([100, 0, 0, 0], 3)
+    assert all(hi >= lo for lo, hi in r) and r[-1][1] == 4
+    with pytest.raises(ValueError):
+        balanced_ranges([1, 2], 3)
+
+
+def test_concat_fragments_offsets_row_pointers():
+    a = (np.array([1, 3, 3]), np.array([4, 9]), np.array([1.0, 2.0]))
+    b = (np.array([1, 2]), np.array([7]), np.array([3.0]))
+    p, i, d = concat_fragments([a, b])
+    assert p.tolist() == [1, 3, 3, 4] and i.tolist() == [4, 9, 7] and d.tolist() == [1.0, 2.0, 3.0]
+    with pytest.raises(ValueError):
+        concat_fragments([(np.array([2, 3]), np.array([1]), np.array([1.0]))])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    for p in (root, os.path.join(root, "b-spline-two-e_b200"), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from hostcheck_lib import HostCheck
+    from oracle import bs2e_oracle as O
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        run = O.OracleRun(**SMALL_CASES[case])
+        run.slater(); run.rk_map(); run.one_particle(); run.basis()
+        glx, glw = O.gauss_legendre(run.p["k_GL"])
+        hc = HostCheck(run.p["k"], run.grid, run.p["max_k"], glx, glw)
+        hc.set_R(np.transpose(run.R, (2, 0, 1)))      # every rank holds the whole R^k
+        hc.set_one_particle(run.H_vec, run.S)
+        full = run.p["full"]
+        my_elems = 0
+        results = []
+        for s in run.syms:
+            if s.n_config < world:
+                continue
+            # count pass on every rank (cheap), identical ranges everywhere
+            (Hp, _, _), (Sp, _, _) = hc.block(s.l, s.conf_n, s.conf_l, full)
+            ranges = balanced_ranges(np.diff(Hp) + np.diff(Sp), world)
+            lo, hi = ranges[rank]
+            (fHp, fHi, fHd), (fSp, fSi, fSd) = hc.block(s.l, s.conf_n, s.conf_l, full, rows=(lo, hi))
+            my_elems += len(fHi) + len(fSi)
+            frag = [None] * world
+            dist.all_gather_object(frag, ((fHp, fHi, fHd), (fSp, fSi, fSd)))   # host-side concatenation
+            if rank == 0:
+                H = concat_fragments([f[0] for f in frag])
+                S = concat_fragments([f[1] for f in frag])
+                nnz = O.count_nnz(run.bs.k, s, run.p["max_k"], full)
+                Ho, So, emitted = run.block(s, nnz=nnz)
+                results.append((H, S, Ho, So, nnz))
+        # the reductions bench.py uses: total elements (sum), time (max)
+        t = torch.tensor([float(my_elems)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        m = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert m.item() == world
+            total = 0
+            for H, S, Ho, So, nnz in results:
+                assert np.array_equal(H[0], Ho.index_ptr) and np.array_equal(H[1], Ho.indices)
+                assert np.array_equal(S[0], So.index_ptr) and np.array_equal(S[1], So.indices)
+                scale = np.abs(Ho.data).max()
+                assert np.max(np.abs(H[2] - Ho.data)) <= 1e-12 * scale
+                assert np.max(np.abs(S[2] - So.data)) <= 1e-12 * np.abs(So.data).max()
+                total += nnz[0] + nnz[1]
+            assert int(t.item()) == total and len(results) > 0
+            open(os.path.join(out_dir, "ok"), "w").write(str(total))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["trunc_k5", "wide_k6"])
+def test_two_ranks_tile_every_block(case, tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").exists()
