@@ -24,8 +24,6 @@
 #include <set>
 #include <unordered_map>
 
-#include <cuda.h>
-
 #include "ctx.h"
 #include "plan.h"
 #include "site_core.h"

@@ -1,6 +1,5 @@
 // ctx.h -- internal state behind the opaque handles of include/bs2e.h
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -80,8 +79,6 @@ struct bs2e_ctx {
     // stage B product
     double* d_R = nullptr;  // [K1][P][ldP]
     bool have_R = false;
-    CUtensorMap tmapR{};    // TMA descriptor of d_R with the site-window box (block.cu)
-    bool have_tmap = false;
 
     // stage C inputs (band storage)
     int lmax_1p = -1;

@@ -12,7 +12,6 @@
 // over the <= ks common cells using the prefix tables of stage A, and the
 // same-cell integrals r_d_k are added.  Bound: HBM write, 8 B per R^k value.
 #include "ctx.h"
-#include "site_core.h"
 
 namespace bs2e {
 
@@ -22,44 +21,12 @@ rk_build_kernel(Geom g, CellData cd, double* __restrict__ R)
     rk_build_thread(g, cd, R, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
 }
 
-// TMA descriptor of R[k][p1][p2] whose box is one staged site window of the stage-C fill
-// kernel: cpad columns x (2w+1) rows x K1 planes (site_core.h).  cuTensorMapEncodeTiled is
-// reached through the runtime so that libcuda is not a link-time dependency.
-static void make_rk_tensor_map(bs2e_ctx* c)
-{
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                 CUtensorMapFloatOOBfill);
-    c->have_tmap = false;
-    const Geom& g = c->hg;
-    const int bw = 2 * g.w + 1, cpad = site_cpad(g);
-    if (cpad > 256 || bw > 256 || g.K1 > 256) return;  // box extents are limited to 256
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess || !fn) {
-        cudaGetLastError();
-        return;
-    }
-    const cuuint64_t dims[3] = {(cuuint64_t)g.ldP, (cuuint64_t)g.P, (cuuint64_t)g.K1};
-    const cuuint64_t strides[2] = {(cuuint64_t)g.ldP * sizeof(double),
-                                   (cuuint64_t)g.P * g.ldP * sizeof(double)};
-    const cuuint32_t box[3] = {(cuuint32_t)cpad, (cuuint32_t)bw, (cuuint32_t)g.K1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult rc = ((EncodeFn)fn)(&c->tmapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->d_R, dims, strides, box,
-                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    c->have_tmap = rc == CUDA_SUCCESS;
-}
-
 void run_rk_build(bs2e_ctx* c)
 {
     if (!c->have_cells) throw Error("bs2e_rk_build: call bs2e_slater_cells first");
     const Geom& g = c->dg;
     if (!c->d_R) {
         c->d_R = dev_alloc<double>((size_t)g.K1 * g.P * g.ldP);
-        make_rk_tensor_map(c);
     }
     dim3 grid((g.ldP / 2 + kRkThreads - 1) / kRkThreads, (g.P + kRkRows - 1) / kRkRows, g.K1);
     rk_build_kernel<<<grid, kRkThreads, 0, c->stream>>>(g, c->cell_data(), c->d_R);

@@ -10,8 +10,11 @@
 // (hamiltonian.f90:164-165) and reads the same values of R^k; only the
 // angular factors and the (l_c,l_d) clipping differ.  The union of the two
 // windows, enumerated in CSR order (n_c ascending, n_d ascending), is the
-// CANDIDATE list of the site; slot numbering of the staged R^k values is
-// D-window row-major followed by X-window row-major.
+// CANDIDATE list of the site.  One thread of the site's CTA owns one candidate
+// column for the whole site: it keeps the column's R^k values of all
+// multipoles (both windows) in registers, and for every column block works out
+// once per storage mode whether and where the column is stored; the rows of
+// the site then differ only in their angular factors and output base.
 #pragma once
 #include "core.h"
 
@@ -23,18 +26,7 @@ struct Site {
     int nnc;     // number of n_c slots
     int cDlo, cDhi, dDlo, dDhi, dw, nD;  // D window: n_c range, n_d range, width, entries
     int cXlo, cXhi, dXlo, dXhi, xw, nX;  // X window
-    // staged R^k values: Rv[win*xoff + k*kst + r*cpad + c], r = n_c - first n_c of the
-    // window, c = n_d - first n_d (the box a TMA tile load drops into shared memory)
-    // The first column of a TMA box must be 16-byte aligned, so a box starts at the even
-    // column below the window and shD / shX (0 or 1) is the window's offset inside it.
-    int cpad, kst, xoff, shD, shX;
 };
-
-// padded column count of a staged window (TMA: inner box extent must be a multiple of 16 B)
-BS2E_HD int site_cpad(const Geom& g) { return 2 * g.w + 2; }  // 2w+1 columns + 1 for the alignment shift
-BS2E_HD int site_kst(const Geom& g) { return (2 * g.w + 1) * site_cpad(g); }
-// doubles per staged window, rounded so that the second window stays 128-byte aligned
-BS2E_HD int site_win_doubles(const Geom& g) { return (g.K1 * site_kst(g) + 15) & ~15; }
 
 // wantX = false: every exchange window of the site is clipped away by the basis
 // (n_a - w exceeds the largest n_2 of any configuration), the site is treated as if
@@ -59,11 +51,6 @@ BS2E_HD Site make_site(const Geom& g, int na, int nb, bool wantX)
     s.xw = s.dXhi - s.dXlo + 1;
     s.nD = (s.cDhi - s.cDlo + 1) * s.dw;
     s.nX = (s.cXhi - s.cXlo + 1) * s.xw;
-    s.cpad = site_cpad(g);
-    s.kst = site_kst(g);
-    s.xoff = site_win_doubles(g);
-    s.shD = pair_index(g, nb, s.dDlo) & 1;
-    s.shX = wantX ? (pair_index(g, na, s.dXlo) & 1) : 0;
     s.ncu = union2(s.cDlo, s.cDhi, s.cXlo, s.cXhi);
     s.nnc = union2_count(s.ncu);
     return s;
@@ -89,18 +76,6 @@ BS2E_HD Union2 site_nd_union(const Site& s, int nc)
     const bool d = site_nc_inD(s, nc), x = site_nc_inX(s, nc);
     return union2(d ? s.dDlo : 0, d ? s.dDhi : -1, x ? s.dXlo : 0, x ? s.dXhi : -1);
 }
-
-// slot of a column (n_c,n_d) in the staged D / X window (caller guarantees membership)
-BS2E_HD int site_slotD(const Site& s, int nc, int nd) { return (nc - s.cDlo) * s.cpad + (nd - s.dDlo) + s.shD; }
-BS2E_HD int site_slotX(const Site& s, int nc, int nd) { return s.xoff + (nc - s.cXlo) * s.cpad + (nd - s.dXlo) + s.shX; }
-
-// first row / column of R (pair indices) of the staged windows: window D holds
-// R^k[pair(n_a,n_c)][pair(n_b,n_d)], window X holds R^k[pair(n_b,n_c)][pair(n_a,n_d)]
-// (the exchange integral read through R^k(ab;dc) = R^k(ba;cd))
-BS2E_HD int site_rowD(const Geom& g, const Site& s) { return pair_index(g, s.na, s.cDlo); }
-BS2E_HD int site_colD(const Geom& g, const Site& s) { return pair_index(g, s.nb, s.dDlo) & ~1; }
-BS2E_HD int site_rowX(const Geom& g, const Site& s) { return pair_index(g, s.nb, s.cXlo); }
-BS2E_HD int site_colX(const Geom& g, const Site& s) { return pair_index(g, s.na, s.dXlo) & ~1; }
 
 // ---- per (site, column block) tables ---------------------------------------
 // Clipping of the two windows by the configurations that exist in column block
