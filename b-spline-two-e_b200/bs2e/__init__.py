@@ -49,6 +49,7 @@ ABI = {
     "bs2e_block_count": (C.c_int, [vp, i64, i64, _pi, _pi, i64, C.POINTER(i64), C.POINTER(i64)]),
     "bs2e_block_fill": (C.c_int, [vp, i64, i64, _pi, _pi, i64, vp, vp, vp, vp, vp, vp]),
     "bs2e_block_plan": (C.c_int, [vp, i64, i64, _pi, _pi, i64, i64, i64, C.POINTER(vp)]),
+    "bs2e_block_plan_ranges": (C.c_int, [vp, i64, i64, _pi, _pi, i64, i64, _pi, _pi, C.POINTER(vp)]),
     "bs2e_block_nnz": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "bs2e_block_row_counts": (C.c_int, [vp, vp, vp]),
     "bs2e_block_recount": (C.c_int, [vp]),
@@ -213,16 +214,17 @@ class CSR:
 class Block:
     """One symmetry block (or a row range of it) being assembled on the GPU."""
 
-    def __init__(self, ctx, handle, n_config, row_lo, row_hi):
+    def __init__(self, ctx, handle, n_config, ranges):
         self.ctx, self.h = ctx, handle
-        self.n_config, self.row_lo, self.row_hi = n_config, row_lo, row_hi
+        self.n_config, self.ranges = n_config, [(int(a), int(b)) for a, b in ranges]
+        self.row_lo, self.row_hi = self.ranges[0][0], self.ranges[-1][1]
         a, b = i64(), i64()
         _chk(lib().bs2e_block_nnz(self.h, C.byref(a), C.byref(b)))
         self.nnz_H, self.nnz_S = int(a.value), int(b.value)
 
     @property
     def nrows(self):
-        return self.row_hi - self.row_lo + 1
+        return sum(b - a + 1 for a, b in self.ranges)
 
     def row_counts(self):
         cH = np.zeros(self.nrows, np.int64)
@@ -373,13 +375,21 @@ class Context:
         nnz = self.block_count(sym, full)
         return self.block_fill(sym, full, nnz)
 
-    def block_plan(self, sym, full, rows=None) -> Block:
+    def block_plan(self, sym, full, rows=None, ranges=None) -> Block:
+        """rows=(lo,hi): one row range; ranges=[(lo,hi),...]: a union of ascending row ranges
+        (the multi-GPU partition, bs2e.sharding.site_partition)."""
         cn, cl = self._conf(sym)
-        lo, hi = (1, sym.n_config) if rows is None else rows
         h = vp()
+        if ranges is not None:
+            lo = np.ascontiguousarray([r[0] for r in ranges], np.int64)
+            hi = np.ascontiguousarray([r[1] for r in ranges], np.int64)
+            _chk(lib().bs2e_block_plan_ranges(self.h, sym.l, sym.n_config, cn, cl, int(bool(full)),
+                                              len(lo), lo, hi, C.byref(h)))
+            return Block(self, h, sym.n_config, list(zip(lo.tolist(), hi.tolist())))
+        lo, hi = (1, sym.n_config) if rows is None else rows
         _chk(lib().bs2e_block_plan(self.h, sym.l, sym.n_config, cn, cl, int(bool(full)), lo, hi,
                                    C.byref(h)))
-        return Block(self, h, sym.n_config, lo, hi)
+        return Block(self, h, sym.n_config, [(lo, hi)])
 
 
 # ---------------------------------------------------------------------------

@@ -51,3 +51,81 @@ def concat_fragments(frags):
         dat.append(np.asarray(d))
         run += nnz
     return np.concatenate(ptrs), np.concatenate(idx), np.concatenate(dat)
+
+
+def site_partition(conf_n, weights, parts):
+    """Deal the rows of a block to `parts` GPUs by the first radial index n(1).
+
+    All rows (l1,l2; n1,n2) of a radial site (n1,n2) read the same R^k values and the
+    site kernel amortises its per-site work over them, so a site must not be split
+    between GPUs.  The n1 axis is cut into `parts` contiguous intervals of (nearly)
+    equal total weight; a GPU owns every row whose n1 falls into its interval.  Inside
+    each (l1,l2) group of the configuration list those rows are contiguous
+    (orbital_tools.f90:157-193: n1 is the outer loop), so a part is a short list of
+    ascending row ranges -- the argument of bs2e_block_plan_ranges.
+
+    conf_n: (n_config, 2) array of term%configs(:)%n; weights: per-row work (stored
+    H + S entries).  Returns a list of `parts` lists of (lo, hi), 1-based inclusive;
+    a part may be empty when there are fewer distinct n1 than parts.
+    """
+    n1 = np.asarray(conf_n)[:, 0].astype(np.int64)
+    w = np.asarray(weights, np.float64)
+    nmax = int(n1.max())
+    per_n1 = np.bincount(n1, weights=w, minlength=nmax + 1)[1:]          # index n1-1
+    present = np.flatnonzero(np.bincount(n1, minlength=nmax + 1)[1:] > 0) + 1
+    if len(present) >= parts:
+        cuts = balanced_ranges(per_n1[present - 1], parts)               # over the present n1 values
+        bounds = [(int(present[lo - 1]), int(present[hi - 1])) for lo, hi in cuts]
+    else:
+        bounds = [(int(v), int(v)) for v in present] + [(1, 0)] * (parts - len(present))
+    out = []
+    for a, b in bounds:
+        mine = (n1 >= a) & (n1 <= b)
+        edge = np.diff(np.concatenate([[0], mine.astype(np.int8), [0]]))
+        starts, ends = np.flatnonzero(edge == 1) + 1, np.flatnonzero(edge == -1)
+        out.append([(int(s), int(e)) for s, e in zip(starts, ends)])
+    return out
+
+
+def merge_fragments(n_config, parts):
+    """Assemble the CSR of a whole block from per-GPU fragments of row-range unions.
+
+    parts: list of (ranges, (index_ptr, indices, data)); ranges as given to
+    bs2e_block_plan_ranges, the fragment arrays as bs2e_block_download returns them
+    (rows of the union in ascending order, index_ptr starting at 1).  Every row
+    1..n_config must be covered exactly once.
+    """
+    counts = np.full(n_config, -1, np.int64)
+    for ranges, (p, _, _) in parts:
+        p = np.asarray(p, np.int64)
+        cnt = np.diff(p)
+        k = 0
+        for lo, hi in ranges:
+            n = hi - lo + 1
+            if np.any(counts[lo - 1:hi] >= 0):
+                raise ValueError("row ranges of different fragments overlap")
+            counts[lo - 1:hi] = cnt[k:k + n]
+            k += n
+        if k != len(cnt):
+            raise ValueError("fragment rows do not match its ranges")
+    if np.any(counts < 0):
+        raise ValueError("fragments do not cover every row")
+    ptr = np.concatenate([[1], 1 + np.cumsum(counts)]).astype(np.int64)
+    nnz = int(ptr[-1] - 1)
+    idx = np.empty(nnz, np.int64)
+    dat = None
+    for ranges, (p, i, d) in parts:
+        p = np.asarray(p, np.int64)
+        if dat is None:
+            dat = np.empty(nnz, np.asarray(d).dtype)
+        k = 0
+        for lo, hi in ranges:
+            n = hi - lo + 1
+            src0, src1 = int(p[k] - 1), int(p[k + n] - 1)        # one contiguous run per range
+            dst0 = int(ptr[lo - 1] - 1)
+            idx[dst0:dst0 + (src1 - src0)] = np.asarray(i)[src0:src1]
+            dat[dst0:dst0 + (src1 - src0)] = np.asarray(d)[src0:src1]
+            k += n
+    if dat is None:
+        dat = np.empty(0, np.complex128)
+    return ptr, idx, dat

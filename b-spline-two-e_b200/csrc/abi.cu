@@ -246,7 +246,18 @@ int bs2e_block_plan(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
     return guarded("bs2e_block_plan", [&] {
         if (!c || !conf_n || !conf_l || !blk) throw Error("null argument");
         use_device(c);
-        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, row_lo, row_hi);
+        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &row_lo, &row_hi);
+    });
+}
+
+int bs2e_block_plan_ranges(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
+                           const int64_t* conf_l, int64_t full, int64_t n_ranges,
+                           const int64_t* range_lo, const int64_t* range_hi, bs2e_block** blk)
+{
+    return guarded("bs2e_block_plan_ranges", [&] {
+        if (!c || !conf_n || !conf_l || !blk || !range_lo || !range_hi) throw Error("null argument");
+        use_device(c);
+        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, n_ranges, range_lo, range_hi);
     });
 }
 
@@ -346,7 +357,8 @@ int bs2e_block_count(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* co
     return guarded("bs2e_block_count", [&] {
         if (!c || !conf_n || !conf_l) throw Error("null argument");
         use_device(c);
-        bs2e_block* b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, n_config);
+        const int64_t one = 1;
+        bs2e_block* b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &one, &n_config);
         if (nnz_H) *nnz_H = b->nnzH;
         if (nnz_S) *nnz_S = b->nnzS;
         const ParkKey key{c, L, n_config, full != 0, conf_hash(n_config, conf_n, conf_l)};
@@ -375,7 +387,8 @@ int bs2e_block_fill(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
             auto it = g_parked.find(key);
             if (it != g_parked.end()) { b = it->second; g_parked.erase(it); }
         }
-        if (!b) b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, n_config);
+        const int64_t one = 1;
+        if (!b) b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &one, &n_config);
         try {
             block_assemble(b);
             block_download(b, H_ptr, H_idx, H_dat, S_ptr, S_idx, S_dat);

@@ -33,13 +33,13 @@ namespace bs2e {
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-__global__ void block_count_kernel(Geom g, Plan pl, long long row_lo, long long nrows,
+__global__ void block_count_kernel(Geom g, Plan pl, long long nrows,
                                    long long* __restrict__ cntH, long long* __restrict__ cntS)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx > nrows) return;
     long long h = 0, s = 0;
-    if (idx < nrows) row_count(g, pl, (int)(row_lo + idx), &h, &s);
+    if (idx < nrows) row_count(g, pl, pl.rows[idx], &h, &s);
     cntH[idx] = h;  // slot nrows holds 0 so that the scan yields the total
     cntS[idx] = s;
 }
@@ -55,7 +55,7 @@ __global__ void ptr_one_based_kernel(long long n, long long* __restrict__ a, lon
 constexpr int kFillWarps = 8;
 
 __global__ void __launch_bounds__(kFillWarps * 32)
-block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, long long row_lo,
+block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R,
                   long long nrows, const long long* __restrict__ Hptr,
                   const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
                   double2* __restrict__ Hdat, long long* __restrict__ Sidx,
@@ -65,7 +65,7 @@ block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R, lon
     if (wrow >= nrows) return;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const RowInfo r = row_info(pl, (int)(row_lo + wrow));
+    const RowInfo r = row_info(pl, pl.rows[wrow]);
     long long hpos = Hptr[wrow] - 1, spos = Sptr[wrow] - 1;
 
     for_each_chunk(g, pl, r, [&](int bj, int nc, const Segment& s, const Coupling& c, int base, int hi) {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void load_coefs(const double* __restrict__ cf, double
 template <int NT, int KMAX, bool CFSM, bool WX>
 __global__ void __launch_bounds__(NT, KMAX <= 13 ? (WX ? 512 : 768) / NT : 256 / NT)
 site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int site_off, const double* __restrict__ R,
-                 long long row_lo, const long long* __restrict__ Hptr,
+                 const long long* __restrict__ Hptr,
                  const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
                  double2* __restrict__ Hdat, long long* __restrict__ Sidx,
                  double2* __restrict__ Sdat)
@@ -295,7 +295,7 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
             const int rowi = srows[g0 + ri];
             const RowInfo r = row_info(pl, rowi);
             if (lane == 0) {
-                const long long wrow = (long long)rowi - row_lo;
+                const long long wrow = pl.row_local[rowi - 1];
                 rcache[ri] = RowCache{Hptr[wrow] - 1, Sptr[wrow] - 1, r.bi, r.la, r.lb, 0};
             }
             int run = 0;
@@ -457,9 +457,9 @@ void block_count_scan(bs2e_block* b, bool read_totals)
 {
     bs2e_ctx* c = b->ctx;
     cudaStream_t st = c->stream;
-    const long long nrows = b->row_hi - b->row_lo + 1;
+    const long long nrows = b->nrows;
     block_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(
-        c->dg, b->dplan, b->row_lo, nrows, b->d_cntH, b->d_cntS);
+        c->dg, b->dplan, nrows, b->d_cntH, b->d_cntS);
     BS2E_LAUNCHED();
     size_t tmp = b->scan_tmp_bytes;
     BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntH, b->d_Hptr, nrows + 1, st));
@@ -485,11 +485,12 @@ void block_count_scan(bs2e_block* b, bool read_totals)
 // plan: derive the block structure from the configuration list, count, scan
 // ---------------------------------------------------------------------------
 bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
-                       const int64_t* conf_l, int full, long long row_lo, long long row_hi)
+                       const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
+                       const int64_t* range_hi)
 {
     HostPlan hp;
     try {
-        hp = build_host_plan(c->hg, L, n_config, conf_n, conf_l, full, row_lo, row_hi);
+        hp = build_host_plan(c->hg, L, n_config, conf_n, conf_l, full, n_ranges, range_lo, range_hi);
     } catch (const std::invalid_argument& e) {
         throw Error(e.what());
     }
@@ -499,8 +500,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     b->L = L;
     b->full = full ? 1 : 0;
     b->n_config = n_config;
-    b->row_lo = row_lo;
-    b->row_hi = row_hi;
+    b->nrows = (long long)hp.rows.size();
     b->lmax = hp.lmax;
     try {
         cudaStream_t st = c->stream;
@@ -514,6 +514,8 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         b->d_row_n1 = dev_upload(hp.row_n1, st);
         b->d_row_n2 = dev_upload(hp.row_n2, st);
         b->d_row_blk = dev_upload(hp.row_blk, st);
+        b->d_rows = dev_upload(hp.rows, st);
+        b->d_row_local = dev_upload(hp.row_local, st);
         b->nsites = (int)hp.site_key.size();
         b->nsites_x = hp.nsites_x;
         if (b->nsites > 0) {
@@ -537,9 +539,12 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         pl.row_n1 = b->d_row_n1;
         pl.row_n2 = b->d_row_n2;
         pl.row_blk = b->d_row_blk;
+        pl.nrows = (int)hp.rows.size();
+        pl.rows = b->d_rows;
+        pl.row_local = b->d_row_local;
         pl.max_nd = hp.max_nd;
 
-        const long long nrows = row_hi - row_lo + 1;
+        const long long nrows = b->nrows;
         b->d_cntH = dev_alloc<long long>(nrows + 1);
         b->d_cntS = dev_alloc<long long>(nrows + 1);
         b->d_Hptr = dev_alloc<long long>(nrows + 1);
@@ -568,7 +573,7 @@ void block_assemble(bs2e_block* b)
         b->d_Sidx = dev_alloc<long long>(b->nnzS);
         b->d_Sdat = dev_alloc<double>(2 * (size_t)b->nnzS);
     }
-    const long long nrows = b->row_hi - b->row_lo + 1;
+    const long long nrows = b->nrows;
     // site kernel unless max_k exceeds its largest instantiation or its tables do
     // not fit shared memory; BS2E_FILL=row asks for the row kernel (A/B measurements)
     const Geom& g = c->dg;
@@ -602,7 +607,7 @@ void block_assemble(bs2e_block* b)
             const size_t bytes = site_smem_bytes(g, nblk, lay.G, site_nkp(kmax), lay.cfsm != 0, lay.nl, wx);
             BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             kern<<<(unsigned)count, nt, bytes, st>>>(
-                c->dg, b->dplan, c->one_body(), sl, lay, first, c->d_R, b->row_lo, b->d_Hptr, b->d_Sptr,
+                c->dg, b->dplan, c->one_body(), sl, lay, first, c->d_R, b->d_Hptr, b->d_Sptr,
                 b->d_Hidx, reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
             BS2E_LAUNCHED();
         };
@@ -629,7 +634,7 @@ void block_assemble(bs2e_block* b)
         }
     } else {
         block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,
-                            c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, b->row_lo, nrows,
+                            c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, nrows,
                                          b->d_Hptr, b->d_Sptr, b->d_Hidx,
                                          reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx,
                                          reinterpret_cast<double2*>(b->d_Sdat));
@@ -643,7 +648,7 @@ void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat
 {
     if (!b->assembled) throw Error("block_download: call bs2e_block_assemble first");
     cudaStream_t st = b->ctx->stream;
-    const long long nrows = b->row_hi - b->row_lo + 1;
+    const long long nrows = b->nrows;
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
         if (dst && bytes) BS2E_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     };
@@ -659,7 +664,7 @@ void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat
 void block_row_counts(bs2e_block* b, int64_t* cH, int64_t* cS)
 {
     cudaStream_t st = b->ctx->stream;
-    const long long nrows = b->row_hi - b->row_lo + 1;
+    const long long nrows = b->nrows;
     if (cH) BS2E_CUDA(cudaMemcpyAsync(cH, b->d_cntH, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, st));
     if (cS) BS2E_CUDA(cudaMemcpyAsync(cS, b->d_cntS, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, st));
     BS2E_CUDA(cudaStreamSynchronize(st));
@@ -698,6 +703,7 @@ void block_free(bs2e_block* b)
     cudaFree(b->d_blk); cudaFree(b->d_ncrow); cudaFree(b->d_flags); cudaFree(b->d_krange);
     cudaFree(b->d_angD); cudaFree(b->d_angX); cudaFree(b->d_angP);
     cudaFree(b->d_row_n1); cudaFree(b->d_row_n2); cudaFree(b->d_row_blk);
+    cudaFree(b->d_rows); cudaFree(b->d_row_local);
     cudaFree(b->d_site_key); cudaFree(b->d_site_ptr); cudaFree(b->d_site_rows);
     cudaFree(b->d_cntH); cudaFree(b->d_cntS); cudaFree(b->d_Hptr); cudaFree(b->d_Sptr);
     cudaFree(b->d_Hidx); cudaFree(b->d_Sidx); cudaFree(b->d_Hdat); cudaFree(b->d_Sdat);

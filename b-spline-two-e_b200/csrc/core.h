@@ -247,6 +247,10 @@ struct Plan {
     const unsigned short* row_n1;   // [n_config]
     const unsigned short* row_n2;   // [n_config]
     const unsigned short* row_blk;  // [n_config]
+    // the planned rows (a union of ascending row ranges of the block)
+    int nrows;
+    const int* rows;       // [nrows]    local row -> configuration index (1-based)
+    const int* row_local;  // [n_config] configuration index - 1 -> local row, -1: not planned
 };
 
 // union of two closed integer intervals as <= 2 disjoint ascending intervals

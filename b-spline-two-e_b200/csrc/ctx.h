@@ -95,7 +95,7 @@ struct bs2e_ctx {
 struct bs2e_block {
     bs2e_ctx* ctx = nullptr;
     int L = 0, full = 0, lmax = 0;
-    long long n_config = 0, row_lo = 1, row_hi = 0;
+    long long n_config = 0, nrows = 0;   // nrows: planned rows (union of row ranges)
     bs2e::Plan dplan{};  // device pointers
     // device-side plan storage
     bs2e::BlockDesc* d_blk = nullptr;
@@ -104,6 +104,7 @@ struct bs2e_block {
     bs2e::KRange* d_krange = nullptr;
     double *d_angD = nullptr, *d_angX = nullptr, *d_angP = nullptr;
     unsigned short *d_row_n1 = nullptr, *d_row_n2 = nullptr, *d_row_blk = nullptr;
+    int *d_rows = nullptr, *d_row_local = nullptr;
     // rows grouped by radial site (site kernel)
     unsigned* d_site_key = nullptr;
     int *d_site_ptr = nullptr, *d_site_rows = nullptr;
@@ -130,7 +131,8 @@ void fetch_rk_keys(bs2e_ctx* c, long long n_keys, const int64_t* keys, double* v
 void fetch_rk_plane(bs2e_ctx* c, int k, double* out);
 
 bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
-                       const int64_t* conf_l, int full, long long row_lo, long long row_hi);
+                       const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
+                       const int64_t* range_hi);
 void block_count_scan(bs2e_block* b, bool read_totals);
 void block_assemble(bs2e_block* b);
 void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat, int64_t* S_ptr,

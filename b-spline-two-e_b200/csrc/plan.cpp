@@ -41,13 +41,28 @@ double ang_cached(int k, int la, int lb, int lc, int ld, int L)
 }  // namespace
 
 HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_t* conf_n,
-                         const int64_t* conf_l, int full, long long row_lo, long long row_hi)
+                         const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
+                         const int64_t* range_hi)
 {
     typedef std::invalid_argument Error;
     if (n_config <= 0) throw Error("block_plan: n_config must be positive");
     if (n_config > 2147483000LL) throw Error("block_plan: n_config exceeds 32-bit row indices");
-    if (row_lo < 1 || row_hi > n_config || row_hi < row_lo)
-        throw Error("block_plan: row range outside 1..n_config");
+    if (n_ranges < 1 || !range_lo || !range_hi) throw Error("block_plan: no row range given");
+    std::vector<int> rows;
+    std::vector<int> row_local((size_t)n_config, -1);
+    {
+        long long prev = 0;
+        for (long long q = 0; q < n_ranges; ++q) {
+            const long long lo = range_lo[q], hi = range_hi[q];
+            if (lo < 1 || hi > n_config || hi < lo) throw Error("block_plan: row range outside 1..n_config");
+            if (lo <= prev) throw Error("block_plan: row ranges must be ascending and disjoint");
+            for (long long i = lo; i <= hi; ++i) {
+                row_local[(size_t)i - 1] = (int)rows.size();
+                rows.push_back((int)i);
+            }
+            prev = hi;
+        }
+    }
     if (hg.nb > 65535) throw Error("block_plan: n_b exceeds 16-bit storage");
     if (L < 0 || L > 255) throw Error("block_plan: L out of range");
 
@@ -157,10 +172,10 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
     std::vector<int> site_ptr, site_rows;
     int nsites_x = 0;
     if ((size_t)stride * stride <= ((size_t)1 << 26)) {  // else: no site list, the row kernel is used
-        const long long nrows = row_hi - row_lo + 1;
+        const long long nrows = (long long)rows.size();
         const size_t nkeys = (size_t)stride * stride;
         std::vector<int> kcount(nkeys + 1, 0);
-        for (long long i = row_lo - 1; i < row_hi; ++i) ++kcount[(size_t)rn1[i] * stride + rn2[i] + 1];
+        for (const int r1 : rows) ++kcount[(size_t)rn1[r1 - 1] * stride + rn2[r1 - 1] + 1];
         // distinct sites, bucketed by (has exchange windows, number of rows)
         int max_nd_all = 0;
         for (auto v : rn2) max_nd_all = v > max_nd_all ? v : max_nd_all;
@@ -191,9 +206,9 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
         for (int q = 0; q < nsites; ++q) site_ptr[q + 1] += site_ptr[q];
         site_rows.resize((size_t)nrows);
         std::vector<int> cursor(site_ptr.begin(), site_ptr.end() - 1);
-        for (long long i = row_lo - 1; i < row_hi; ++i) {
-            const int sidx = site_of_key[(size_t)rn1[i] * stride + rn2[i]];
-            site_rows[cursor[sidx]++] = (int)(i + 1);
+        for (const int r1 : rows) {
+            const int sidx = site_of_key[(size_t)rn1[r1 - 1] * stride + rn2[r1 - 1]];
+            site_rows[cursor[sidx]++] = r1;
         }
     }
 
@@ -221,6 +236,8 @@ HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_
     hp.row_n1 = std::move(rn1);
     hp.row_n2 = std::move(rn2);
     hp.row_blk = std::move(rblk);
+    hp.rows = std::move(rows);
+    hp.row_local = std::move(row_local);
     return hp;
 }
 
@@ -243,6 +260,9 @@ Plan HostPlan::view() const
     pl.row_n1 = row_n1.data();
     pl.row_n2 = row_n2.data();
     pl.row_blk = row_blk.data();
+    pl.nrows = (int)rows.size();
+    pl.rows = rows.data();
+    pl.row_local = row_local.data();
     return pl;
 }
 

@@ -18,7 +18,8 @@ struct HostPlan {
     std::vector<double> angP;  // packed by parity for the site kernel, [nblk][nblk][2*nkp]
     int nkp = 0;
     std::vector<unsigned short> row_n1, row_n2, row_blk;
-    // rows row_lo..row_hi grouped by radial site (n1,n2): sites with exchange windows
+    std::vector<int> rows, row_local;  // planned rows: local -> configuration index, and back (-1: not planned)
+    // the planned rows grouped by radial site (n1,n2): sites with exchange windows
     // first, inside each class the sites with most rows first
     std::vector<unsigned> site_key;  // n1 << 16 | n2
     std::vector<int> site_ptr;       // [nsites+1]
@@ -27,7 +28,15 @@ struct HostPlan {
     Plan view() const;  // Plan over the HOST arrays
 };
 
+// rows = union of the n_ranges ascending, disjoint, inclusive 1-based ranges [range_lo[q], range_hi[q]]
 HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_t* conf_n,
-                         const int64_t* conf_l, int full, long long row_lo, long long row_hi);
+                         const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
+                         const int64_t* range_hi);
+inline HostPlan build_host_plan(const Geom& hg, int L, long long n_config, const int64_t* conf_n,
+                                const int64_t* conf_l, int full, long long row_lo, long long row_hi)
+{
+    const int64_t lo = row_lo, hi = row_hi;
+    return build_host_plan(hg, L, n_config, conf_n, conf_l, full, 1, &lo, &hi);
+}
 
 }  // namespace bs2e

@@ -16,9 +16,11 @@ integrals/s of stages A+B is reported beside it ("rk_integrals_per_s").
   --impl reference : the CPU oracle port of the reference path on the host cores
 
 N>1 (torchrun, one rank per GPU): strong scaling.  Every rank builds the R^k
-tensor (cheaper than an all-gather) and assembles a
-contiguous, nnz-balanced row range of every symmetry block; no data-path
-collective.  value = elements of all ranks / max-over-ranks stage-C time.
+tensor (cheaper than an all-gather) and assembles its
+share of the rows of every symmetry block -- rows are dealt by the first radial
+index of their configuration so that radial sites stay whole, balanced on the
+stored entries (bs2e.sharding.site_partition); no data-path collective.
+value = elements of all ranks / max-over-ranks stage-C time.
 """
 import argparse
 import ctypes
@@ -128,7 +130,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import bs2e
-    from bs2e.sharding import balanced_ranges
+    from bs2e.sharding import site_partition
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus:
@@ -174,13 +176,17 @@ def run_ours(args):
     ranges = []
     for s in syms:
         if world == 1:
-            ranges.append((1, s.n_config))
-        else:   # nnz-balanced contiguous row ranges from the count pass
+            ranges.append([(1, s.n_config)])
+        else:   # rows dealt by their first radial index (radial sites stay whole), balanced on
+                # the stored entries of the count pass
             tmp = ctx.block_plan(s, full)
             cH, cS = tmp.row_counts()
             tmp.free()
-            ranges.append(balanced_ranges(cH + cS, world)[rank])
-    blocks = [ctx.block_plan(s, full, rows=r) for s, r in zip(syms, ranges)]
+            mine = site_partition(s.conf_n, cH + cS, world)[rank]
+            if not mine:
+                raise SystemExit(f"rank {rank}: empty share of block L={s.l} (more GPUs than radial indices)")
+            ranges.append(mine)
+    blocks = [ctx.block_plan(s, full, ranges=r) for s, r in zip(syms, ranges)]
     for b in blocks:
         b.assemble()            # allocates the CSR fragment on the device
     ctx.sync()
@@ -271,7 +277,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: " + describe(args.workload, setup, syms),
                        "elements_per_step": total_elems, "rk_integrals_per_step": n_rk,
                        "l2": "256 MiB buffer written between timed iterations; R^k and CSR output exceed L2",
-                       "parallelism": "R^k replicated per GPU, symmetry-block rows sharded" if world > 1 else "single GPU"},
+                       "parallelism": "R^k replicated per GPU, rows of every symmetry block dealt by first radial index (radial sites stay whole), no collective" if world > 1 else "single GPU"},
             "stage_ms_per_step": {"A_cells": tA / K, "B_rk": tB / K, "C_blocks": tC / K},
             "rk_integrals_per_s": rk_per_s,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -340,14 +346,14 @@ def run_e2e(args, bs2e, ctx, setup, syms, ranges, blocks, S, H_vec, world, barri
         if count_bytes:
             h2d += sum(h.nbytes for h in H_vec) + S.nbytes
         for s, r, b in zip(syms, ranges, blocks):
-            n = r[1] - r[0] + 1
+            n = sum(hi - lo + 1 for lo, hi in r)
             out = tuple(a[:m] for a, m in zip(pin.arrs, (n + 1, max(b.nnz_H, 1), 2 * max(b.nnz_H, 1),
                                                          n + 1, max(b.nnz_S, 1), 2 * max(b.nnz_S, 1))))
             if world == 1:
                 nnz = ctx.block_count(s, full)              # H2D configs + count pass
                 ctx.block_fill(s, full, nnz, out=out)       # fill + D2H into pinned host arrays
             else:
-                blk = ctx.block_plan(s, full, rows=r)
+                blk = ctx.block_plan(s, full, ranges=r)
                 blk.assemble()
                 blk.download(out=out)
                 blk.free()
@@ -374,7 +380,7 @@ def run_e2e(args, bs2e, ctx, setup, syms, ranges, blocks, S, H_vec, world, barri
             "ms_per_step_stage_C": tC * 1e3 / steps,
             "rk_integrals_per_s": n_rk * steps / tAB,
             "api": "bs2e_set_one_particle + bs2e_block_count + bs2e_block_fill (pinned host arrays)"
-                   if world == 1 else "bs2e_block_plan(rows) + assemble + download (pinned host arrays)"}
+                   if world == 1 else "bs2e_block_plan_ranges + assemble + download (pinned host arrays)"}
 
 
 # ---------------------------------------------------------------------------

@@ -110,8 +110,18 @@ int bs2e_block_fill(bs2e_ctx *ctx, int64_t L, int64_t n_config,
 int bs2e_block_plan(bs2e_ctx *ctx, int64_t L, int64_t n_config,
                     const int64_t *conf_n, const int64_t *conf_l, int64_t full,
                     int64_t row_lo, int64_t row_hi, bs2e_block **blk);
+/* The same for a union of n_ranges ascending, disjoint row ranges
+ * [range_lo[q], range_hi[q]]; the fragment holds those rows in ascending order.
+ * This is the unit of the multi-GPU partition: rows are dealt to GPUs by the
+ * first radial index n(1) of their configuration, so that all rows of a radial
+ * site (which share their R^k values) stay on one GPU; inside every (l1,l2)
+ * group of the configuration list such rows form one contiguous range.      */
+int bs2e_block_plan_ranges(bs2e_ctx *ctx, int64_t L, int64_t n_config,
+                           const int64_t *conf_n, const int64_t *conf_l, int64_t full,
+                           int64_t n_ranges, const int64_t *range_lo,
+                           const int64_t *range_hi, bs2e_block **blk);
 int bs2e_block_nnz(bs2e_block *blk, int64_t *nnz_H, int64_t *nnz_S);
-/* per-row entry counts of the planned rows (row_hi-row_lo+1 values each) */
+/* per-row entry counts of the planned rows (one value per planned row each) */
 int bs2e_block_row_counts(bs2e_block *blk, int64_t *cnt_H, int64_t *cnt_S);
 /* Repeat the count pass + scan of an existing plan with everything already
  * resident on the device (no host synchronisation); used for device-timed

@@ -132,25 +132,25 @@ int hc_set_one_particle(HcCtx* c, int64_t max_l_1p, const double* H_vec, const d
     }
 }
 
-// emulates block_plan (count kernel + scan) for rows row_lo..row_hi
+// emulates block_plan (count kernel + scan) for the union of the given row ranges
 int hc_block_count(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
-                   const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
-                   int64_t* H_ptr, int64_t* S_ptr)
+                   const int64_t* conf_l, int64_t full, int64_t n_ranges, const int64_t* range_lo,
+                   const int64_t* range_hi, int64_t* H_ptr, int64_t* S_ptr)
 {
     try {
-        HostPlan hp = build_host_plan(c->hg.g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
+        HostPlan hp = build_host_plan(c->hg.g, (int)L, n_config, conf_n, conf_l, (int)full, n_ranges, range_lo, range_hi);
         const Plan pl = hp.view();
         long long accH = 1, accS = 1;
-        for (long long i = row_lo; i <= row_hi; ++i) {
+        for (int idx = 0; idx < pl.nrows; ++idx) {
             long long h, s;
-            row_count(c->hg.g, pl, (int)i, &h, &s);
-            H_ptr[i - row_lo] = accH;
-            S_ptr[i - row_lo] = accS;
+            row_count(c->hg.g, pl, pl.rows[idx], &h, &s);
+            H_ptr[idx] = accH;
+            S_ptr[idx] = accS;
             accH += h;
             accS += s;
         }
-        H_ptr[row_hi - row_lo + 1] = accH;
-        S_ptr[row_hi - row_lo + 1] = accS;
+        H_ptr[pl.nrows] = accH;
+        S_ptr[pl.nrows] = accS;
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -160,20 +160,21 @@ int hc_block_count(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
 
 // emulates block_fill_kernel: one "warp" per row, 32 lanes, ballot emulated
 int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
-                  const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
-                  const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
+                  const int64_t* conf_l, int64_t full, int64_t n_ranges, const int64_t* range_lo,
+                  const int64_t* range_hi, const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
                   int64_t* S_idx, double* S_dat)
 {
     try {
         const Geom& g = c->hg.g;
-        HostPlan hp = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
+        HostPlan hp = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, n_ranges, range_lo, range_hi);
         if (hp.lmax > c->lmax_1p) throw std::invalid_argument("l exceeds max_l_1p");
         const Plan pl = hp.view();
         const OneBody ob{c->Hb.data(), c->Sb.data()};
         const double* R = c->R.data();
-        for (long long i = row_lo; i <= row_hi; ++i) {
+        for (int wrow = 0; wrow < pl.nrows; ++wrow) {
+            const long long i = pl.rows[wrow];
             const RowInfo r = row_info(pl, (int)i);
-            long long hpos = H_ptr[i - row_lo] - 1, spos = S_ptr[i - row_lo] - 1;
+            long long hpos = H_ptr[wrow] - 1, spos = S_ptr[wrow] - 1;
             for_each_chunk(g, pl, r, [&](int bj, int nc, const Segment& s, const Coupling& cp, int base, int hi) {
                 bool storeS[32];
                 Element el[32];
@@ -202,7 +203,7 @@ int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                     }
                 spos += cnt;
             });
-            if (hpos != H_ptr[i - row_lo + 1] - 1 || spos != S_ptr[i - row_lo + 1] - 1)
+            if (hpos != H_ptr[wrow + 1] - 1 || spos != S_ptr[wrow + 1] - 1)
                 throw std::logic_error("fill wrote a different number of entries than counted, row " +
                                        std::to_string(i));
         }
@@ -220,7 +221,7 @@ int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
 // from site_core.h.  group_rows > 0 overrides the rows-per-group of the launcher (to
 // exercise the multi-group path on small bases).
 template <int KMAX>
-static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, long long row_hi,
+static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
                               int group_rows, int nthreads, const int64_t* H_ptr, const int64_t* S_ptr,
                               int64_t* H_idx, double* H_dat, int64_t* S_idx, double* S_dat)
 {
@@ -303,7 +304,8 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
                 ++rows_seen;
                 const RowInfo r = row_info(pl, rowi);
                 if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
-                const long long wrow = rowi - row_lo;
+                const long long wrow = pl.row_local[rowi - 1];
+                if (wrow < 0 || pl.rows[wrow] != rowi) throw std::logic_error("row map inconsistent");
                 rcache[ri] = RowC{H_ptr[wrow] - 1, S_ptr[wrow] - 1, r.bi, r.la, r.lb};
                 int run = 0;
                 for (int bj = 0; bj < nblk; ++bj) {
@@ -399,24 +401,24 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_, long long row_lo, l
                 }
         }
     }
-    if (rows_seen != row_hi - row_lo + 1) throw std::logic_error("site list does not cover the rows");
+    if (rows_seen != pl.nrows) throw std::logic_error("site list does not cover the rows");
 }
 
 extern "C" {
 
 int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
-                 const int64_t* conf_l, int64_t full, int64_t row_lo, int64_t row_hi,
-                 const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
+                 const int64_t* conf_l, int64_t full, int64_t n_ranges, const int64_t* range_lo,
+                 const int64_t* range_hi, const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
                  int64_t* S_idx, double* S_dat, int64_t group_rows, int64_t nthreads)
 {
     try {
         const Geom& g = c->hg.g;
-        HostPlan hp_ = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, row_lo, row_hi);
+        HostPlan hp_ = build_host_plan(g, (int)L, n_config, conf_n, conf_l, (int)full, n_ranges, range_lo, range_hi);
         if (hp_.lmax > c->lmax_1p) throw std::invalid_argument("l exceeds max_l_1p");
         if (hp_.site_key.empty()) throw std::logic_error("no site list");
 #define HC_SITE(KM)                                                                                  \
     case KM:                                                                                         \
-        site_fill_emulate<KM>(c, hp_, row_lo, row_hi, (int)group_rows, (int)nthreads, H_ptr, S_ptr,  \
+        site_fill_emulate<KM>(c, hp_, (int)group_rows, (int)nthreads, H_ptr, S_ptr,  \
                               H_idx, H_dat, S_idx, S_dat);                                           \
         break;
         switch (site_kmax_for(g.K1)) {

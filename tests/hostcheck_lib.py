@@ -34,8 +34,8 @@ def lib():
         L.hc_get_R.argtypes = [C.c_void_p, _pd]
         L.hc_set_R.argtypes = [C.c_void_p, _pd]
         L.hc_set_one_particle.argtypes = [C.c_void_p, i64, _pd, _pd]
-        L.hc_block_count.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, i64, _pi, _pi]
-        L.hc_block_fill.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, i64, _pi, _pi,
+        L.hc_block_count.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, _pi, _pi, _pi, _pi]
+        L.hc_block_fill.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, _pi, _pi, _pi, _pi,
                                     _pi, _pd, _pi, _pd]
         L.hc_site_fill.argtypes = L.hc_block_fill.argtypes + [i64, i64]
         _lib = L
@@ -89,22 +89,26 @@ class HostCheck:
         if lib().hc_set_one_particle(self.h, len(H_vec) - 1, Hv, Sf):
             raise RuntimeError(lib().hc_last_error().decode())
 
-    def block(self, L, conf_n, conf_l, full, rows=None, kernel="site", group_rows=0, nthreads=256):
+    def block(self, L, conf_n, conf_l, full, rows=None, kernel="site", group_rows=0, nthreads=256,
+              ranges=None):
         n = len(conf_n)
         cn = np.ascontiguousarray(conf_n.reshape(-1), np.int64)
         cl = np.ascontiguousarray(conf_l.reshape(-1), np.int64)
-        lo, hi = (1, n) if rows is None else rows
-        nr = hi - lo + 1
+        if ranges is None:
+            ranges = [(1, n) if rows is None else rows]
+        lo = np.ascontiguousarray([r[0] for r in ranges], np.int64)
+        hi = np.ascontiguousarray([r[1] for r in ranges], np.int64)
+        nr = int(np.sum(hi - lo + 1))
         Hp = np.zeros(nr + 1, np.int64)
         Sp = np.zeros(nr + 1, np.int64)
-        if lib().hc_block_count(self.h, L, n, cn, cl, int(full), lo, hi, Hp, Sp):
+        if lib().hc_block_count(self.h, L, n, cn, cl, int(full), len(lo), lo, hi, Hp, Sp):
             raise RuntimeError(lib().hc_last_error().decode())
         nH, nS = int(Hp[-1] - 1), int(Sp[-1] - 1)
         Hi = np.full(max(nH, 1), -1, np.int64)
         Si = np.full(max(nS, 1), -1, np.int64)
         Hd = np.full(2 * max(nH, 1), np.nan)
         Sd = np.full(2 * max(nS, 1), np.nan)
-        args = (self.h, L, n, cn, cl, int(full), lo, hi, Hp, Sp, Hi, Hd, Si, Sd)
+        args = (self.h, L, n, cn, cl, int(full), len(lo), lo, hi, Hp, Sp, Hi, Hd, Si, Sd)
         rc = lib().hc_site_fill(*args, group_rows, nthreads) if kernel == "site" else lib().hc_block_fill(*args)
         if rc:
             raise RuntimeError(lib().hc_last_error().decode())

@@ -299,3 +299,34 @@ def test_cfg4_scale_blocks_sampled_rows_and_properties():
             ref = O.CSR(None, cap[1], So.index_ptr[lo - 1:hi + 1], So.indices, So.data)
             assert_csr_equal(S, ref, what=f"cfg4 S rows {lo}-{hi} L={s.l}")
     ctx.close()
+
+
+def test_site_partition_fragments_merge_to_whole_block():
+    """the multi-GPU partition (rows dealt by first radial index, bs2e_block_plan_ranges) on one
+    device: the fragments of 3 'ranks' merge to the bit-identical whole block"""
+    from bs2e.sharding import merge_fragments, site_partition
+    run = O.OracleRun(**SMALL_CASES["wide_k6"])
+    run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    for s in run.syms:
+        whole = ctx.block_plan(s, False); whole.assemble()
+        H, S = whole.download()
+        cH, cS = whole.row_counts()
+        whole.free()
+        fragsH, fragsS = [], []
+        for ranges in site_partition(s.conf_n, cH + cS, 3):
+            if not ranges:
+                continue
+            f = ctx.block_plan(s, False, ranges=ranges); f.assemble()
+            fH, fS = f.download()
+            assert f.nrows == sum(b - a + 1 for a, b in ranges)
+            f.free()
+            fragsH.append((ranges, (fH.index_ptr, fH.indices, fH.data)))
+            fragsS.append((ranges, (fS.index_ptr, fS.indices, fS.data)))
+        for M, frags in ((H, fragsH), (S, fragsS)):
+            p, i, d = merge_fragments(s.n_config, frags)
+            assert np.array_equal(p, M.index_ptr) and np.array_equal(i, M.indices) and np.array_equal(d, M.data)
+    with pytest.raises(bs2e.Bs2eError):       # ranges must ascend
+        ctx.block_plan(run.syms[0], False, ranges=[(5, 6), (1, 2)])
+    ctx.close()

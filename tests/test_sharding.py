@@ -1,7 +1,8 @@
 """N>1 logic on CPU: two processes (torch.distributed, gloo backend) shard the
-rows of every symmetry block the way bench.py does on N GPUs -- nnz-balanced
-contiguous row ranges from the count pass, no data-path collective, fragments
-concatenated in row order -- with the CPU emulation of the kernels
+rows of every symmetry block the way bench.py does on N GPUs -- rows dealt by
+their first radial index so that radial sites stay whole, balanced on the stored
+entries of the count pass, no data-path collective, fragments merged in row
+order on the host -- with the CPU emulation of the kernels
 (tests/hostcheck) standing in for the device.  The concatenated CSR must equal
 the oracle's."""
 import os
@@ -11,7 +12,7 @@ import sys
 import numpy as np
 import pytest
 
-from bs2e.sharding import balanced_ranges, concat_fragments
+from bs2e.sharding import balanced_ranges, concat_fragments, merge_fragments, site_partition
 from conftest import SMALL_CASES
 
 
@@ -41,6 +42,50 @@ def test_concat_fragments_offsets_row_pointers():
     assert p.tolist() == [1, 3, 3, 4] and i.tolist() == [4, 9, 7] and d.tolist() == [1.0, 2.0, 3.0]
     with pytest.raises(ValueError):
         concat_fragments([(np.array([2, 3]), np.array([1]), np.array([1.0]))])
+
+
+def test_site_partition_keeps_sites_together_and_merges():
+    import bs2e
+    from oracle import bs2e_oracle as O
+    run = O.OracleRun(**SMALL_CASES["wide_k6"])
+    run.basis()
+    s = max(run.syms, key=lambda q: q.n_config)
+    n = s.n_config
+    rng = np.random.default_rng(5)
+    w = rng.integers(1, 30, n)
+    for parts in (1, 2, 3, 8):
+        part = site_partition(s.conf_n, w, parts)
+        assert len(part) == parts
+        owner = np.full(n, -1)
+        for r, ranges in enumerate(part):
+            assert all(a[1] < b[0] for a, b in zip(ranges, ranges[1:]))      # ascending, disjoint
+            for lo, hi in ranges:
+                assert np.all(owner[lo - 1:hi] == -1)
+                owner[lo - 1:hi] = r
+        assert np.all(owner >= 0)                                            # every row dealt once
+        # all rows that share n1 (hence every radial site) sit on one GPU; n1 intervals ascend with rank
+        n1 = s.conf_n[:, 0]
+        for v in np.unique(n1):
+            assert len(set(owner[n1 == v])) == 1
+        firsts = [n1[owner == r].min() for r in range(parts) if np.any(owner == r)]
+        assert firsts == sorted(firsts)
+        loads = np.array([w[owner == r].sum() for r in range(parts)])
+        if parts <= 3:
+            assert loads.max() <= 1.5 * loads.mean()
+        # fragments of a synthetic CSR (row i holds w[i] entries) merge back to the whole
+        ptr = np.concatenate([[1], 1 + np.cumsum(w)])
+        idx = np.arange(ptr[-1] - 1) * 7 % 1000 + 1
+        dat = np.arange(ptr[-1] - 1) * (1 + 2j)
+        frags = []
+        for ranges in part:
+            rows = np.concatenate([np.arange(lo, hi + 1) for lo, hi in ranges]) if ranges else np.zeros(0, int)
+            fp = np.concatenate([[1], 1 + np.cumsum(w[rows - 1])]).astype(np.int64)
+            sel = np.concatenate([np.arange(ptr[r - 1] - 1, ptr[r] - 1) for r in rows]) if len(rows) else np.zeros(0, int)
+            frags.append((ranges, (fp, idx[sel], dat[sel])))
+        mp_, mi, md = merge_fragments(n, frags)
+        assert np.array_equal(mp_, ptr) and np.array_equal(mi, idx) and np.array_equal(md, dat)
+    with pytest.raises(ValueError):
+        merge_fragments(n, frags[:-1] if len(frags) > 1 else [])
 
 
 def _free_port():
@@ -78,15 +123,20 @@ def _worker(rank, world, port, case, out_dir):
                 continue
             # count pass on every rank (cheap), identical ranges everywhere
             (Hp, _, _), (Sp, _, _) = hc.block(s.l, s.conf_n, s.conf_l, full)
-            ranges = balanced_ranges(np.diff(Hp) + np.diff(Sp), world)
-            lo, hi = ranges[rank]
-            (fHp, fHi, fHd), (fSp, fSi, fSd) = hc.block(s.l, s.conf_n, s.conf_l, full, rows=(lo, hi))
+            part = site_partition(s.conf_n, np.diff(Hp) + np.diff(Sp), world)
+            mine = part[rank]
+            if mine:
+                (fHp, fHi, fHd), (fSp, fSi, fSd) = hc.block(s.l, s.conf_n, s.conf_l, full, ranges=mine)
+            else:
+                e = np.zeros(0, np.int64)
+                (fHp, fHi, fHd), (fSp, fSi, fSd) = (np.ones(1, np.int64), e, np.zeros(0, complex)), \
+                                                   (np.ones(1, np.int64), e, np.zeros(0, complex))
             my_elems += len(fHi) + len(fSi)
             frag = [None] * world
-            dist.all_gather_object(frag, ((fHp, fHi, fHd), (fSp, fSi, fSd)))   # host-side concatenation
+            dist.all_gather_object(frag, (mine, (fHp, fHi, fHd), (fSp, fSi, fSd)))   # host-side merge
             if rank == 0:
-                H = concat_fragments([f[0] for f in frag])
-                S = concat_fragments([f[1] for f in frag])
+                H = merge_fragments(s.n_config, [(f[0], f[1]) for f in frag])
+                S = merge_fragments(s.n_config, [(f[0], f[2]) for f in frag])
                 nnz = O.count_nnz(run.bs.k, s, run.p["max_k"], full)
                 Ho, So, emitted = run.block(s, nnz=nnz)
                 results.append((H, S, Ho, So, nnz))
