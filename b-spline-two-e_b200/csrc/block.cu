@@ -9,10 +9,11 @@
 //   * the angular factors are tabulated once per pair of (l1,l2) blocks on
 //     the host (exact arithmetic, wigner.cpp) and uploaded,
 //   * the band partners of a row are GENERATED from the block structure of
-//     the configuration list (no pair scan): block_count_kernel counts them
-//     in closed form, an exclusive scan builds index_ptr, and
-//     block_fill_kernel (one warp per row) writes indices and values in
-//     ascending column order with coalesced 8/16-byte stores.
+//     the configuration list (no pair scan): site_count_kernel counts them
+//     in closed form per radial site, an exclusive scan builds index_ptr, and
+//     site_fill_kernel (one CTA per radial site, one thread per candidate
+//     column) writes indices and values; block_count_kernel / block_fill_kernel
+//     (one thread / one warp per row) remain as the general fallback.
 // Bound: HBM (24 B written per stored element + R^k gathers).
 #include <cub/device/device_scan.cuh>
 
@@ -42,14 +43,6 @@ __global__ void block_count_kernel(Geom g, Plan pl, long long nrows,
     if (idx < nrows) row_count(g, pl, pl.rows[idx], &h, &s);
     cntH[idx] = h;  // slot nrows holds 0 so that the scan yields the total
     cntS[idx] = s;
-}
-
-__global__ void ptr_one_based_kernel(long long n, long long* __restrict__ a, long long* __restrict__ b)
-{
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    a[idx] += 1;
-    b[idx] += 1;
 }
 
 constexpr int kFillWarps = 8;
@@ -437,6 +430,81 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     }
 }
 
+// Count pass on the site tables.  The row count of a row is the sum over its coupled
+// column blocks of the stored entries of the pair's storage mode, which depend on the
+// site and the column block only.  One WARP per site, no block-wide barrier: lane = column
+// block, one pass over the n_c slots gives the totals of all four storage modes; then
+// lane = column block again for each row of the site.  (block_count_kernel, one thread
+// per row, is kept for plans without a site list.)
+struct CountSmem { int stride; size_t bytes; };
+constexpr int kCountWarps = 4;
+
+__host__ __device__ inline size_t count_smem_bytes(int nblk)
+{
+    return sizeof(unsigned short) * (size_t)kCountWarps * (kModes + 1) * nblk + 16;
+}
+
+__global__ void __launch_bounds__(kCountWarps * 32)
+site_count_kernel(Geom g, Plan pl, SiteList sl, long long* __restrict__ cntH, long long* __restrict__ cntS)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int nblk = pl.nblk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned short* tot = reinterpret_cast<unsigned short*>(smraw) + (size_t)warp * (kModes + 1) * nblk;
+    unsigned short* stot = tot + (size_t)kModes * nblk;   // S entries of the diagonal pair of block bj
+    const int sidx = blockIdx.x * kCountWarps + warp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cntH[pl.nrows] = 0; cntS[pl.nrows] = 0; }  // the scan yields the totals there
+    if (sidx >= sl.nsites) return;
+    const unsigned key = sl.key[sidx];
+    const bool wantX = site_wants_X(g, pl.max_nd, (int)(key >> 16));
+    const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), wantX);
+    const int* srows = sl.rows + sl.ptr[sidx];
+    const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
+    const int nnc = s.nnc;
+    for (int bj = lane; bj < nblk; bj += 32) {
+        const bool samex = pl.blk[bj].l1 == pl.blk[bj].l2;
+        int cD = 0, cX = 0, cDX = 0, cG = 0, cS = 0;
+        for (int q = 0; q < nnc; ++q) {
+            const SiteEntry e = site_entry(g, pl, s, bj, q);
+            cD += entry_count(e, true, false);
+            cX += entry_count(e, false, true);
+            cDX += entry_count(e, true, true);
+            const SiteEntry ec = pl.full ? e : entry_cut(e, s, site_nc(s, q));
+            cG += entry_count(ec, true, true);
+            cS += entry_count(ec, true, samex);
+        }
+        tot[kModeD * nblk + bj] = (unsigned short)cD;
+        tot[kModeX * nblk + bj] = (unsigned short)cX;
+        tot[kModeDX * nblk + bj] = (unsigned short)cDX;
+        tot[kModeDiag * nblk + bj] = (unsigned short)cG;
+        stot[bj] = (unsigned short)cS;
+    }
+    __syncwarp();
+    for (int ri = 0; ri < nr; ++ri) {
+        const int rowi = srows[ri];
+        const RowInfo r = row_info(pl, rowi);
+        int run = 0, srun = 0;
+        for (int bj = lane; bj < nblk; bj += 32) {
+            int mode = pair_mode(pl, r, bj);
+            if (mode >= 0) {
+                mode = effective_mode(mode, tot[kModeD * nblk + bj], wantX ? tot[kModeX * nblk + bj] : 0);
+                run += (wantX || mode != kModeX) ? tot[mode * nblk + bj] : 0;
+                if (mode == kModeDiag) srun += stot[bj];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            run += __shfl_xor_sync(0xffffffffu, run, o);
+            srun += __shfl_xor_sync(0xffffffffu, srun, o);
+        }
+        if (lane == 0) {
+            const int wrow = pl.row_local[rowi - 1];
+            cntH[wrow] = run;
+            cntS[wrow] = srun;
+        }
+    }
+}
+
 __global__ void checksum_kernel(long long n, const long long* __restrict__ idx,
                                 const double* __restrict__ dat, unsigned long long* out)
 {
@@ -458,17 +526,23 @@ void block_count_scan(bs2e_block* b, bool read_totals)
     bs2e_ctx* c = b->ctx;
     cudaStream_t st = c->stream;
     const long long nrows = b->nrows;
-    block_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(
-        c->dg, b->dplan, nrows, b->d_cntH, b->d_cntS);
+    const char* cmode = getenv("BS2E_COUNT");
+    const size_t cbytes = count_smem_bytes(b->dplan.nblk);
+    if (b->nsites > 0 && cbytes <= 48 * 1024 && !(cmode && strcmp(cmode, "row") == 0)) {
+        const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
+        site_count_kernel<<<(unsigned)((b->nsites + kCountWarps - 1) / kCountWarps), kCountWarps * 32, cbytes, st>>>(
+            c->dg, b->dplan, sl, b->d_cntH, b->d_cntS);
+    } else {
+        block_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(
+            c->dg, b->dplan, nrows, b->d_cntH, b->d_cntS);
+    }
     BS2E_LAUNCHED();
     size_t tmp = b->scan_tmp_bytes;
-    BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntH, b->d_Hptr, nrows + 1, st));
+    // exclusive scan seeded with 1: the 1-based index_ptr of the reference (sparse_array_tools.f90:63-89)
+    BS2E_CUDA(cub::DeviceScan::ExclusiveScan(b->d_scan_tmp, tmp, b->d_cntH, b->d_Hptr, cub::Sum(), 1LL, nrows + 1, st));
     g_launches.fetch_add(2);  // DeviceScanInitKernel + DeviceScanKernel
-    BS2E_CUDA(cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, tmp, b->d_cntS, b->d_Sptr, nrows + 1, st));
+    BS2E_CUDA(cub::DeviceScan::ExclusiveScan(b->d_scan_tmp, tmp, b->d_cntS, b->d_Sptr, cub::Sum(), 1LL, nrows + 1, st));
     g_launches.fetch_add(2);
-    ptr_one_based_kernel<<<(unsigned)((nrows + 1 + 255) / 256), 256, 0, st>>>(nrows + 1, b->d_Hptr,
-                                                                             b->d_Sptr);
-    BS2E_LAUNCHED();
     if (read_totals) {
         long long lastH = 0, lastS = 0;
         BS2E_CUDA(cudaMemcpyAsync(&lastH, b->d_Hptr + nrows, sizeof(long long),
@@ -550,7 +624,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         b->d_Hptr = dev_alloc<long long>(nrows + 1);
         b->d_Sptr = dev_alloc<long long>(nrows + 1);
         size_t tmp = 0;
-        BS2E_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b->d_cntH, b->d_Hptr, nrows + 1, st));
+        BS2E_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp, b->d_cntH, b->d_Hptr, cub::Sum(), 1LL, nrows + 1, st));
         b->scan_tmp_bytes = tmp;
         BS2E_CUDA(cudaMalloc(&b->d_scan_tmp, tmp ? tmp : 1));
         block_count_scan(b, true);

@@ -293,6 +293,7 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
                 }
             }
             hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)hrun;
+            if (diag) sp[(size_t)bj * (ncmax + 1) + nnc] = (unsigned short)srun;   // site_count_kernel
         }
         const int* srows = hp_.site_rows.data() + hp_.site_ptr[sidx];
         const int nr = hp_.site_ptr[sidx + 1] - hp_.site_ptr[sidx];
@@ -307,18 +308,20 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
                 const long long wrow = pl.row_local[rowi - 1];
                 if (wrow < 0 || pl.rows[wrow] != rowi) throw std::logic_error("row map inconsistent");
                 rcache[ri] = RowC{H_ptr[wrow] - 1, S_ptr[wrow] - 1, r.bi, r.la, r.lb};
-                int run = 0;
+                int run = 0, srun = 0;
                 for (int bj = 0; bj < nblk; ++bj) {
                     int cnt = 0, mode = pair_mode(pl, r, bj);
                     if (mode >= 0) {
                         const unsigned short* hb = hp.data() + (bj * kModes) * (ncmax + 1) + nnc;
                         mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
                         cnt = (wantX || mode != kModeX) ? hb[mode * (ncmax + 1)] : 0;
+                        if (mode == kModeDiag) srun += sp[(size_t)bj * (ncmax + 1) + nnc];
                     }
                     pm[ri * nblk + bj] = cnt > 0 ? pm_pack(run, mode, (r.la + pl.blk[bj].l1) & 1) : 0u;
                     run += cnt;
                 }
-                if (run != H_ptr[wrow + 1] - H_ptr[wrow])
+                // the site-table count (site_count_kernel) must agree with the row-by-row count
+                if (run != H_ptr[wrow + 1] - H_ptr[wrow] || srun != S_ptr[wrow + 1] - S_ptr[wrow])
                     throw std::logic_error("site fill: row " + std::to_string(rowi) + " counted differently");
             }
             // phase 3b: the pairs of each column block, filed by storage mode
