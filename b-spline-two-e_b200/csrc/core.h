@@ -155,58 +155,79 @@ BS2E_HD double rk_element(const Geom& g, const CellData& cd, int k, int p1, int 
     return val;
 }
 
-// One thread of the stage-B kernel: two adjacent p2 columns of kRkRows p1 rows
-// of the plane of multipole k.  Disjoint cell ranges collapse to one product
-// of total moments; overlapping ranges take the general element.
+// The stage-B kernel works on tiles of kRkRows p1 rows x 2*kRkThreads p2 columns of
+// the plane of multipole k.  Disjoint cell ranges collapse to one product of total
+// moments (97 % of the tensor: a streaming write, phase 1); the elements whose cell
+// ranges overlap are collected per tile and computed by all threads of the tile
+// together in phase 2, so that no warp runs the general formula with a few lanes.
 constexpr int kRkRows = 16;      // p1 rows per CTA
 constexpr int kRkThreads = 128;  // each thread owns two adjacent p2 columns
 
-BS2E_HD void rk_build_thread(const Geom& g, const CellData& cd, double* R, int bx, int by, int k,
-                             int tx)
+struct RkRow { int lo, hi; double trk, trmk; };  // cell range and total moments of a pair
+
+BS2E_HD RkRow rk_row_data(const Geom& g, const CellData& cd, int k, int p)
+{
+    RkRow r;
+    r.lo = 1; r.hi = 0; r.trk = 0.0; r.trmk = 0.0;
+    if (p < g.P) {
+        const PairAC q = g.pair[p];
+        r.lo = pair_lo_cell(g, q.a, q.c);
+        r.hi = pair_hi_cell(g, q.a, q.c);
+        r.trk = cd.pre[((size_t)k * g.P + p) * (g.ks + 1) + g.ks];
+        r.trmk = cd.sufx[((size_t)k * g.P + p) * (g.ks + 1)];
+    }
+    return r;
+}
+
+// phase 1 of a tile, thread tx: rows[] holds rk_row_data of the tile's p1 rows.
+// general(code) is called for every element that needs the general formula,
+// code = row | local column << 4.
+template <class G>
+BS2E_HD void rk_stream_thread(const Geom& g, const CellData& cd, double* R, const RkRow* rows, int bx, int by,
+                              int k, int tx, G&& general)
 {
     const int p2 = (bx * kRkThreads + tx) * 2;
     if (p2 >= g.ldP) return;
-    const int ks = g.ks;
-    const size_t kP = (size_t)k * g.P;
-
-    int lo2[2], hi2[2];
-    double trk2[2], trmk2[2];
-    bool ok[2];
-    for (int e = 0; e < 2; ++e) {
-        ok[e] = (p2 + e) < g.P;
-        lo2[e] = hi2[e] = 0;
-        trk2[e] = trmk2[e] = 0.0;
-        if (ok[e]) {
-            const PairAC q = g.pair[p2 + e];
-            lo2[e] = pair_lo_cell(g, q.a, q.c);
-            hi2[e] = pair_hi_cell(g, q.a, q.c);
-            trk2[e] = cd.pre[(kP + p2 + e) * (ks + 1) + ks];
-            trmk2[e] = cd.sufx[(kP + p2 + e) * (ks + 1)];
-        }
-    }
+    const RkRow c0 = rk_row_data(g, cd, k, p2), c1 = rk_row_data(g, cd, k, p2 + 1);
+    const bool ok0 = p2 < g.P, ok1 = p2 + 1 < g.P;
     const int r0 = by * kRkRows;
-    for (int row = 0; row < kRkRows; ++row) {
-        const int p1 = r0 + row;
-        if (p1 >= g.P) break;
-        const PairAC q1 = g.pair[p1];
-        const int lo1 = pair_lo_cell(g, q1.a, q1.c), hi1 = pair_hi_cell(g, q1.a, q1.c);
-        const double trk1 = cd.pre[(kP + p1) * (ks + 1) + ks];
-        const double trmk1 = cd.sufx[(kP + p1) * (ks + 1)];
-        double out[2];
-        for (int e = 0; e < 2; ++e) {
-            if (!ok[e]) out[e] = 0.0;
-            else if (hi1 < lo2[e]) out[e] = trk1 * trmk2[e];   // electron 1 strictly inside
-            else if (hi2[e] < lo1) out[e] = trmk1 * trk2[e];   // electron 2 strictly inside
-            else out[e] = rk_element(g, cd, k, p1, p2 + e);
+    double* dst = R + ((size_t)k * g.P + r0) * g.ldP + p2;
+    for (int row = 0; row < kRkRows; ++row, dst += g.ldP) {
+        if (r0 + row >= g.P) break;
+        const RkRow a = rows[row];
+        double o0 = 0.0, o1 = 0.0;
+        bool g0 = false, g1 = false;
+        if (ok0) {
+            if (a.hi < c0.lo) o0 = a.trk * c0.trmk;        // electron 1 strictly inside
+            else if (c0.hi < a.lo) o0 = a.trmk * c0.trk;   // electron 2 strictly inside
+            else g0 = true;
         }
-        double* dst = R + (kP + p1) * g.ldP + p2;
+        if (ok1) {
+            if (a.hi < c1.lo) o1 = a.trk * c1.trmk;
+            else if (c1.hi < a.lo) o1 = a.trmk * c1.trk;
+            else g1 = true;
+        }
+        if (g0) general(row | ((tx * 2) << 4));
+        if (g1) general(row | ((tx * 2 + 1) << 4));
 #if defined(__CUDA_ARCH__)
-        *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[1]);
+        if (!g0 && !g1) *reinterpret_cast<double2*>(dst) = make_double2(o0, o1);
+        else {
+            if (!g0) dst[0] = o0;
+            if (!g1) dst[1] = o1;
+        }
 #else
-        dst[0] = out[0];
-        dst[1] = out[1];
+        if (!g0) dst[0] = o0;
+        if (!g1) dst[1] = o1;
 #endif
     }
+}
+
+// phase 2 of a tile: one collected element
+BS2E_HD void rk_general_item(const Geom& g, const CellData& cd, double* R, int bx, int by, int k, int code)
+{
+    const int p1 = by * kRkRows + (code & 15);
+    const int p2 = bx * kRkThreads * 2 + (code >> 4);
+    R[((size_t)k * g.P + p1) * g.ldP + p2] = rk_element(g, cd, k, p1, p2);
 }
 
 // ---------------------------------------------------------------------------

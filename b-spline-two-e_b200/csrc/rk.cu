@@ -18,7 +18,18 @@ namespace bs2e {
 __global__ void __launch_bounds__(kRkThreads)
 rk_build_kernel(Geom g, CellData cd, double* __restrict__ R)
 {
-    rk_build_thread(g, cd, R, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+    __shared__ RkRow rows[kRkRows];
+    __shared__ unsigned short list[kRkRows * kRkThreads * 2];
+    __shared__ int count;
+    const int bx = blockIdx.x, by = blockIdx.y, k = blockIdx.z, tx = threadIdx.x;
+    if (tx < kRkRows) rows[tx] = rk_row_data(g, cd, k, by * kRkRows + tx);
+    if (tx == 0) count = 0;
+    __syncthreads();
+    rk_stream_thread(g, cd, R, rows, bx, by, k, tx,
+                     [&](int code) { list[atomicAdd(&count, 1)] = (unsigned short)code; });
+    __syncthreads();
+    const int n = count;
+    for (int i = tx; i < n; i += kRkThreads) rk_general_item(g, cd, R, bx, by, k, list[i]);
 }
 
 void run_rk_build(bs2e_ctx* c)

@@ -101,9 +101,15 @@ void hc_rk_build(HcCtx* c)
     const int gx = (g.ldP / 2 + kRkThreads - 1) / kRkThreads, gy = (g.P + kRkRows - 1) / kRkRows;
     for (int k = 0; k < g.K1; ++k)
         for (int by = 0; by < gy; ++by)
-            for (int bx = 0; bx < gx; ++bx)
+            for (int bx = 0; bx < gx; ++bx) {
+                RkRow rows[kRkRows];
+                std::vector<int> list;
+                for (int tx = 0; tx < kRkRows; ++tx) rows[tx] = rk_row_data(g, cd, k, by * kRkRows + tx);
                 for (int tx = 0; tx < kRkThreads; ++tx)
-                    rk_build_thread(g, cd, c->R.data(), bx, by, k, tx);
+                    rk_stream_thread(g, cd, c->R.data(), rows, bx, by, k, tx, [&](int code) { list.push_back(code); });
+                if (list.size() > (size_t)kRkRows * kRkThreads * 2) throw std::logic_error("tile list overflow");
+                for (int code : list) rk_general_item(g, cd, c->R.data(), bx, by, k, code);
+            }
 }
 
 void hc_get_R(HcCtx* c, double* R) { memcpy(R, c->R.data(), sizeof(double) * c->R.size()); }
