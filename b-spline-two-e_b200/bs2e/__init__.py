@@ -54,6 +54,7 @@ ABI = {
     "bs2e_block_row_counts": (C.c_int, [vp, vp, vp]),
     "bs2e_block_recount": (C.c_int, [vp]),
     "bs2e_block_assemble": (C.c_int, [vp]),
+    "bs2e_blocks_run": (C.c_int, [vp, i64, C.POINTER(vp), i64]),
     "bs2e_block_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "bs2e_block_checksum": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "bs2e_block_free": (C.c_int, [vp]),
@@ -374,6 +375,11 @@ class Context:
     def construct_block_tensor(self, sym, full):
         nnz = self.block_count(sym, full)
         return self.block_fill(sym, full, nnz)
+
+    def blocks_run(self, blocks, recount=True):
+        """count pass + fill of several planned blocks, pipelined over internal streams"""
+        arr = (vp * len(blocks))(*[b.h for b in blocks])
+        _chk(lib().bs2e_blocks_run(self.h, len(blocks), arr, int(bool(recount))))
 
     def block_plan(self, sym, full, rows=None, ranges=None) -> Block:
         """rows=(lo,hi): one row range; ranges=[(lo,hi),...]: a union of ascending row ranges

@@ -115,6 +115,14 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         cudaFree(c->d_mom_rk); cudaFree(c->d_mom_rmk); cudaFree(c->d_pre); cudaFree(c->d_sufx);
         cudaFree(c->d_rd); cudaFree(c->d_R); cudaFree(c->d_Hb); cudaFree(c->d_Sb);
         if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+        if (c->have_lanes) {
+            for (auto& ln : c->lanes) {
+                cudaStreamSynchronize(ln.main); cudaStreamSynchronize(ln.side);
+                cudaStreamDestroy(ln.main); cudaStreamDestroy(ln.side);
+                cudaEventDestroy(ln.fork); cudaEventDestroy(ln.join); cudaEventDestroy(ln.done);
+            }
+            cudaEventDestroy(c->ev_start);
+        }
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         if (c->ev_join) cudaEventDestroy(c->ev_join);
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -294,6 +302,15 @@ int bs2e_block_assemble(bs2e_block* b)
         if (!b) throw Error("null block");
         use_device(b->ctx);
         block_assemble(b);
+    });
+}
+
+int bs2e_blocks_run(bs2e_ctx* c, int64_t n, bs2e_block** blks, int64_t recount)
+{
+    return guarded("bs2e_blocks_run", [&] {
+        if (!c || (n > 0 && !blks)) throw Error("null argument");
+        use_device(c);
+        blocks_run(c, n, blks, recount != 0);
     });
 }
 

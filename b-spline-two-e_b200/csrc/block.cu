@@ -521,10 +521,12 @@ __global__ void checksum_kernel(long long n, const long long* __restrict__ idx,
 }
 
 // count pass + exclusive scan -> 1-based index_ptr of the planned rows
-void block_count_scan(bs2e_block* b, bool read_totals)
+BlockStreams default_streams(bs2e_ctx* c) { return BlockStreams{c->stream, c->side, c->ev_fork, c->ev_join}; }
+
+void block_count_scan(bs2e_block* b, bool read_totals, const BlockStreams* bsp)
 {
     bs2e_ctx* c = b->ctx;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = bsp ? bsp->main : c->stream;
     const long long nrows = b->nrows;
     const char* cmode = getenv("BS2E_COUNT");
     const size_t cbytes = count_smem_bytes(b->dplan.nblk);
@@ -635,9 +637,10 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     return b;
 }
 
-void block_assemble(bs2e_block* b)
+void block_assemble(bs2e_block* b, const BlockStreams* bsp)
 {
     bs2e_ctx* c = b->ctx;
+    const BlockStreams bs = bsp ? *bsp : default_streams(c);
     if (!c->have_R) throw Error("block_assemble: call bs2e_rk_build first");
     if (!c->have_1p) throw Error("block_assemble: call bs2e_set_one_particle first");
     if (b->lmax > c->lmax_1p) throw Error("block_assemble: configuration l exceeds max_l_1p of H_vec");
@@ -672,12 +675,12 @@ void block_assemble(bs2e_block* b)
         // the SMs the other launch leaves idle in its last wave
         const bool fork = b->nsites_x > 0 && b->nsites_x < b->nsites;
         if (fork) {
-            BS2E_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-            BS2E_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            BS2E_CUDA(cudaEventRecord(bs.fork, bs.main));
+            BS2E_CUDA(cudaStreamWaitEvent(bs.side, bs.fork, 0));
         }
         auto launch = [&](auto kern, int nt, bool wx, int first, int count) {
             if (count <= 0) return;
-            cudaStream_t st = (fork && !wx) ? c->side : c->stream;
+            cudaStream_t st = (fork && !wx) ? bs.side : bs.main;
             const size_t bytes = site_smem_bytes(g, nblk, lay.G, site_nkp(kmax), lay.cfsm != 0, lay.nl, wx);
             BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             kern<<<(unsigned)count, nt, bytes, st>>>(
@@ -703,18 +706,52 @@ void block_assemble(bs2e_block* b)
         }
 #undef BS2E_SITE
         if (fork) {
-            BS2E_CUDA(cudaEventRecord(c->ev_join, c->side));
-            BS2E_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            BS2E_CUDA(cudaEventRecord(bs.join, bs.side));
+            BS2E_CUDA(cudaStreamWaitEvent(bs.main, bs.join, 0));
         }
     } else {
         block_fill_kernel<<<(unsigned)((nrows + kFillWarps - 1) / kFillWarps), kFillWarps * 32, 0,
-                            c->stream>>>(c->dg, b->dplan, c->one_body(), c->d_R, nrows,
+                            bs.main>>>(c->dg, b->dplan, c->one_body(), c->d_R, nrows,
                                          b->d_Hptr, b->d_Sptr, b->d_Hidx,
                                          reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx,
                                          reinterpret_cast<double2*>(b->d_Sdat));
         BS2E_LAUNCHED();
     }
     b->assembled = true;
+}
+
+// count pass (optional) + fill of several blocks of one context, consecutive blocks on
+// different stream pairs; everything is ordered after the work already queued on the
+// context's stream and the context's stream waits for all of it.
+void blocks_run(bs2e_ctx* c, long long n, bs2e_block** blks, bool recount)
+{
+    if (n <= 0) return;
+    if (!c->have_lanes) {
+        for (auto& ln : c->lanes) {
+            BS2E_CUDA(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+            BS2E_CUDA(cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking));
+            BS2E_CUDA(cudaEventCreateWithFlags(&ln.fork, cudaEventDisableTiming));
+            BS2E_CUDA(cudaEventCreateWithFlags(&ln.join, cudaEventDisableTiming));
+            BS2E_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        }
+        BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+        c->have_lanes = true;
+    }
+    for (long long i = 0; i < n; ++i)
+        if (!blks[i] || blks[i]->ctx != c) throw Error("bs2e_blocks_run: block of another context");
+    BS2E_CUDA(cudaEventRecord(c->ev_start, c->stream));
+    const int nl = (int)std::min<long long>(n, bs2e_ctx::kLanes);
+    for (int l = 0; l < nl; ++l) BS2E_CUDA(cudaStreamWaitEvent(c->lanes[l].main, c->ev_start, 0));
+    for (long long i = 0; i < n; ++i) {
+        bs2e_ctx::Lane& ln = c->lanes[i % nl];
+        const BlockStreams bs{ln.main, ln.side, ln.fork, ln.join};
+        if (recount) block_count_scan(blks[i], false, &bs);
+        block_assemble(blks[i], &bs);
+    }
+    for (int l = 0; l < nl; ++l) {
+        BS2E_CUDA(cudaEventRecord(c->lanes[l].done, c->lanes[l].main));
+        BS2E_CUDA(cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
+    }
 }
 
 void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat, int64_t* S_ptr,

@@ -57,6 +57,14 @@ struct bs2e_ctx {
     // side stream + events: the two site-kernel launches of a block run concurrently
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // extra lanes for bs2e_blocks_run: consecutive blocks are issued on different
+    // (main, side) stream pairs so that count passes and the last waves of the fill
+    // launches of one block overlap the work of the next
+    struct Lane { cudaStream_t main = nullptr, side = nullptr; cudaEvent_t fork = nullptr, join = nullptr, done = nullptr; };
+    static constexpr int kLanes = 3;
+    Lane lanes[kLanes];
+    cudaEvent_t ev_start = nullptr;
+    bool have_lanes = false;
     int max_k = 0;
 
     // host copy of the basis geometry
@@ -133,8 +141,12 @@ void fetch_rk_plane(bs2e_ctx* c, int k, double* out);
 bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
                        const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
                        const int64_t* range_hi);
-void block_count_scan(bs2e_block* b, bool read_totals);
-void block_assemble(bs2e_block* b);
+// the streams a block's work is issued on (default: the context's own pair)
+struct BlockStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
+BlockStreams default_streams(bs2e_ctx* c);
+void block_count_scan(bs2e_block* b, bool read_totals, const BlockStreams* bs = nullptr);
+void block_assemble(bs2e_block* b, const BlockStreams* bs = nullptr);
+void blocks_run(bs2e_ctx* c, long long n, bs2e_block** blks, bool recount);
 void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat, int64_t* S_ptr,
                     int64_t* S_idx, double* S_dat);
 void block_row_counts(bs2e_block* b, int64_t* cH, int64_t* cS);

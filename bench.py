@@ -205,16 +205,20 @@ def run_ours(args):
             ea = ev(); ea.record(stream)
             ctx.rk_build()
             e1 = ev(); e1.record(stream)
-            fills = []
-            for b in blocks:
-                b.recount()                                 # count pass + scan (index_ptr)
-                f0 = ev(); f0.record(stream)
-                b.assemble()                                # block_fill_kernel
-                f1 = ev(); f1.record(stream)
-                fills.append((f0, f1))
+            ctx.blocks_run(blocks, recount=True)            # count pass + scan + fill of every block
             e2 = ev(); e2.record(stream)
         if rec is not None:
-            rec.append((e0, ea, e1, e2, fills))
+            rec.append((e0, ea, e1, e2))
+
+    def fill_only_step(rec):
+        """the fill of each block timed on its own (roofline of the dominant kernel)"""
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            for b in blocks:
+                f0 = ev(); f0.record(stream)
+                b.assemble()                                # the two concurrent site_fill_kernel launches
+                f1 = ev(); f1.record(stream)
+                rec.append((f0, f1))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -235,10 +239,17 @@ def run_ours(args):
     launches = bs2e.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    tA = sum(e0.elapsed_time(ea) for e0, ea, e1, e2, f in rec)
-    tB = sum(ea.elapsed_time(e1) for e0, ea, e1, e2, f in rec)
-    tC = sum(e1.elapsed_time(e2) for e0, ea, e1, e2, f in rec)
-    fill_ms = [[f0.elapsed_time(f1) for f0, f1 in f] for *_, f in rec]
+    # separate pass: every block's fill alone on the stream (per-launch duration for the roofline)
+    frec = []
+    n_fill_steps = max(1, min(args.steps, 5))
+    for _ in range(n_fill_steps):
+        fill_only_step(frec)
+    barrier()
+
+    tA = sum(e0.elapsed_time(ea) for e0, ea, e1, e2 in rec)
+    tB = sum(ea.elapsed_time(e1) for e0, ea, e1, e2 in rec)
+    tC = sum(e1.elapsed_time(e2) for e0, ea, e1, e2 in rec)
+    fill_ms = [f0.elapsed_time(f1) for f0, f1 in frec]
     tA, tB, tC = max_over_ranks(tA), max_over_ranks(tB), max_over_ranks(tC)
     wall = max_over_ranks(wall)
     K = args.steps
@@ -246,8 +257,8 @@ def run_ours(args):
     rk_per_s = n_rk * K / ((tA + tB) * 1e-3)
 
     # ---- roofline of the dominant kernel (site_fill_kernel), this rank ----
-    fill_total_ms = sum(sum(x) for x in fill_ms)
-    n_fill = K * len(blocks)
+    fill_total_ms = sum(fill_ms)
+    n_fill = n_fill_steps * len(blocks)
     alg_bytes_per_launch = 24.0 * my_elems / len(blocks)       # 16 B data + 8 B index per element
     avg_fill_ms = fill_total_ms / n_fill
     peak, peak_src = measured_peak_hbm()
@@ -255,7 +266,11 @@ def run_ours(args):
     roofline = {"kernel": "site_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "avg_launch_ms": avg_fill_ms, "share_of_stage_C": fill_total_ms / max(tC, 1e-9),
+                "avg_launch_ms": avg_fill_ms,
+                "timed": f"{n_fill_steps} extra passes after the timed steps, each block's fill alone on the stream "
+                         "(a launch = the two concurrent site_fill_kernel launches of one symmetry block); in the timed "
+                         "steps the blocks are pipelined over three stream pairs (bs2e_blocks_run)",
+                "share_of_stage_C": (fill_total_ms / n_fill_steps) / max(tC / K, 1e-9),
                 "rk_build": {"achieved": 8.0 * n_rk * K / (tB * 1e-3) / 1e9, "unit": "GB/s",
                              "frac": 8.0 * n_rk * K / (tB * 1e-3) / 1e9 / peak, "bound": "hbm"}}
 

@@ -128,6 +128,13 @@ int bs2e_block_row_counts(bs2e_block *blk, int64_t *cnt_H, int64_t *cnt_S);
  * benchmarking of the count stage. */
 int bs2e_block_recount(bs2e_block *blk);
 int bs2e_block_assemble(bs2e_block *blk);
+/* Count pass (when recount != 0) and bs2e_block_assemble of n planned blocks of
+ * one context in one call.  Consecutive blocks are issued on different internal
+ * streams, so the count pass and the last wave of one block's fill overlap the
+ * next block; the work is ordered after what is queued on the context's stream,
+ * which in turn waits for all of it.  Stands in for the loop over symmetries of
+ * src/apps/main_basis_setup.f90:105-116 when the CSR fragments stay on the device. */
+int bs2e_blocks_run(bs2e_ctx *ctx, int64_t n, bs2e_block **blks, int64_t recount);
 int bs2e_block_download(bs2e_block *blk, int64_t *H_ptr, int64_t *H_idx, double *H_dat,
                         int64_t *S_ptr, int64_t *S_idx, double *S_dat);
 /* 64-bit checksums of the device-resident fragment (indices and raw data

@@ -330,3 +330,24 @@ def test_site_partition_fragments_merge_to_whole_block():
     with pytest.raises(bs2e.Bs2eError):       # ranges must ascend
         ctx.block_plan(run.syms[0], False, ranges=[(5, 6), (1, 2)])
     ctx.close()
+
+
+def test_blocks_run_pipelined_equals_block_by_block(case):
+    """bs2e_blocks_run (count + fill of all blocks over internal streams) == one block at a time"""
+    run, ctx = case
+    syms = [s for s in run.syms if s.n_config > 0]
+    seq = []
+    for s in syms:
+        b = ctx.block_plan(s, False); b.assemble()
+        seq.append(b.download()); b.free()
+    blocks = [ctx.block_plan(s, False) for s in syms]
+    for rep in range(2):                      # second pass: outputs already allocated, recount on the device
+        ctx.blocks_run(blocks, recount=True)
+        ctx.sync()
+        for b, (H0, S0) in zip(blocks, seq):
+            H, S = b.download()
+            for M, M0 in ((H, H0), (S, S0)):
+                assert np.array_equal(M.index_ptr, M0.index_ptr) and np.array_equal(M.indices, M0.indices)
+                assert np.array_equal(M.data, M0.data)
+    for b in blocks:
+        b.free()
