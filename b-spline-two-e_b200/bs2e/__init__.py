@@ -60,6 +60,17 @@ ABI = {
     "bs2e_block_free": (C.c_int, [vp]),
     "bs2e_host_alloc": (C.c_int, [i64, C.POINTER(vp)]),
     "bs2e_host_free": (C.c_int, [vp]),
+    "bs2e_file_create_block_diag": (C.c_int, [C.c_char_p, i64, _pi, C.POINTER(vp)]),
+    "bs2e_file_write_block": (C.c_int, [vp, i64, i64, i64, vp, vp, vp]),
+    "bs2e_file_write_block_fragments": (C.c_int, [vp, i64, i64, i64, _pi, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "bs2e_file_close": (C.c_int, [vp]),
+    "bs2e_file_write_basis": (C.c_int, [C.c_char_p, i64, i64, i64, i64, _pi, _pi, _pi, _pi,
+                                        C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "bs2e_file_write_splines": (C.c_int, [C.c_char_p, i64, i64, _pd]),
+    "bs2e_file_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "bs2e_file_next_record": (C.c_int, [vp, C.POINTER(i64)]),
+    "bs2e_file_record_data": (C.c_int, [vp, vp, i64]),
+    "bs2e_file_set_max_subrecord": (C.c_int, [i64]),
     "bs2e_launch_count": (i64, []),
     "bs2e_host_generate_grid": (i64, [i64, i64, i64, f64, f64, vp, i64]),
     "bs2e_host_gauss_legendre": (C.c_int, [i64, f64, f64, _pd, _pd]),

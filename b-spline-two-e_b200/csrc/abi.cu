@@ -12,6 +12,7 @@
 
 #include "../../include/bs2e.h"
 #include "ctx.h"
+#include "files.h"
 #include "geom_host.h"
 #include "host.h"
 #include "wigner.h"
@@ -485,6 +486,109 @@ int bs2e_host_free(void* ptr)
 }
 
 int64_t bs2e_launch_count(void) { return g_launches.load(); }
+
+// ---- result files (host only) ----------------------------------------------
+struct bs2e_file {
+    std::unique_ptr<files::Writer> w;
+    std::unique_ptr<files::Reader> r;
+    std::vector<char> rec;
+};
+
+int bs2e_file_create_block_diag(const char* path, int64_t n_blocks, const int64_t* block_rows, bs2e_file** f)
+{
+    return guarded("bs2e_file_create_block_diag", [&] {
+        if (!path || !f || n_blocks < 0 || (n_blocks > 0 && !block_rows)) throw Error("bad argument");
+        std::unique_ptr<bs2e_file> h(new bs2e_file());
+        h->w.reset(new files::Writer(path));
+        h->w->block_diag_header(n_blocks, block_rows);
+        *f = h.release();
+    });
+}
+
+int bs2e_file_write_block(bs2e_file* f, int64_t rows, int64_t cols, int64_t nnz, const int64_t* index_ptr,
+                          const int64_t* indices, const double* data)
+{
+    return guarded("bs2e_file_write_block", [&] {
+        if (!f || !f->w) throw Error("file not open for writing");
+        if (nnz > 0 && (!index_ptr || !indices || !data)) throw Error("null array");
+        f->w->csr_block(rows, cols, nnz, index_ptr, indices, data);
+    });
+}
+
+int bs2e_file_write_block_fragments(bs2e_file* f, int64_t rows, int64_t cols, int64_t n_frag,
+                                    const int64_t* frag_rows, const int64_t* const* frag_ptr,
+                                    const int64_t* const* frag_idx, const double* const* frag_dat)
+{
+    return guarded("bs2e_file_write_block_fragments", [&] {
+        if (!f || !f->w) throw Error("file not open for writing");
+        if (n_frag < 1 || !frag_rows || !frag_ptr || !frag_idx || !frag_dat) throw Error("bad argument");
+        std::vector<long long> fr(frag_rows, frag_rows + n_frag);
+        f->w->csr_block_fragments(rows, cols, (int)n_frag, fr.data(), frag_ptr, frag_idx, frag_dat);
+    });
+}
+
+int bs2e_file_close(bs2e_file* f)
+{
+    return guarded("bs2e_file_close", [&] {
+        if (!f) return;
+        std::unique_ptr<bs2e_file> h(f);
+        if (h->w) h->w->close();
+    });
+}
+
+int bs2e_file_write_basis(const char* path, int64_t max_l_1p, int64_t max_L, int64_t two_el, int64_t n_sym,
+                          const int64_t* sym_l, const int64_t* sym_m, const int64_t* sym_pi,
+                          const int64_t* n_config, const int64_t* const* conf_n, const int64_t* const* conf_l,
+                          const int64_t* const* conf_eqv)
+{
+    return guarded("bs2e_file_write_basis", [&] {
+        if (!path || n_sym < 0) throw Error("bad argument");
+        files::write_basis(path, max_l_1p, max_L, two_el != 0, n_sym, sym_l, sym_m, sym_pi, n_config, conf_n,
+                           conf_l, conf_eqv);
+    });
+}
+
+int bs2e_file_write_splines(const char* path, int64_t k, int64_t n_knots, const double* knots)
+{
+    return guarded("bs2e_file_write_splines", [&] {
+        if (!path || !knots) throw Error("bad argument");
+        files::write_splines(path, k, n_knots, knots);
+    });
+}
+
+int bs2e_file_open(const char* path, bs2e_file** f)
+{
+    return guarded("bs2e_file_open", [&] {
+        if (!path || !f) throw Error("bad argument");
+        std::unique_ptr<bs2e_file> h(new bs2e_file());
+        h->r.reset(new files::Reader(path));
+        *f = h.release();
+    });
+}
+
+int bs2e_file_next_record(bs2e_file* f, int64_t* nbytes)
+{
+    return guarded("bs2e_file_next_record", [&] {
+        if (!f || !f->r || !nbytes) throw Error("file not open for reading");
+        f->r->next_record(f->rec);
+        *nbytes = (int64_t)f->rec.size();
+    });
+}
+
+int bs2e_file_record_data(bs2e_file* f, void* dst, int64_t nbytes)
+{
+    return guarded("bs2e_file_record_data", [&] {
+        if (!f || !f->r || (nbytes > 0 && !dst)) throw Error("bad argument");
+        if ((size_t)nbytes != f->rec.size()) throw Error("size does not match the current record");
+        if (nbytes) std::memcpy(dst, f->rec.data(), (size_t)nbytes);
+    });
+}
+
+int bs2e_file_set_max_subrecord(int64_t bytes)
+{
+    files::set_max_subrecord(bytes);
+    return 0;
+}
 
 // ---- host companions -------------------------------------------------------
 int64_t bs2e_host_generate_grid(int64_t k, int64_t m, int64_t Z, double h_max, double r_max,

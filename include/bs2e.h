@@ -147,6 +147,43 @@ int bs2e_block_free(bs2e_block *blk);
 int bs2e_host_alloc(int64_t bytes, void **ptr);
 int bs2e_host_free(void *ptr);
 
+/* ---- result files of basis_setup, written natively (no Fortran runtime):
+ *      gfortran unformatted sequential records, 8-byte default integers.  Lets a
+ *      driver hand the GPU-built matrices to the reference's consumers (diag,
+ *      quasi, time_prop read them with CS_block_diag_load, load_basis,
+ *      load_bsplines) and stream a block that does not fit host staging.
+ * H_diag.dat / S_diag.dat: block_diag_CS%store (src/tools/block_tools.f90:458-485);
+ * basis.dat: basis%store (src/tools/orbital_tools.f90:364-387);
+ * splines.dat: b_spline%store (src/tools/bspline_tools.f90:375-386).            */
+typedef struct bs2e_file bs2e_file;
+int bs2e_file_create_block_diag(const char *path, int64_t n_blocks,
+                                const int64_t *block_rows, bs2e_file **f);
+int bs2e_file_write_block(bs2e_file *f, int64_t rows, int64_t cols, int64_t nnz,
+                          const int64_t *index_ptr, const int64_t *indices,
+                          const double *data);
+/* the same block given as CSR fragments of consecutive row ranges (each with an
+ * index_ptr starting at 1, as bs2e_block_download returns them)              */
+int bs2e_file_write_block_fragments(bs2e_file *f, int64_t rows, int64_t cols,
+                                    int64_t n_frag, const int64_t *frag_rows,
+                                    const int64_t *const *frag_ptr,
+                                    const int64_t *const *frag_idx,
+                                    const double *const *frag_dat);
+int bs2e_file_close(bs2e_file *f);
+/* conf_n[q], conf_l[q]: (2, n_config[q]); conf_eqv[q]: (n_config[q]) */
+int bs2e_file_write_basis(const char *path, int64_t max_l_1p, int64_t max_L,
+                          int64_t two_el, int64_t n_sym, const int64_t *sym_l,
+                          const int64_t *sym_m, const int64_t *sym_pi,
+                          const int64_t *n_config, const int64_t *const *conf_n,
+                          const int64_t *const *conf_l, const int64_t *const *conf_eqv);
+int bs2e_file_write_splines(const char *path, int64_t k, int64_t n_knots,
+                            const double *knots);
+/* record-level reader of the same files (CS_block_diag_load, block_tools.f90:487-524) */
+int bs2e_file_open(const char *path, bs2e_file **f);
+int bs2e_file_next_record(bs2e_file *f, int64_t *nbytes);
+int bs2e_file_record_data(bs2e_file *f, void *dst, int64_t nbytes);
+/* test hook: split records into subrecords of at most this many bytes (0: default 2^31-9) */
+int bs2e_file_set_max_subrecord(int64_t bytes);
+
 /* Number of kernels this library has launched since load (all contexts). */
 int64_t bs2e_launch_count(void);
 

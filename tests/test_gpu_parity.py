@@ -351,3 +351,48 @@ def test_blocks_run_pipelined_equals_block_by_block(case):
                 assert np.array_equal(M.data, M0.data)
     for b in blocks:
         b.free()
+
+
+def test_downstream_shift_invert_He_singlet_S():
+    """what the `diag` consumer does with the files of basis_setup
+    (src/diagonalization/diagonalization.f90:86-117: shift-invert ARPACK on (H - sigma S)) on
+    matrices the GPU path built end to end from the product's own host inputs: the He 1^1S and
+    2^1S energies at l_max = 2 on the reference's test grid (tests/test_mat_els.f90:70-77)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    setup = bs2e.BasisSetup(k=8, m=3, Z=2, h_max=1.5, r_max=15.0, k_GL=14, max_k=4, max_L=0, max_l_1p=2,
+                            max_l2=2, CAP_eta=0j, CAP_r_0=45.0, full=False, z_pol=True)
+    H_diag, S_diag = setup.run()
+    H, S = H_diag[0], S_diag[0]
+    n = H.shape[0]
+    assert n == 3106 and H.nnz == 784861 and S.nnz == 263282          # SURVEY.md section 8c
+    up = lambda M: sp.csr_matrix((M.data.real, M.indices - 1, M.index_ptr - 1), shape=(n, n))
+    full = lambda U: U + U.T - sp.diags(U.diagonal())
+    Hf, Sf = full(up(H)), full(up(S))
+    assert abs(H.data.imag).max() == 0.0                               # no CAP: real symmetric problem
+    ev = sla.eigsh(Hf.tocsc(), k=2, M=Sf.tocsc(), sigma=-3.0, which="LM", return_eigenvectors=False)
+    ev = np.sort(ev)
+    assert abs(ev[0] + 2.90276684) < 2e-8 and abs(ev[1] + 2.14584449) < 2e-8
+    setup.ctx.close()
+
+
+def test_driver_writes_result_files_streamed_and_whole(tmp_path):
+    """bs2e.driver: the basis_setup call order on the GPU with H_diag.dat / S_diag.dat /
+    basis.dat / splines.dat as output; streaming a block in row-range fragments must give
+    byte-identical files, and the files must hold the oracle's matrices"""
+    from bs2e import driver, files as F
+    p = SMALL_CASES["trunc_k5"]
+    a, b = tmp_path / "whole", tmp_path / "streamed"
+    st_a = driver.run_basis_setup(str(a), **p)
+    st_b = driver.run_basis_setup(str(b), max_fragment_bytes=20000, **p)
+    assert all(q[4] == 1 for q in st_a) and any(q[4] > 1 for q in st_b)
+    for name in ("H_diag.dat", "S_diag.dat", "basis.dat", "splines.dat"):
+        assert (a / name).read_bytes() == (b / name).read_bytes()
+    run = _oracle(p)
+    _, shape, Hb = F.read_block_diag(a / "H_diag.dat")
+    _, _, Sb = F.read_block_diag(a / "S_diag.dat")
+    assert shape[0] == sum(s.n_config for s in run.syms)
+    for s, Hg, Sg in zip(run.syms, Hb, Sb):
+        H, S, _ = run.block(s)
+        assert_csr_equal(Hg, H, scale_tol=5e-12, what=f"file H L={s.l}")
+        assert_csr_equal(Sg, S, scale_tol=5e-12, what=f"file S L={s.l}")
