@@ -2,6 +2,7 @@
 #include <sched.h>
 
 #include <cctype>
+#include <chrono>
 #include <complex>
 #include <cstdio>
 #include <cstring>
@@ -84,6 +85,12 @@ int bs2e_ctx_create(int64_t k_spline, int64_t n_knots, const double* knots, int6
         if (prop.major < 10) throw Error("this library is built for sm_100a (B200) only");
         BS2E_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
+        {   // keep freed output arrays in the device's default memory pool (see dev_alloc_async)
+            cudaMemPool_t pool = nullptr;
+            BS2E_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
+            unsigned long long keep = ~0ull;
+            BS2E_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         BS2E_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
         BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -127,6 +134,10 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         if (c->ev_join) cudaEventDestroy(c->ev_join);
         if (c->own_stream) cudaStreamDestroy(c->stream);
+        {   // hand the cached output pages back
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        }
         delete c;
     });
 }
@@ -376,7 +387,12 @@ int bs2e_block_count(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* co
         if (!c || !conf_n || !conf_l) throw Error("null argument");
         use_device(c);
         const int64_t one = 1;
+        const bool trace = getenv("BS2E_TRACE") != nullptr;
+        const auto tc0 = std::chrono::steady_clock::now();
         bs2e_block* b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &one, &n_config);
+        if (trace)
+            fprintf(stderr, "bs2e_block_count L=%lld: %.2f ms\n", (long long)L,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
         if (nnz_H) *nnz_H = b->nnzH;
         if (nnz_S) *nnz_S = b->nnzS;
         const ParkKey key{c, L, n_config, full != 0, conf_hash(n_config, conf_n, conf_l)};
@@ -406,15 +422,25 @@ int bs2e_block_fill(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
             if (it != g_parked.end()) { b = it->second; g_parked.erase(it); }
         }
         const int64_t one = 1;
+        const bool trace = getenv("BS2E_TRACE") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
         if (!b) b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &one, &n_config);
+        double t1 = 0, t2 = 0, t3 = 0;
         try {
+            t1 = now();
             block_assemble(b);
+            if (trace) { cudaStreamSynchronize(c->stream); t2 = now(); }
             block_download(b, H_ptr, H_idx, H_dat, S_ptr, S_idx, S_dat);
+            t3 = now();
         } catch (...) {
             block_free(b);
             throw;
         }
         block_free(b);
+        if (trace)
+            fprintf(stderr, "bs2e_block_fill L=%lld: plan %.2f ms, alloc+fill %.2f ms, download %.2f ms, free %.2f ms\n",
+                    (long long)L, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     });
 }
 

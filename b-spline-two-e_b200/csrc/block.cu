@@ -645,10 +645,10 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
     if (!c->have_1p) throw Error("block_assemble: call bs2e_set_one_particle first");
     if (b->lmax > c->lmax_1p) throw Error("block_assemble: configuration l exceeds max_l_1p of H_vec");
     if (!b->d_Hidx) {
-        b->d_Hidx = dev_alloc<long long>(b->nnzH);
-        b->d_Hdat = dev_alloc<double>(2 * (size_t)b->nnzH);
-        b->d_Sidx = dev_alloc<long long>(b->nnzS);
-        b->d_Sdat = dev_alloc<double>(2 * (size_t)b->nnzS);
+        b->d_Hidx = dev_alloc_async<long long>(b->nnzH, bs.main);
+        b->d_Hdat = dev_alloc_async<double>(2 * (size_t)b->nnzH, bs.main);
+        b->d_Sidx = dev_alloc_async<long long>(b->nnzS, bs.main);
+        b->d_Sdat = dev_alloc_async<double>(2 * (size_t)b->nnzS, bs.main);
     }
     const long long nrows = b->nrows;
     // site kernel unless max_k exceeds its largest instantiation or its tables do
@@ -817,7 +817,13 @@ void block_free(bs2e_block* b)
     cudaFree(b->d_rows); cudaFree(b->d_row_local);
     cudaFree(b->d_site_key); cudaFree(b->d_site_ptr); cudaFree(b->d_site_rows);
     cudaFree(b->d_cntH); cudaFree(b->d_cntS); cudaFree(b->d_Hptr); cudaFree(b->d_Sptr);
-    cudaFree(b->d_Hidx); cudaFree(b->d_Sidx); cudaFree(b->d_Hdat); cudaFree(b->d_Sdat);
+    {   // stream-ordered: returns at once, the pool keeps the pages for the next block
+        cudaStream_t st = b->ctx ? b->ctx->stream : nullptr;
+        if (b->d_Hidx) cudaFreeAsync(b->d_Hidx, st);
+        if (b->d_Sidx) cudaFreeAsync(b->d_Sidx, st);
+        if (b->d_Hdat) cudaFreeAsync(b->d_Hdat, st);
+        if (b->d_Sdat) cudaFreeAsync(b->d_Sdat, st);
+    }
     cudaFree(b->d_scan_tmp);
     delete b;
 }

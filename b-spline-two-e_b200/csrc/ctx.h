@@ -39,6 +39,18 @@ T* dev_alloc(size_t n)
     BS2E_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
     return p;
 }
+// Stream-ordered allocation for the large CSR output arrays: cudaMalloc / cudaFree of
+// multi-GB buffers cost 5-500 ms each (measured; cudaFree unmaps synchronously), the
+// driver's memory pool with an unlimited release threshold (set in bs2e_ctx_create)
+// keeps the pages and hands them to the next block.
+template <class T>
+T* dev_alloc_async(size_t n, cudaStream_t st)
+{
+    T* p = nullptr;
+    BS2E_CUDA(cudaMallocAsync(&p, sizeof(T) * (n ? n : 1), st));
+    return p;
+}
+
 template <class T>
 T* dev_upload(const std::vector<T>& v, cudaStream_t st)
 {
