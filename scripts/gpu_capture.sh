@@ -16,6 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/ncu_launch.log 2>&1
 # setup (4 + 5 counts + 10 fills) and one warm-up step (19) are skipped, the timed step is captured
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"site_fill|block_fill|rk_build|diag_cells|block_count|cell_moments|pair_prefix" -s 38 -c 19 -o $out/full \
+    -k regex:"site_fill|block_fill|rk_build|diag_cells|site_count|block_count|cell_moments|pair_prefix" -s 38 -c 19 -o $out/full \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $out/ncu_full.log 2>&1
 ls -la $out
