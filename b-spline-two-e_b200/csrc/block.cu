@@ -178,7 +178,7 @@ __device__ __forceinline__ void load_coefs(const double* __restrict__ cf, double
 // WX: the sites of this launch have exchange windows (site_wants_X); the sites that
 // have none run a leaner instantiation (no exchange registers, half the n_c slots).
 template <int NT, int KMAX, bool CFSM, bool WX>
-__global__ void __launch_bounds__(NT, KMAX <= 13 ? (WX ? 512 : 768) / NT : 256 / NT)
+__global__ void __launch_bounds__(NT, (WX ? (KMAX <= 13 ? 512 : KMAX <= 21 ? 384 : 256) : (KMAX <= 13 ? 768 : 512)) / NT)
 site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int site_off, const double* __restrict__ R,
                  const long long* __restrict__ Hptr,
                  const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
