@@ -53,7 +53,15 @@ def concat_fragments(frags):
     return np.concatenate(ptrs), np.concatenate(idx), np.concatenate(dat)
 
 
-def site_partition(conf_n, weights, parts):
+def exchange_cost(max_k):
+    """Measured cost of a stored element at a site WITH exchange windows relative to one
+    without (the fill kernel keeps the R^k values of both windows in registers there:
+    128 / 168 / 248 registers per thread for <= 13 / 21 / 31 multipoles)."""
+    k1 = max_k + 1
+    return 1.4 if k1 <= 13 else 2.0 if k1 <= 21 else 2.7
+
+
+def site_partition(conf_n, weights, parts, k_spline=None, x_cost=1.0):
     """Deal the rows of a block to `parts` GPUs by the first radial index n(1).
 
     All rows (l1,l2; n1,n2) of a radial site (n1,n2) read the same R^k values and the
@@ -65,11 +73,16 @@ def site_partition(conf_n, weights, parts):
     ascending row ranges -- the argument of bs2e_block_plan_ranges.
 
     conf_n: (n_config, 2) array of term%configs(:)%n; weights: per-row work (stored
-    H + S entries).  Returns a list of `parts` lists of (lo, hi), 1-based inclusive;
-    a part may be empty when there are fewer distinct n1 than parts.
+    H + S entries).  With k_spline and x_cost > 1 the rows of sites that have exchange
+    windows (n1 - (k_spline-1) <= largest n2, site_core.h: site_wants_X) weigh x_cost
+    times more, see exchange_cost().  Returns a list of `parts` lists of (lo, hi),
+    1-based inclusive; a part may be empty when there are fewer distinct n1 than parts.
     """
     n1 = np.asarray(conf_n)[:, 0].astype(np.int64)
     w = np.asarray(weights, np.float64)
+    if k_spline is not None and x_cost != 1.0:
+        has_x = n1 - (int(k_spline) - 1) <= int(np.asarray(conf_n)[:, 1].max())
+        w = np.where(has_x, w * float(x_cost), w)
     nmax = int(n1.max())
     per_n1 = np.bincount(n1, weights=w, minlength=nmax + 1)[1:]          # index n1-1
     present = np.flatnonzero(np.bincount(n1, minlength=nmax + 1)[1:] > 0) + 1

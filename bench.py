@@ -130,7 +130,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import bs2e
-    from bs2e.sharding import site_partition
+    from bs2e.sharding import exchange_cost, site_partition
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus:
@@ -182,7 +182,7 @@ def run_ours(args):
             tmp = ctx.block_plan(s, full)
             cH, cS = tmp.row_counts()
             tmp.free()
-            mine = site_partition(s.conf_n, cH + cS, world)[rank]
+            mine = site_partition(s.conf_n, cH + cS, world, setup.k, exchange_cost(setup.p['max_k']))[rank]
             if not mine:
                 raise SystemExit(f"rank {rank}: empty share of block L={s.l} (more GPUs than radial indices)")
             ranges.append(mine)

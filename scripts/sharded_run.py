@@ -28,12 +28,16 @@ def main():
     import torch
     import torch.distributed as dist
     import bs2e
-    from bs2e.sharding import site_partition
+    from bs2e.sharding import exchange_cost, site_partition
 
     workload = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    # profiling aid: BS2E_FAKE_SHARD="r/n" runs the share of rank r of n on a single GPU
+    fake = os.environ.get("BS2E_FAKE_SHARD")
     torch.cuda.set_device(local)
+    if fake:
+        fr, fn = (int(v) for v in fake.split("/"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -63,12 +67,17 @@ def main():
 
     per_block, tot_ms, my_elems, xor = [], 0.0, 0, 0
     t_wall = time.perf_counter()
+    only = os.environ.get("BS2E_ONLY_BLOCKS")
+    if only:
+        syms = [syms[int(q)] for q in only.split(",")]
     for s in syms:
         whole = ctx.block_plan(s, full)                     # counts of all rows: partition weights
         cH, cS = whole.row_counts()
         nnz_all = whole.nnz_H + whole.nnz_S
         whole.free()
-        mine = site_partition(s.conf_n, cH + cS, world)[rank]
+        xc = exchange_cost(setup.p['max_k'])
+        mine = (site_partition(s.conf_n, cH + cS, fn, setup.k, xc)[fr] if fake
+                else site_partition(s.conf_n, cH + cS, world, setup.k, xc)[rank])
         ms, el = 0.0, 0
         if mine:
             blk = ctx.block_plan(s, full, ranges=mine)
@@ -86,7 +95,7 @@ def main():
             blk.free()
         ms_max = allred(ms, dist.ReduceOp.MAX if world > 1 else None)
         el_sum = allred(el, dist.ReduceOp.SUM if world > 1 else None)
-        assert int(el_sum) == nnz_all, (el_sum, nnz_all)    # the shares tile the block
+        assert fake or int(el_sum) == nnz_all, (el_sum, nnz_all)    # the shares tile the block
         per_block.append({"L": s.l, "pi": s.pi, "n_config": s.n_config, "elements": int(el_sum),
                           "ms": ms_max, "csr_gb": 24e-9 * el_sum})
         tot_ms += ms_max

@@ -86,6 +86,11 @@ def test_site_partition_keeps_sites_together_and_merges():
         assert np.array_equal(mp_, ptr) and np.array_equal(mi, idx) and np.array_equal(md, dat)
     with pytest.raises(ValueError):
         merge_fragments(n, frags[:-1] if len(frags) > 1 else [])
+    # rows of sites with exchange windows weighted up: the first share shrinks, the tiling holds
+    plain = site_partition(s.conf_n, w, 2)
+    costly = site_partition(s.conf_n, w, 2, k_spline=6, x_cost=3.0)
+    rows = lambda part: sum(hi - lo + 1 for lo, hi in part)
+    assert rows(costly[0]) < rows(plain[0]) and rows(costly[0]) + rows(costly[1]) == n
 
 
 def _free_port():
