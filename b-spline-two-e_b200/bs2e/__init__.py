@@ -60,6 +60,9 @@ ABI = {
     "bs2e_block_free": (C.c_int, [vp]),
     "bs2e_host_alloc": (C.c_int, [i64, C.POINTER(vp)]),
     "bs2e_host_free": (C.c_int, [vp]),
+    "bs2e_set_radial_dipole": (C.c_int, [vp, i64, _pd, vp]),
+    "bs2e_dip_block_count": (C.c_int, [vp, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64, C.POINTER(i64)]),
+    "bs2e_dip_block_fill": (C.c_int, [vp, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64, vp, vp, vp]),
     "bs2e_file_create_block_diag": (C.c_int, [C.c_char_p, i64, _pi, C.POINTER(vp)]),
     "bs2e_file_write_block": (C.c_int, [vp, i64, i64, i64, vp, vp, vp]),
     "bs2e_file_write_block_fragments": (C.c_int, [vp, i64, i64, i64, _pi, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
@@ -386,6 +389,29 @@ class Context:
     def construct_block_tensor(self, sym, full):
         nnz = self.block_count(sym, full)
         return self.block_fill(sym, full, nnz)
+
+    # ---- dipole blocks: construct_dip_block_tensor (dipole.f90:8-47) ----
+    def set_radial_dipole(self, gauge, A, B=None):
+        """A = r_mat (gauge 'l') or dr_mat (gauge 'v'), B = r_inv_mat: Fortran (n, n') matrices"""
+        flat = lambda M: np.ascontiguousarray(np.asfortranarray(M).ravel(order="F").view(np.float64))
+        Bf = flat(B) if B is not None else None
+        _chk(lib().bs2e_set_radial_dipole(self.h, ord(gauge), flat(A), _ptr(Bf)))
+
+    def construct_dip_block_tensor(self, sym1, sym2, q, compute=True):
+        s1 = np.ascontiguousarray([sym1.l, sym1.m, sym1.pi], np.int64)
+        s2 = np.ascontiguousarray([sym2.l, sym2.m, sym2.pi], np.int64)
+        cn1, cl1 = self._conf(sym1)
+        cn2, cl2 = self._conf(sym2)
+        args = (self.h, q, s1, sym1.n_config, cn1, cl1, s2, sym2.n_config, cn2, cl2, int(bool(compute)))
+        n = i64()
+        _chk(lib().bs2e_dip_block_count(*args, C.byref(n)))
+        nnz = int(n.value)
+        ptr = np.ones(sym1.n_config + 1, np.int64)      # nnz = 0: dip_block%init leaves an empty block
+        idx = np.zeros(max(nnz, 1), np.int64)
+        dat = np.zeros(2 * max(nnz, 1))
+        if nnz > 0:
+            _chk(lib().bs2e_dip_block_fill(*args, _ptr(ptr), _ptr(idx), _ptr(dat)))
+        return CSR((sym1.n_config, sym2.n_config), nnz, ptr, idx[:nnz], dat.view(np.complex128)[:nnz])
 
     def blocks_run(self, blocks, recount=True):
         """count pass + fill of several planned blocks, pipelined over internal streams"""

@@ -122,6 +122,7 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         cudaFree(c->d_rowoff); cudaFree(c->d_pair);
         cudaFree(c->d_mom_rk); cudaFree(c->d_mom_rmk); cudaFree(c->d_pre); cudaFree(c->d_sufx);
         cudaFree(c->d_rd); cudaFree(c->d_R); cudaFree(c->d_Hb); cudaFree(c->d_Sb);
+        cudaFree(c->d_dipA); cudaFree(c->d_dipB);
         if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
         if (c->have_lanes) {
             for (auto& ln : c->lanes) {
@@ -256,6 +257,58 @@ int bs2e_set_one_particle(bs2e_ctx* c, int64_t max_l_1p, const double* H_vec, co
         BS2E_CUDA(cudaStreamSynchronize(c->stream));
         c->lmax_1p = (int)max_l_1p;
         c->have_1p = true;
+    });
+}
+
+int bs2e_set_radial_dipole(bs2e_ctx* c, int64_t gauge, const double* A, const double* B)
+{
+    return guarded("bs2e_set_radial_dipole", [&] {
+        if (!c || !A) throw Error("null argument");
+        if (gauge != 'l' && gauge != 'v') throw Error("gauge must be 'l' (108) or 'v' (118)");
+        if (gauge == 'v' && !B) throw Error("the velocity gauge needs r_inv_mat");
+        use_device(c);
+        const Geom& g = c->hg;
+        const size_t per = band_doubles(g);
+        std::vector<double> Ab(per, 0.0), Bb(gauge == 'v' ? per : 0, 0.0);
+        try {
+            pack_band(g, A, Ab.data(), gauge == 'l' ? "r_mat" : "dr_mat");
+            if (gauge == 'v') pack_band(g, B, Bb.data(), "r_inv_mat");
+        } catch (const std::invalid_argument& e) {
+            throw Error(e.what());
+        }
+        BS2E_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_dipA);
+        cudaFree(c->d_dipB);
+        c->d_dipA = c->d_dipB = nullptr;
+        c->d_dipA = dev_upload(Ab, c->stream);
+        if (gauge == 'v') c->d_dipB = dev_upload(Bb, c->stream);
+        BS2E_CUDA(cudaStreamSynchronize(c->stream));
+        c->dip_gauge = (int)gauge;
+        c->have_dip = true;
+    });
+}
+
+int bs2e_dip_block_count(bs2e_ctx* c, int64_t q, const int64_t* sym1, int64_t n_config1, const int64_t* conf_n1,
+                         const int64_t* conf_l1, const int64_t* sym2, int64_t n_config2, const int64_t* conf_n2,
+                         const int64_t* conf_l2, int64_t compute, int64_t* nnz)
+{
+    return guarded("bs2e_dip_block_count", [&] {
+        if (!c || !sym1 || !sym2 || !conf_n1 || !conf_l1 || !conf_n2 || !conf_l2 || !nnz) throw Error("null argument");
+        use_device(c);
+        *nnz = dip_block_run(c, (int)q, sym1, n_config1, conf_n1, conf_l1, sym2, n_config2, conf_n2, conf_l2,
+                             compute != 0, nullptr, nullptr, nullptr);
+    });
+}
+
+int bs2e_dip_block_fill(bs2e_ctx* c, int64_t q, const int64_t* sym1, int64_t n_config1, const int64_t* conf_n1,
+                        const int64_t* conf_l1, const int64_t* sym2, int64_t n_config2, const int64_t* conf_n2,
+                        const int64_t* conf_l2, int64_t compute, int64_t* index_ptr, int64_t* indices, double* data)
+{
+    return guarded("bs2e_dip_block_fill", [&] {
+        if (!c || !sym1 || !sym2 || !conf_n1 || !conf_l1 || !conf_n2 || !conf_l2 || !index_ptr) throw Error("null argument");
+        use_device(c);
+        dip_block_run(c, (int)q, sym1, n_config1, conf_n1, conf_l1, sym2, n_config2, conf_n2, conf_l2, compute != 0,
+                      index_ptr, indices, data);
     });
 }
 

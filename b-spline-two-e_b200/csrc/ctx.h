@@ -104,6 +104,10 @@ struct bs2e_ctx {
     int lmax_1p = -1;
     double *d_Hb = nullptr, *d_Sb = nullptr;
     bool have_1p = false;
+    // radial dipole matrices (band storage): gauge 'l': A = r_mat; gauge 'v': A = dr_mat, B = r_inv_mat
+    int dip_gauge = 0;
+    double *d_dipA = nullptr, *d_dipB = nullptr;
+    bool have_dip = false;
 
     bs2e::CellData cell_data() const
     {
@@ -164,4 +168,7 @@ void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat
 void block_row_counts(bs2e_block* b, int64_t* cH, int64_t* cS);
 void block_checksum(bs2e_block* b, uint64_t* sH, uint64_t* sS);
 void block_free(bs2e_block* b);
+long long dip_block_run(bs2e_ctx* c, int q, const int64_t* sym1, long long n1, const int64_t* conf_n1,
+                        const int64_t* conf_l1, const int64_t* sym2, long long n2, const int64_t* conf_n2,
+                        const int64_t* conf_l2, bool compute, int64_t* index_ptr, int64_t* indices, double* data);
 }  // namespace bs2e

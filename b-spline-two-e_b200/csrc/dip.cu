@@ -1,0 +1,120 @@
+// dip.cu -- dipole blocks <sym1| d_q |sym2> as CSR matrices on the device.
+//
+// Stands in for construct_dip_block_tensor + init_dip_block
+// (src/mat_els/dipole.f90:8-47,87-146).  The reference scans all n1 x n2 configuration
+// pairs twice; here the stored columns of a row are generated from the (l1,l2) group
+// structure of the column list (dip_core.h), a count kernel + exclusive scan give
+// index_ptr, and one warp per row writes indices and values in ascending column order.
+// HBM-write bound (24 B per stored element), no R^k involved.
+#include <cub/device/device_scan.cuh>
+
+#include "ctx.h"
+#include "dip_plan.h"
+
+namespace bs2e {
+
+__global__ void dip_count_kernel(Geom g, Plan plC, DipTables dt, long long* __restrict__ cnt)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx > dt.nrows) return;
+    cnt[idx] = idx < dt.nrows ? dip_row_count(g, plC, dt, (int)idx + 1) : 0;  // slot nrows: total after the scan
+}
+
+constexpr int kDipWarps = 8;
+
+namespace {
+struct DevArena {   // device arrays of one call, released on every exit path
+    std::vector<void*> p;
+    ~DevArena() { for (void* q : p) cudaFree(q); }
+    template <class T> T* up(const std::vector<T>& v, cudaStream_t s) { T* d = dev_upload(v, s); p.push_back(d); return d; }
+    template <class T> T* alloc(size_t n) { T* d = dev_alloc<T>(n); p.push_back(d); return d; }
+};
+}  // namespace
+
+__global__ void __launch_bounds__(kDipWarps * 32)
+dip_fill_kernel(Geom g, Plan plC, DipTables dt, DipBand bd, const long long* __restrict__ ptr,
+                long long* __restrict__ idx, double2* __restrict__ dat)
+{
+    const long long wrow = (long long)blockIdx.x * kDipWarps + (threadIdx.x >> 5);
+    if (wrow >= dt.nrows) return;
+    const int lane = threadIdx.x & 31;
+    const RowInfo r = dip_row(dt, (int)wrow + 1);
+    long long pos = ptr[wrow] - 1;
+    dip_for_each_chunk(g, plC, dt, r, [&](int bj, int nc, const Segment& s, int base, int hi) {
+        const int nd = base + lane;
+        if (nd <= hi) {
+            const Cplx v = dip_value(g, dt, bd, r, bj, nc, nd);
+            idx[pos + lane] = (long long)s.jbase + nd;
+            dat[pos + lane] = make_double2(v.re, v.im);
+        }
+        pos += imin(32, hi - base + 1);
+    });
+}
+
+// count -> scan -> (optionally) fill + download.  index_ptr may be NULL (count only).
+long long dip_block_run(bs2e_ctx* c, int q, const int64_t* sym1, long long n1, const int64_t* conf_n1,
+                        const int64_t* conf_l1, const int64_t* sym2, long long n2, const int64_t* conf_n2,
+                        const int64_t* conf_l2, bool compute, int64_t* index_ptr, int64_t* indices, double* data)
+{
+    if (!c->have_dip) throw Error("dipole block: call bs2e_set_radial_dipole first");
+    if (!c->have_1p) throw Error("dipole block: call bs2e_set_one_particle first (overlap matrix)");
+    HostDipPlan hp;
+    try {
+        hp = build_dip_plan(c->hg, c->dip_gauge, q, sym1, n1, conf_n1, conf_l1, sym2, n2, conf_n2, conf_l2, compute);
+    } catch (const std::invalid_argument& e) {
+        throw Error(e.what());
+    }
+    if (hp.empty) return 0;   // dip_block%init(shape, 0): no arrays are written (dipole.f90:26-30)
+    cudaStream_t st = c->stream;
+    DevArena dev;
+    Plan plC{};
+    plC.nblk = hp.cols.nblk;
+    plC.n_config = (int)n2;
+    plC.full = 1;
+    plC.L = (int)sym2[0];
+    plC.max_nd = hp.cols.max_nd;
+    plC.blk = dev.up(hp.cols.blocks, st);
+    plC.ncrow = dev.up(hp.cols.ncrow, st);
+    DipTables dt = hp.tables();
+    dt.flag = dev.up(hp.flag, st);
+    dt.coef = dev.up(hp.coef, st);
+    dt.row_n1 = dev.up(hp.rows.row_n1, st);
+    dt.row_n2 = dev.up(hp.rows.row_n2, st);
+    dt.row_blk = dev.up(hp.rows.row_blk, st);
+    const long long nrows = n1;
+    long long* d_cnt = dev.alloc<long long>(nrows + 1);
+    long long* d_ptr = dev.alloc<long long>(nrows + 1);
+    dip_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(c->dg, plC, dt, d_cnt);
+    BS2E_LAUNCHED();
+    size_t tmp = 0;
+    BS2E_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp, d_cnt, d_ptr, cub::Sum(), 1LL, nrows + 1, st));
+    void* d_tmp = dev.alloc<char>(tmp ? tmp : 1);
+    BS2E_CUDA(cub::DeviceScan::ExclusiveScan(d_tmp, tmp, d_cnt, d_ptr, cub::Sum(), 1LL, nrows + 1, st));
+    g_launches.fetch_add(2);
+    long long last = 0;
+    BS2E_CUDA(cudaMemcpyAsync(&last, d_ptr + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    BS2E_CUDA(cudaStreamSynchronize(st));
+    const long long nnz = last - 1;
+    if (!index_ptr || nnz == 0) return nnz;
+    long long* d_idx = dev_alloc_async<long long>((size_t)nnz, st);
+    double* d_dat = dev_alloc_async<double>(2 * (size_t)nnz, st);
+    try {
+        const DipBand bd{c->d_dipA, c->d_dipB ? c->d_dipB : c->d_dipA, c->d_Sb};
+        dip_fill_kernel<<<(unsigned)((nrows + kDipWarps - 1) / kDipWarps), kDipWarps * 32, 0, st>>>(
+            c->dg, plC, dt, bd, d_ptr, d_idx, reinterpret_cast<double2*>(d_dat));
+        BS2E_LAUNCHED();
+        BS2E_CUDA(cudaMemcpyAsync(index_ptr, d_ptr, sizeof(long long) * (nrows + 1), cudaMemcpyDeviceToHost, st));
+        BS2E_CUDA(cudaMemcpyAsync(indices, d_idx, sizeof(long long) * nnz, cudaMemcpyDeviceToHost, st));
+        BS2E_CUDA(cudaMemcpyAsync(data, d_dat, sizeof(double) * 2 * nnz, cudaMemcpyDeviceToHost, st));
+        BS2E_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaFreeAsync(d_idx, st);
+        cudaFreeAsync(d_dat, st);
+        throw;
+    }
+    cudaFreeAsync(d_idx, st);
+    cudaFreeAsync(d_dat, st);
+    return nnz;
+}
+
+}  // namespace bs2e

@@ -200,6 +200,30 @@ double six_j(int j1, int j2, int j3, int j4, int j5, int j6)
 }
 
 // wigner_tools.f90:107-112
+// General 3j symbol for integer j, m (wigner_tools.f90:30-45 calls gsl_sf_coupling_3j):
+// Racah's single sum in long double; the arguments of this path are small (the dipole
+// Wigner-Eckart factor (L 1 L'; -M q M')), so factorials stay far inside the range.
+double three_j(int ja, int jb, int jc, int ma, int mb, int mc)
+{
+    auto fact = [](int n) { long double f = 1.0L; for (int q = 2; q <= n; ++q) f *= (long double)q; return f; };
+    auto tri = [](int a, int b, int c) { return a + b >= c && a + c >= b && b + c >= a; };
+    if (ja < 0 || jb < 0 || jc < 0 || ma + mb + mc != 0) return 0.0;
+    if (std::abs(ma) > ja || std::abs(mb) > jb || std::abs(mc) > jc || !tri(ja, jb, jc)) return 0.0;
+    const int t1 = jb - jc - ma, t2 = ja + mb - jc, t3 = ja + jb - jc, t4 = ja - ma, t5 = jb + mb;
+    const int tmin = std::max(0, std::max(t1, t2)), tmax = std::min(t3, std::min(t4, t5));
+    if (tmax < tmin) return 0.0;
+    long double sum = 0.0L;
+    for (int t = tmin; t <= tmax; ++t) {
+        const long double d = fact(t) * fact(t - t1) * fact(t - t2) * fact(t3 - t) * fact(t4 - t) * fact(t5 - t);
+        sum += ((t & 1) ? -1.0L : 1.0L) / d;
+    }
+    const long double delta = fact(ja + jb - jc) * fact(ja - jb + jc) * fact(-ja + jb + jc) / fact(ja + jb + jc + 1);
+    long double v = sqrtl(delta * fact(ja + ma) * fact(ja - ma) * fact(jb + mb) * fact(jb - mb) * fact(jc + mc) *
+                          fact(jc - mc)) * sum;
+    if ((ja - jb - mc) & 1) v = -v;
+    return (double)v;
+}
+
 double C_red_mat(int k, int a, int b)
 {
     const double sgn = (a & 1) ? -1.0 : 1.0;

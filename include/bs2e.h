@@ -147,6 +147,26 @@ int bs2e_block_free(bs2e_block *blk);
 int bs2e_host_alloc(int64_t bytes, void **ptr);
 int bs2e_host_free(void *ptr);
 
+/* ---- dipole blocks (the next stage of basis_setup, main_basis_setup.f90:125-152).
+ * bs2e_set_radial_dipole: type(radial_dipole) as setup_radial_dip fills it
+ *   (src/mat_els/mat_els.f90:14-19,120-170): dense complex n_b x n_b column-major;
+ *   gauge 'l' (108): A = r_mat, B ignored; gauge 'v' (118): A = dr_mat, B = r_inv_mat.
+ * bs2e_dip_block_count / _fill = init_dip_block + construct_dip_block_tensor
+ *   (src/mat_els/dipole.f90:8-47,87-146) for the block <sym1| d_q |sym2>: sym = (l, m, pi),
+ *   rows are the configurations of sym1, columns those of sym2, q in {-1,0,1}; compute as
+ *   in the reference (a block that is forbidden or not computed has nnz = 0 and no arrays).
+ *   The overlap matrix is the one given to bs2e_set_one_particle.  index_ptr has
+ *   n_config1+1 entries; indices / data have the nnz of the count call.              */
+int bs2e_set_radial_dipole(bs2e_ctx *ctx, int64_t gauge, const double *A, const double *B);
+int bs2e_dip_block_count(bs2e_ctx *ctx, int64_t q, const int64_t *sym1, int64_t n_config1,
+                         const int64_t *conf_n1, const int64_t *conf_l1, const int64_t *sym2,
+                         int64_t n_config2, const int64_t *conf_n2, const int64_t *conf_l2,
+                         int64_t compute, int64_t *nnz);
+int bs2e_dip_block_fill(bs2e_ctx *ctx, int64_t q, const int64_t *sym1, int64_t n_config1,
+                        const int64_t *conf_n1, const int64_t *conf_l1, const int64_t *sym2,
+                        int64_t n_config2, const int64_t *conf_n2, const int64_t *conf_l2,
+                        int64_t compute, int64_t *index_ptr, int64_t *indices, double *data);
+
 /* ---- result files of basis_setup, written natively (no Fortran runtime):
  *      gfortran unformatted sequential records, 8-byte default integers.  Lets a
  *      driver hand the GPU-built matrices to the reference's consumers (diag,

@@ -1173,3 +1173,169 @@ int orc_construct_block_tensor(const orc_bspline *bs, int64_t max_l_1p,
 #undef H_
     return overflow ? -1 : 0;
 }
+
+/* ======================================================================== */
+/* Dipole blocks                                       */
+/* ======================================================================== */
+
+/* wigner_tools.f90:30-45 three_j -> gsl_sf_coupling_3j, integer j and m.
+ * Racah's formula in long double (all j <= ~30 here: factorials <= 100!
+ * stay inside the long double range and the sum has no severe cancellation
+ * for the small arguments of this path).                                    */
+static long double lfact(int64_t n)
+{
+    long double f = 1.0L;
+    for (int64_t q = 2; q <= n; ++q) f *= (long double)q;
+    return f;
+}
+
+double orc_three_j(int64_t ja, int64_t jb, int64_t jc, int64_t ma, int64_t mb, int64_t mc)
+{
+    if (ja < 0 || jb < 0 || jc < 0) return 0.0;
+    if (ma + mb + mc != 0) return 0.0;
+    if (iabs64(ma) > ja || iabs64(mb) > jb || iabs64(mc) > jc) return 0.0;
+    if (!triangle_ok(ja, jb, jc)) return 0.0;
+    const int64_t t1 = jb - jc - ma, t2 = ja + mb - jc;       /* lower limits -t1, -t2 */
+    const int64_t t3 = ja + jb - jc, t4 = ja - ma, t5 = jb + mb;
+    const int64_t tmin = imax64(0, imax64(t1, t2)), tmax = imin64(t3, imin64(t4, t5));
+    if (tmax < tmin) return 0.0;
+    long double sum = 0.0L;
+    for (int64_t t = tmin; t <= tmax; ++t) {
+        long double d = lfact(t) * lfact(t - t1) * lfact(t - t2) * lfact(t3 - t) * lfact(t4 - t) * lfact(t5 - t);
+        sum += ((t & 1) ? -1.0L : 1.0L) / d;
+    }
+    long double delta = lfact(ja + jb - jc) * lfact(ja - jb + jc) * lfact(-ja + jb + jc) / lfact(ja + jb + jc + 1);
+    long double pref = sqrtl(delta * lfact(ja + ma) * lfact(ja - ma) * lfact(jb + mb) * lfact(jb - mb) *
+                             lfact(jc + mc) * lfact(jc - mc));
+    long double v = pref * sum;
+    if ((ja - jb - mc) & 1) v = -v;
+    return (double)v;
+}
+
+/* mat_els.f90:120-170 setup_radial_dip with :348-390 compute_radial_dip_len /
+ * compute_radial_dip_vel.  gauge 'l': A = r_mat, B untouched (may be NULL);
+ * gauge 'v': A = dr_mat, B = r_inv_mat.  Dense complex n_b x n_b, column-major. */
+int orc_setup_radial_dip(const orc_bspline *bs, int64_t k_GL, int gauge, double *A_out, double *B_out)
+{
+    if (gauge != 'l' && gauge != 'v') return -1;
+    const int64_t nb = bs->n_b, cells = bs->nbp - 1;
+    zcplx *A = (zcplx *)A_out, *B = (zcplx *)B_out;
+    for (int64_t q = 0; q < nb * nb; ++q) A[q] = 0.0;
+    if (gauge == 'v') for (int64_t q = 0; q < nb * nb; ++q) B[q] = 0.0;
+    double *x = (double *)malloc(sizeof(double) * (size_t)(k_GL * cells));
+    double *w = (double *)malloc(sizeof(double) * (size_t)(k_GL * cells));
+    for (int64_t c = 0; c < cells; ++c)
+        orc_gauss_legendre(k_GL, bs->bp[c], bs->bp[c + 1], x + c * k_GL, w + c * k_GL);
+    double *cw = (double *)calloc((size_t)bs->n, sizeof(double));
+    const zcplx mi = -I;   /* dcmplx(0.d0,-1.d0) */
+    for (int64_t j_b = 1; j_b <= nb; ++j_b)
+        for (int64_t i_b = 1; i_b <= nb; ++i_b) {
+            if (iabs64(j_b - i_b) >= bs->k) continue;
+            for (int64_t i_r = 1; i_r <= cells; ++i_r) {
+                if (!(support(bs, i_r, i_b + 1) && support(bs, i_r, j_b + 1))) continue;
+                const double *r = x + (i_r - 1) * k_GL, *ww = w + (i_r - 1) * k_GL;
+                const size_t at = (size_t)((i_b - 1) + nb * (j_b - 1));
+                for (int64_t q = 0; q < k_GL; ++q) {
+                    double B_i = bspl_unit(bs, cw, i_b, r[q], 0, i_r);
+                    double B_j = bspl_unit(bs, cw, j_b, r[q], 0, i_r);
+                    if (gauge == 'l') {
+                        A[at] = A[at] + ww[q] * r[q] * B_i * B_j;
+                    } else {
+                        double D_B_j = bspl_unit(bs, cw, j_b, r[q], 1, i_r);
+                        A[at] = A[at] + mi * ww[q] * B_i * D_B_j;
+                        B[at] = B[at] + mi * ww[q] * B_i * B_j / r[q];
+                    }
+                }
+            }
+        }
+    free(cw); free(x); free(w);
+    return 0;
+}
+
+typedef struct {
+    int gauge;
+    int64_t nb;
+    const zcplx *A, *B, *S;
+} dip_ctx;
+
+/* mat_els.f90:772-811 dip_red_1p_len / dip_red_1p_vel for the pair (n,l) -> (n_p,l_p) */
+static zcplx dip_red_1p(const dip_ctx *c, int64_t n, int64_t n_p, int64_t l, int64_t l_p)
+{
+    const size_t at = (size_t)((n - 1) + c->nb * (n_p - 1));
+    if (c->gauge == 'l') return c->A[at] * orc_C_red_mat(1, l, l_p);
+    if (iabs64(l - l_p) != 1) return 0.0;
+    if (l > l_p) return sqrt((double)l) * (c->A[at] - (double)(l_p + 1) * c->B[at]);
+    return -sqrt((double)l_p) * (c->A[at] + (double)l_p * c->B[at]);
+}
+
+/* mat_els.f90:739-770 dip_red_mat; n = (n1,n2), l = (l1,l2) of both configurations */
+static zcplx dip_red_mat(const dip_ctx *c, int64_t L_1, int64_t L_2, const int64_t *n1, const int64_t *l1,
+                         const int64_t *n2, const int64_t *l2)
+{
+    zcplx res_1 = 0.0, res_2 = 0.0;
+    const double rt = sqrt((double)((2 * L_1 + 1) * (2 * L_2 + 1)));
+    if (l1[1] == l2[1]) {
+        double sg = ((l1[0] + l1[1] + L_2 + 1) & 1) ? -1.0 : 1.0;
+        res_1 = sg * rt * orc_six_j(L_1, 1, L_2, l2[0], l1[1], l1[0]) * dip_red_1p(c, n1[0], n2[0], l1[0], l2[0]) *
+                c->S[(size_t)((n1[1] - 1) + c->nb * (n2[1] - 1))];
+    }
+    if (l1[0] == l2[0]) {
+        double sg = ((l1[0] + l2[1] + L_1 + 1) & 1) ? -1.0 : 1.0;
+        res_2 = sg * rt * orc_six_j(L_1, 1, L_2, l2[1], l1[0], l1[1]) * dip_red_1p(c, n1[1], n2[1], l1[1], l2[1]) *
+                c->S[(size_t)((n1[0] - 1) + c->nb * (n2[0] - 1))];
+    }
+    return res_1 + res_2;
+}
+
+/* mat_els.f90:813-831 ang_dip_red */
+static double ang_dip_red(int64_t L_1, int64_t L_2, const int64_t *l1, const int64_t *l2)
+{
+    double res = 0.0;
+    if (l1[1] == l2[1]) res = res + fabs(orc_six_j(L_1, 1, L_2, l2[0], l1[1], l1[0]) * orc_C_red_mat(1, l1[0], l2[0]));
+    if (l1[0] == l2[0]) res = res + fabs(orc_six_j(L_1, 1, L_2, l2[1], l1[0], l1[1]) * orc_C_red_mat(1, l1[1], l2[1]));
+    return res;
+}
+
+/* dipole.f90:8-47 construct_dip_block_tensor with :87-146 init_dip_block.
+ * sym = (l, m, pi).  Returns nnz (>= 0); when index_ptr is NULL only counts.
+ * An empty block (forbidden, or compute false) has nnz 0 and no arrays.      */
+int64_t orc_dip_block(const orc_bspline *bs, int gauge, const double *A, const double *B, const double *S,
+                      int64_t q, const int64_t *sym1, int64_t n1c, const int64_t *conf_n1, const int64_t *conf_l1,
+                      const int64_t *sym2, int64_t n2c, const int64_t *conf_n2, const int64_t *conf_l2,
+                      int64_t compute, int64_t *index_ptr, int64_t *indices, double *data_)
+{
+    const int64_t ks = bs->k;
+    const int64_t L_1 = sym1[0], L_2 = sym2[0];
+    const int parity_allowed = (sym1[2] != 0) != (sym2[2] != 0);
+    double ang = orc_three_j(L_1, 1, L_2, -sym1[1], q, sym2[1]);
+    if ((L_1 - sym1[1]) & 1) ang = -ang;
+    if (fabs(ang) < 5.e-16 || !parity_allowed || !compute) return 0;
+    dip_ctx c = { gauge, bs->n_b, (const zcplx *)A, (const zcplx *)B, (const zcplx *)S };
+    zcplx *data = (zcplx *)data_;
+    int64_t ptr = 1;
+    for (int64_t i = 1; i <= n1c; ++i) {
+        const int64_t *na = conf_n1 + 2 * (i - 1), *la = conf_l1 + 2 * (i - 1);
+        if (index_ptr) index_ptr[i - 1] = ptr;
+        for (int64_t j = 1; j <= n2c; ++j) {
+            const int64_t *nc = conf_n2 + 2 * (j - 1), *lc = conf_l2 + 2 * (j - 1);
+            int sup = (iabs64(na[0] - nc[0]) < ks) && (iabs64(na[1] - nc[1]) < ks);
+            int sup_ex = (iabs64(na[0] - nc[1]) < ks) && (iabs64(na[1] - nc[0]) < ks);
+            int nz = 0;
+            if (sup) { if (ang_dip_red(L_1, L_2, la, lc) > 5.e-16) nz = 1; }
+            else if (sup_ex) { if (ang_dip_red(L_1, L_2, la, lc) > 5.e-16) nz = 1; }
+            if (!nz) continue;
+            if (index_ptr) {
+                /* dipole.f90:36-42 + mat_els.f90:717-737 dip_mat_neq */
+                const int64_t nx[2] = { nc[1], nc[0] }, lx[2] = { lc[1], lc[0] };
+                zcplx red = dip_red_mat(&c, L_1, L_2, na, la, nc, lc);
+                double sg = ((L_2 + lc[0] + lc[1]) & 1) ? -1.0 : 1.0;
+                zcplx red_ex = sg * dip_red_mat(&c, L_1, L_2, na, la, nx, lx);
+                indices[ptr - 1] = j;
+                data[ptr - 1] = ang * (red + red_ex);
+            }
+            ptr = ptr + 1;
+        }
+    }
+    if (index_ptr) index_ptr[n1c] = ptr;
+    return ptr - 1;
+}

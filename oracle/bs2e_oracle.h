@@ -147,6 +147,18 @@ int orc_construct_block_tensor(const orc_bspline *bs, int64_t max_l_1p,
                                int64_t cap_S, int64_t *S_ptr, int64_t *S_idx, double *S_dat,
                                int64_t *emitted);
 
+/* ---- dipole blocks ------------------------------------ */
+/* wigner_tools.f90:30-45 three_j (integer j, m) */
+double orc_three_j(int64_t ja, int64_t jb, int64_t jc, int64_t ma, int64_t mb, int64_t mc);
+/* mat_els.f90:120-170,348-390: gauge 'l': A = r_mat; gauge 'v': A = dr_mat, B = r_inv_mat */
+int orc_setup_radial_dip(const orc_bspline *bs, int64_t k_GL, int gauge, double *A, double *B);
+/* dipole.f90:8-47,87-146 construct_dip_block_tensor / init_dip_block; sym = (l, m, pi);
+ * index_ptr == NULL: count only.  Returns nnz.                                        */
+int64_t orc_dip_block(const orc_bspline *bs, int gauge, const double *A, const double *B, const double *S,
+                      int64_t q, const int64_t *sym1, int64_t n1c, const int64_t *conf_n1, const int64_t *conf_l1,
+                      const int64_t *sym2, int64_t n2c, const int64_t *conf_n2, const int64_t *conf_l2,
+                      int64_t compute, int64_t *index_ptr, int64_t *indices, double *data);
+
 int64_t orc_max_threads(void);
 
 #ifdef __cplusplus

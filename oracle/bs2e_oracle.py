@@ -79,6 +79,10 @@ def lib():
                                                  i64, _pi, _pi, _pd,
                                                  i64, _pi, _pi, _pd, _pi]),
         "orc_max_threads": (i64, []),
+        "orc_three_j": (f64, [i64] * 6),
+        "orc_setup_radial_dip": (C.c_int, [vp, i64, C.c_int, vp, vp]),
+        "orc_dip_block": (i64, [vp, C.c_int, vp, vp, _pd, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi,
+                                i64, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -116,6 +120,10 @@ def six_j(a, b, c, d, e, f):
 
 def ang_k_LS(k, la, lb, lc, ld, L):
     return lib().orc_ang_k_LS(k, la, lb, lc, ld, L)
+
+
+def three_j(ja, jb, jc, ma, mb, mc):
+    return lib().orc_three_j(ja, jb, jc, ma, mb, mc)
 
 
 class BSpline:
@@ -378,3 +386,51 @@ class OracleRun:
     def block(self, sym, rows=None, nnz=None):
         return construct_block_tensor(self.bs, self.H_vec, self.S, sym, self.p["max_k"],
                                       self.R, self.p["full"], nnz=nnz, rows=rows)
+
+
+# --------------------------------------------------------------------------
+# dipole blocks
+# --------------------------------------------------------------------------
+@dataclass
+class RadialDipole:
+    """type(radial_dipole) of mat_els.f90:14-19: gauge 'l' holds r_mat in A; gauge 'v'
+    holds dr_mat in A and r_inv_mat in B.  Fortran (n, n') matrices: M[n-1, n'-1]."""
+    gauge: str
+    A: np.ndarray
+    B: np.ndarray
+
+
+def setup_radial_dip(bs: BSpline, k_GL, gauge) -> RadialDipole:
+    nb = bs.n_b
+    A = np.zeros(2 * nb * nb)
+    B = np.zeros(2 * nb * nb) if gauge == "v" else None
+    rc = lib().orc_setup_radial_dip(bs._h, k_GL, ord(gauge), A.ctypes.data_as(C.c_void_p),
+                                    B.ctypes.data_as(C.c_void_p) if B is not None else None)
+    if rc != 0:
+        raise ValueError(f"unrecognised gauge {gauge!r}")
+    f = lambda M: M.view(np.complex128).reshape(nb, nb, order="F")
+    return RadialDipole(gauge, f(A), f(B) if B is not None else None)
+
+
+def construct_dip_block_tensor(bs: BSpline, rd: RadialDipole, S, sym1: Sym, sym2: Sym, q, compute=True):
+    """dipole.f90:8-47: CSR block <sym1| d_q |sym2> (rows: configurations of sym1)."""
+    flat = lambda M: np.ascontiguousarray(np.asfortranarray(M).ravel(order="F").view(np.float64))
+    A = flat(rd.A)
+    B = flat(rd.B) if rd.B is not None else None
+    Sf = flat(S)
+    s1 = np.ascontiguousarray([sym1.l, sym1.m, sym1.pi], np.int64)
+    s2 = np.ascontiguousarray([sym2.l, sym2.m, sym2.pi], np.int64)
+    args = (bs._h, ord(rd.gauge), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p) if B is not None else None,
+            Sf, q, s1, sym1.n_config, np.ascontiguousarray(sym1.conf_n.reshape(-1)),
+            np.ascontiguousarray(sym1.conf_l.reshape(-1)), s2, sym2.n_config,
+            np.ascontiguousarray(sym2.conf_n.reshape(-1)), np.ascontiguousarray(sym2.conf_l.reshape(-1)),
+            int(bool(compute)))
+    nnz = int(lib().orc_dip_block(*args, None, None, None))
+    ptr = np.ones(sym1.n_config + 1, np.int64)
+    idx = np.zeros(max(nnz, 1), np.int64)
+    dat = np.zeros(2 * max(nnz, 1))
+    if nnz > 0:
+        got = int(lib().orc_dip_block(*args, ptr.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
+                                      dat.ctypes.data_as(C.c_void_p)))
+        assert got == nnz
+    return CSR((sym1.n_config, sym2.n_config), nnz, ptr, idx[:nnz], dat.view(np.complex128)[:nnz])

@@ -14,6 +14,7 @@
 #include "../../b-spline-two-e_b200/csrc/plan.h"
 #include "../../b-spline-two-e_b200/csrc/slater_core.h"
 #include "../../b-spline-two-e_b200/csrc/site_core.h"
+#include "../../b-spline-two-e_b200/csrc/dip_plan.h"
 
 using namespace bs2e;
 
@@ -24,6 +25,8 @@ struct HcCtx {
     std::vector<double> mom_rk, mom_rmk, pre, sufx, rd, R;
     std::vector<double> Hb, Sb;
     int lmax_1p = -1;
+    std::vector<double> dipA, dipB;
+    int dip_gauge = 0;
 };
 
 extern "C" {
@@ -439,6 +442,73 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
     } catch (const std::exception& e) {
         g_err = e.what();
         return 1;
+    }
+}
+
+}  // extern "C"
+
+// ---- dipole blocks: emulates dip_count_kernel / dip_fill_kernel (dip.cu) ----
+extern "C" {
+
+int hc_set_radial_dipole(HcCtx* c, int64_t gauge, const double* A, const double* B)
+{
+    try {
+        const Geom& g = c->hg.g;
+        c->dipA.assign(band_doubles(g), 0.0);
+        c->dipB.assign(band_doubles(g), 0.0);
+        pack_band(g, A, c->dipA.data(), "A");
+        if (gauge == 'v') pack_band(g, B, c->dipB.data(), "B");
+        c->dip_gauge = (int)gauge;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// index_ptr == NULL: count only; returns nnz or -1
+int64_t hc_dip_block(HcCtx* c, int64_t q, const int64_t* sym1, int64_t n1, const int64_t* conf_n1,
+                     const int64_t* conf_l1, const int64_t* sym2, int64_t n2, const int64_t* conf_n2,
+                     const int64_t* conf_l2, int64_t compute, int64_t* index_ptr, int64_t* indices, double* data)
+{
+    try {
+        const Geom& g = c->hg.g;
+        HostDipPlan hp = build_dip_plan(g, c->dip_gauge, (int)q, sym1, n1, conf_n1, conf_l1, sym2, n2, conf_n2,
+                                        conf_l2, compute != 0);
+        if (hp.empty) return 0;
+        Plan plC = hp.cols.view();
+        if (plC.full != 1) throw std::logic_error("column plan must be built without the triangle cut");
+        const DipTables dt = hp.tables();
+        const DipBand bd{c->dipA.data(), c->dipB.data(), c->Sb.data()};
+        long long nnz = 0;
+        std::vector<long long> ptr(n1 + 1);
+        for (long long i = 0; i < n1; ++i) {     // count kernel + scan
+            ptr[i] = nnz + 1;
+            nnz += dip_row_count(g, plC, dt, (int)i + 1);
+        }
+        ptr[n1] = nnz + 1;
+        if (!index_ptr) return nnz;
+        for (long long i = 0; i <= n1; ++i) index_ptr[i] = ptr[i];
+        for (long long wrow = 0; wrow < n1; ++wrow) {   // fill kernel: one "warp" per row
+            const RowInfo r = dip_row(dt, (int)wrow + 1);
+            long long pos = ptr[wrow] - 1;
+            dip_for_each_chunk(g, plC, dt, r, [&](int bj, int nc, const Segment& s, int base, int hi) {
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int nd = base + lane;
+                    if (nd > hi) continue;
+                    const Cplx v = dip_value(g, dt, bd, r, bj, nc, nd);
+                    indices[pos + lane] = (long long)s.jbase + nd;
+                    data[2 * (pos + lane)] = v.re;
+                    data[2 * (pos + lane) + 1] = v.im;
+                }
+                pos += imin(32, hi - base + 1);
+            });
+            if (pos != ptr[wrow + 1] - 1) throw std::logic_error("dipole fill wrote a different number of entries than counted");
+        }
+        return nnz;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
     }
 }
 

@@ -38,6 +38,10 @@ def lib():
         L.hc_block_fill.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, _pi, _pi, _pi, _pi,
                                     _pi, _pd, _pi, _pd]
         L.hc_site_fill.argtypes = L.hc_block_fill.argtypes + [i64, i64]
+        L.hc_set_radial_dipole.argtypes = [C.c_void_p, i64, _pd, C.c_void_p]
+        L.hc_dip_block.restype = i64
+        L.hc_dip_block.argtypes = [C.c_void_p, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -113,3 +117,29 @@ class HostCheck:
         if rc:
             raise RuntimeError(lib().hc_last_error().decode())
         return (Hp, Hi[:nH], Hd.view(np.complex128)[:nH]), (Sp, Si[:nS], Sd.view(np.complex128)[:nS])
+
+    # ---- dipole blocks ----
+    def set_radial_dipole(self, gauge, A, B=None):
+        flat = lambda M: np.ascontiguousarray(np.asfortranarray(M).ravel(order="F").view(np.float64))
+        Bf = flat(B) if B is not None else None
+        if lib().hc_set_radial_dipole(self.h, ord(gauge), flat(A), Bf.ctypes.data_as(C.c_void_p) if Bf is not None else None):
+            raise RuntimeError(lib().hc_last_error().decode())
+
+    def dip_block(self, sym1, sym2, q, compute=True):
+        s1 = np.ascontiguousarray([sym1.l, sym1.m, sym1.pi], np.int64)
+        s2 = np.ascontiguousarray([sym2.l, sym2.m, sym2.pi], np.int64)
+        c = lambda a: np.ascontiguousarray(a.reshape(-1), np.int64)
+        args = (self.h, q, s1, sym1.n_config, c(sym1.conf_n), c(sym1.conf_l), s2, sym2.n_config, c(sym2.conf_n),
+                c(sym2.conf_l), int(bool(compute)))
+        nnz = int(lib().hc_dip_block(*args, None, None, None))
+        if nnz < 0:
+            raise RuntimeError(lib().hc_last_error().decode())
+        ptr = np.ones(sym1.n_config + 1, np.int64)
+        idx = np.full(max(nnz, 1), -1, np.int64)
+        dat = np.full(2 * max(nnz, 1), np.nan)
+        if nnz > 0:
+            got = int(lib().hc_dip_block(*args, ptr.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
+                                         dat.ctypes.data_as(C.c_void_p)))
+            if got != nnz:
+                raise RuntimeError(lib().hc_last_error().decode())
+        return ptr, idx[:nnz], dat.view(np.complex128)[:nnz]

@@ -1,0 +1,170 @@
+"""Dipole blocks: oracle anchors (3j vs sympy goldens, radial
+dipole integrals) and the CPU emulation of the dipole kernels (dip_core.h) against the
+oracle's restatement of construct_dip_block_tensor (dipole.f90:8-47,87-146)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg as sl
+
+from hostcheck_lib import HostCheck
+from oracle import bs2e_oracle as O
+from parity_utils import assert_csr_equal
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+DIP_CASES = {
+    # z_pol: M = 0 only, q = 0 couples L <-> L+-1; not z_pol: all M, q = -1,0,1
+    "zpol_k5": dict(k=5, m=2, Z=2, h_max=1.0, r_max=8.0, k_GL=9, max_k=3, max_L=2, max_l_1p=2, max_l2=2,
+                    r_2_max=5.0, CAP_eta=5e-3 + 0j, CAP_r_0=5.0, full=False, z_pol=True),
+    "allM_k4": dict(k=4, m=2, Z=1, h_max=1.0, r_max=6.0, k_GL=8, max_k=2, max_L=2, max_l_1p=2, max_l2=1,
+                    r_all_l=4.0, CAP_eta=0j, CAP_r_0=4.0, full=True, z_pol=False),
+}
+
+
+def test_three_j_matches_sympy_goldens():
+    g = json.load(open(os.path.join(GOLD, "wigner_golden.json")))["three_j"]
+    assert len(g) > 300
+    for ja, jb, jc, ma, mb, mc, ref in g:
+        assert abs(O.three_j(ja, jb, jc, ma, mb, mc) - ref) < 1e-14, (ja, jb, jc, ma, mb, mc)
+    assert O.three_j(1, 1, 1, 0, 0, 0) == 0.0 and O.three_j(2, 1, 1, 2, -1, 0) == 0.0   # structural zeros
+
+
+def test_radial_dipole_integrals():
+    run = O.OracleRun(k=8, m=3, Z=1, h_max=1.5, r_max=30.0, k_GL=14, max_k=0, max_l_1p=1, CAP_eta=0j)
+    run.one_particle()
+    rl = O.setup_radial_dip(run.bs, 14, "l")
+    rv = O.setup_radial_dip(run.bs, 14, "v")
+    assert np.abs(rl.A - rl.A.T).max() < 1e-13 and np.abs(rl.A.imag).max() == 0.0
+    assert np.abs(rv.A + rv.A.T).max() < 1e-13          # -i int B_i B_j' is antisymmetric (no boundary term)
+    assert np.abs(rv.B - rv.B.T).max() < 1e-13 and np.abs(rv.A.real).max() == 0.0
+    E0, V0 = sl.eigh(run.H_vec[0].real, run.S.real)
+    E1, V1 = sl.eigh(run.H_vec[1].real, run.S.real)
+    c1s, c2p = V0[:, 0], V1[:, 0]
+    assert abs(E0[0] + 0.5) < 1e-7 and abs(E1[0] + 0.125) < 1e-7
+    assert abs(c1s @ rl.A.real @ c1s - 1.5) < 1e-6                       # <1s|r|1s> = 3/(2Z)
+    r12 = abs(c1s @ rl.A.real @ c2p)
+    assert abs(r12 - 128 * np.sqrt(6) / 243) < 1e-6                      # <1s|r|2p> = 1.2902663
+    # velocity form: <1s| d/dr + 1/r |2p> = (E_2p - E_1s) <1s|r|2p>  (l' = l+1 branch of dip_red_1p_vel)
+    dv = abs(c1s @ (1j * rv.A) @ c2p + 1.0 * (c1s @ (1j * rv.B) @ c2p))
+    assert abs(dv - 0.375 * r12) < 1e-6
+
+
+@pytest.fixture(scope="module", params=list(DIP_CASES))
+def dip_case(request):
+    p = DIP_CASES[request.param]
+    run = O.OracleRun(**p)
+    run.one_particle(); run.basis()
+    glx, glw = O.gauss_legendre(run.p["k_GL"])
+    hc = HostCheck(run.p["k"], run.grid, run.p["max_k"], glx, glw)
+    hc.set_one_particle(run.H_vec, run.S)
+    return run, hc
+
+
+@pytest.mark.parametrize("gauge", ["l", "v"])
+def test_dipole_blocks_emulation_vs_oracle(dip_case, gauge):
+    run, hc = dip_case
+    rd = O.setup_radial_dip(run.bs, run.p["k_GL"], gauge)
+    hc.set_radial_dipole(gauge, rd.A, rd.B)
+    nonzero = 0
+    for q in (-1, 0, 1):
+        for s1 in run.syms:
+            for s2 in run.syms:
+                if s1.n_config == 0 or s2.n_config == 0:
+                    continue
+                D = O.construct_dip_block_tensor(run.bs, rd, run.S, s1, s2, q)
+                ptr, idx, dat = hc.dip_block(s1, s2, q)
+                assert len(idx) == D.nnz, (q, s1.l, s1.m, s2.l, s2.m)
+                if D.nnz == 0:
+                    continue
+                nonzero += 1
+                got = O.CSR(D.shape, D.nnz, ptr, idx, dat)
+                assert_csr_equal(got, D, what=f"D_{q} ({s1.l},{s1.m},{s1.pi})x({s2.l},{s2.m},{s2.pi}) gauge {gauge}")
+                # compute = .false. (lower triangle of the block matrix when not full): empty block
+                assert len(hc.dip_block(s1, s2, q, compute=False)[1]) == 0
+    assert nonzero >= 2
+
+
+def test_dipole_selection_rules_and_hermiticity(dip_case):
+    """<a|d_q|b> blocks vanish unless parities differ and (L1 1 L2; -M1 q M2) != 0; in the length
+    gauge without CAP the transposed block of <b|d_{-q}|a> carries the sign (-1)^q (d_q^+ = (-1)^q d_{-q})"""
+    run, hc = dip_case
+    rd = O.setup_radial_dip(run.bs, run.p["k_GL"], "l")
+    hc.set_radial_dipole("l", rd.A, None)
+    import scipy.sparse as sp
+    for q in (-1, 0, 1):
+        for s1 in run.syms:
+            for s2 in run.syms:
+                ptr, idx, dat = hc.dip_block(s1, s2, q)
+                allowed = (s1.pi != s2.pi) and abs(O.three_j(s1.l, 1, s2.l, -s1.m, q, s2.m)) > 5e-16
+                assert (len(idx) > 0) == (allowed and s1.n_config > 0 and s2.n_config > 0) or not allowed
+                if not allowed:
+                    assert len(idx) == 0
+                    continue
+                ptr2, idx2, dat2 = hc.dip_block(s2, s1, -q)
+                A = sp.csr_matrix((dat, idx - 1, ptr - 1), shape=(s1.n_config, s2.n_config)).toarray()
+                B = sp.csr_matrix((dat2, idx2 - 1, ptr2 - 1), shape=(s2.n_config, s1.n_config)).toarray()
+                scale = max(np.abs(A).max(), 1e-300)
+                assert np.abs(A - (-1) ** q * B.T).max() <= 1e-11 * scale
+
+
+# ---------------------------------------------------------------------------
+# the device path through the C ABI (bs2e_set_radial_dipole / bs2e_dip_block_*)
+# ---------------------------------------------------------------------------
+def _gpu_ctx(run):
+    import bs2e
+    glx, glw = O.gauss_legendre(run.p["k_GL"])
+    ctx = bs2e.Context(run.p["k"], run.grid, run.p["max_k"], run.p["k_GL"], glx, glw)
+    ctx.set_one_particle(run.H_vec, run.S)       # the overlap matrix of the dipole elements
+    return ctx
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(DIP_CASES))
+@pytest.mark.parametrize("gauge", ["l", "v"])
+def test_gpu_dipole_blocks_vs_oracle(name, gauge):
+    import bs2e
+    run = O.OracleRun(**DIP_CASES[name])
+    run.one_particle(); run.basis()
+    ctx = _gpu_ctx(run)
+    rd = O.setup_radial_dip(run.bs, run.p["k_GL"], gauge)
+    ctx.set_radial_dipole(gauge, rd.A, rd.B)
+    n0 = bs2e.launch_count()
+    nonzero = 0
+    for q in (-1, 0, 1):
+        for i, s1 in enumerate(run.syms):
+            for j, s2 in enumerate(run.syms):
+                compute = run.p["full"] or i <= j        # main_basis_setup.f90:135-139
+                D = O.construct_dip_block_tensor(run.bs, rd, run.S, s1, s2, q, compute)
+                G = ctx.construct_dip_block_tensor(s1, s2, q, compute)
+                assert G.nnz == D.nnz and G.shape == D.shape
+                if D.nnz:
+                    nonzero += 1
+                    assert_csr_equal(G, D, what=f"D_{q} block ({i},{j}) gauge {gauge}")
+    assert nonzero >= 2 and bs2e.launch_count() > n0
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_dipole_reference_grid_and_errors():
+    """the reference's test grid (n_b = 46): the 1S^e -> 1P^o block (3106 x 4k configurations) against
+    the oracle, the length-gauge dipole between the two lowest states, and misuse errors"""
+    import bs2e
+    run = O.OracleRun(k=8, m=3, Z=2, h_max=1.5, r_max=15.0, k_GL=14, max_k=4, max_L=1, max_l_1p=2, max_l2=2,
+                      CAP_eta=0j, CAP_r_0=45.0, full=False, z_pol=True)
+    run.one_particle(); run.basis()
+    ctx = _gpu_ctx(run)
+    s0, s1 = run.syms[0], run.syms[1]
+    with pytest.raises(bs2e.Bs2eError):
+        ctx.construct_dip_block_tensor(s0, s1, 0)        # radial dipole matrices not set
+    rd = O.setup_radial_dip(run.bs, 14, "l")
+    ctx.set_radial_dipole("l", rd.A, None)
+    with pytest.raises(bs2e.Bs2eError):
+        ctx.construct_dip_block_tensor(s0, s1, 2)        # q outside -1..1
+    G = ctx.construct_dip_block_tensor(s0, s1, 0)
+    D = O.construct_dip_block_tensor(run.bs, rd, run.S, s0, s1, 0)
+    assert G.nnz == D.nnz > 100000
+    assert_csr_equal(G, D, what="D_0 1S^e -> 1P^o")
+    assert ctx.construct_dip_block_tensor(s0, s0, 0).nnz == 0    # same parity: forbidden
+    ctx.close()
