@@ -64,6 +64,7 @@ ABI = {
     "bs2e_dip_block_count": (C.c_int, [vp, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64, C.POINTER(i64)]),
     "bs2e_dip_block_fill": (C.c_int, [vp, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64, vp, vp, vp]),
     "bs2e_file_create_block_diag": (C.c_int, [C.c_char_p, i64, _pi, C.POINTER(vp)]),
+    "bs2e_file_create_block_matrix": (C.c_int, [C.c_char_p, i64, i64, _pi, _pi, C.POINTER(vp)]),
     "bs2e_file_write_block": (C.c_int, [vp, i64, i64, i64, vp, vp, vp]),
     "bs2e_file_write_block_fragments": (C.c_int, [vp, i64, i64, i64, _pi, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "bs2e_file_close": (C.c_int, [vp]),
@@ -80,6 +81,7 @@ ABI = {
     "bs2e_host_find_max_n_b": (i64, [i64, i64, _pd, f64]),
     "bs2e_host_setup_S": (C.c_int, [i64, i64, _pd, i64, _pd]),
     "bs2e_host_setup_H_one_particle": (C.c_int, [i64, i64, _pd, i64, i64, i64, f64, f64, f64, i64, _pd]),
+    "bs2e_host_setup_radial_dip": (C.c_int, [i64, i64, _pd, i64, i64, _pd, vp]),
     "bs2e_host_basis_syms": (i64, [i64, i64, _pi, _pi, _pi, i64]),
     "bs2e_host_count_configs": (i64, [i64] * 8 + [vp, vp, vp, i64]),
     "bs2e_host_three_j0": (f64, [i64] * 3),
@@ -162,6 +164,17 @@ def setup_H_one_particle(k, knots, Z, l, CAP_order, CAP_r_0, CAP_eta, k_GL):
     _chk(lib().bs2e_host_setup_H_one_particle(k, len(knots), knots, Z, l, CAP_order, CAP_r_0,
                                               complex(CAP_eta).real, complex(CAP_eta).imag, k_GL, H))
     return H.view(np.complex128).reshape(nb, nb, order="F")
+
+
+def setup_radial_dip(k, knots, k_GL, gauge):
+    """(A, B): gauge 'l': (r_mat, None); gauge 'v': (dr_mat, r_inv_mat); Fortran (n, n') matrices"""
+    knots = np.ascontiguousarray(knots, np.float64)
+    nb = len(knots) - k - 2
+    A = np.zeros(2 * nb * nb)
+    B = np.zeros(2 * nb * nb) if gauge == "v" else None
+    _chk(lib().bs2e_host_setup_radial_dip(k, len(knots), knots, k_GL, ord(gauge), A, _ptr(B)))
+    f = lambda M: M.view(np.complex128).reshape(nb, nb, order="F")
+    return f(A), (f(B) if B is not None else None)
 
 
 @dataclass
@@ -441,7 +454,7 @@ class Context:
 BASIS_DEFAULTS = dict(  # input_tools.f90:825-844
     k=6, m=3, Z=2, h_max=0.5, r_max=15.0, r_2_max=-1.0, r_all_l=-1.0, k_GL=None,
     CAP_order=2, CAP_r_0=10.0, CAP_eta=complex(1e-3, 0.0), max_L=2, max_l_1p=5,
-    max_l2=5, max_k=4, z_pol=True, full=True, two_el=True)
+    max_l2=5, max_k=4, z_pol=True, full=True, two_el=True, gauge="v")
 
 # the five BASELINE.json configurations as namelist values
 CONFIGS = {

@@ -5,22 +5,22 @@ inputs, run the three GPU stages, store `splines.dat`, `basis.dat`, `H_diag.dat`
 `S_diag.dat` in the formats the reference's consumers load (bs2e.files).  A symmetry
 block whose CSR arrays exceed `max_fragment_bytes` is assembled and downloaded in
 row ranges and streamed to the files fragment by fragment, so neither the device nor
-the host ever holds more than one fragment beyond the R^k tensor.
+the host ever holds more than one fragment beyond the R^k tensor.  With dipoles=True the
+dipole blocks follow (main_basis_setup.f90:125-152) into `D_-1.dat`, `D_0.dat`, `D_1.dat`.
 
-Not written here: the dipole blocks D_q.dat and the namelist copy basis_input.dat
-(SURVEY.md 8f rank 1 and the control plane)."""
+Not written here: the namelist copy basis_input.dat (control plane)."""
 from __future__ import annotations
 
 import os
 
 import numpy as np
 
-from . import BasisSetup
+from . import BasisSetup, setup_radial_dip
 from . import files as F
 from .sharding import balanced_ranges
 
 
-def run_basis_setup(out_dir, max_fragment_bytes=2 << 30, device=0, **params):
+def run_basis_setup(out_dir, max_fragment_bytes=2 << 30, device=0, dipoles=False, **params):
     os.makedirs(out_dir, exist_ok=True)
     setup = BasisSetup(device=device, **params)
     p = setup.p
@@ -67,6 +67,15 @@ def run_basis_setup(out_dir, max_fragment_bytes=2 << 30, device=0, **params):
         stats.append((s.l, s.pi, n, nnz, len(fH)))
     wH.close()
     wS.close()
+    if dipoles:                              # setup_radial_dip + construct_dip_block_tensor (:125-152)
+        A, B = setup_radial_dip(setup.k, setup.grid, p["k_GL"], p["gauge"])
+        ctx.set_radial_dipole(p["gauge"], A, B)
+        for q in (-1, 0, 1):
+            w = F.BlockMatrixWriter(os.path.join(out_dir, f"D_{q}.dat"), rows, rows)
+            for j, s2 in enumerate(syms):            # block_CS%store: block column outer
+                for i, s1 in enumerate(syms):
+                    w.write(ctx.construct_dip_block_tensor(s1, s2, q, compute=p["full"] or i <= j))
+            w.close()
     ctx.close()
     return stats
 

@@ -44,6 +44,40 @@ class BlockDiagWriter:
             _chk(lib().bs2e_file_close(h))
 
 
+class BlockMatrixWriter(BlockDiagWriter):
+    """block_CS%store (D_q.dat): write() the blocks in column-major order, block column outer"""
+
+    def __init__(self, path, block_rows, block_cols):
+        r = np.ascontiguousarray(block_rows, np.int64)
+        c = np.ascontiguousarray(block_cols, np.int64)
+        h = vp()
+        _chk(lib().bs2e_file_create_block_matrix(str(path).encode(), len(r), len(c), r, c, C.byref(h)))
+        self.h = h
+
+
+def read_block_matrix(path):
+    """CS_block_load order: returns (block_shape, shape, {(i, j): CSR}) with 0-based block indices"""
+    r = RecordReader(path)
+    try:
+        if bytes(r.next()).decode() != "CSR":
+            raise Bs2eError(f"{path}: blocks must be CSR")
+        bshape = r.next(np.int64)
+        shape = r.next(np.int64)
+        blocks = {}
+        for j in range(int(bshape[1])):
+            for i in range(int(bshape[0])):
+                sh = r.next(np.int64)
+                nnz = int(r.next(np.int64)[0])
+                if nnz > 0:
+                    ptr, idx, dat = r.next(np.int64), r.next(np.int64), r.next(np.complex128)
+                else:
+                    ptr, idx, dat = np.ones(int(sh[0]) + 1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.complex128)
+                blocks[(i, j)] = CSR((int(sh[0]), int(sh[1])), nnz, ptr, idx, dat)
+        return tuple(int(v) for v in bshape), tuple(int(v) for v in shape), blocks
+    finally:
+        r.close()
+
+
 def write_block_diag(path, blocks):
     w = BlockDiagWriter(path, [b.shape[0] for b in blocks])
     for b in blocks:

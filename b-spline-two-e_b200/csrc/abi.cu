@@ -584,6 +584,18 @@ int bs2e_file_create_block_diag(const char* path, int64_t n_blocks, const int64_
     });
 }
 
+int bs2e_file_create_block_matrix(const char* path, int64_t n_block_rows, int64_t n_block_cols,
+                                  const int64_t* block_rows, const int64_t* block_cols, bs2e_file** f)
+{
+    return guarded("bs2e_file_create_block_matrix", [&] {
+        if (!path || !f || n_block_rows < 1 || n_block_cols < 1 || !block_rows || !block_cols) throw Error("bad argument");
+        std::unique_ptr<bs2e_file> h(new bs2e_file());
+        h->w.reset(new files::Writer(path));
+        h->w->block_matrix_header(n_block_rows, n_block_cols, block_rows, block_cols);
+        *f = h.release();
+    });
+}
+
 int bs2e_file_write_block(bs2e_file* f, int64_t rows, int64_t cols, int64_t nnz, const int64_t* index_ptr,
                           const int64_t* indices, const double* data)
 {
@@ -710,6 +722,21 @@ int bs2e_host_setup_H_one_particle(int64_t k, int64_t n_knots, const double* kno
         host::setup_H_one_particle((int)k, t, (int)Z, (int)l, (int)CAP_order, CAP_r_0,
                                    std::complex<double>(CAP_eta_re, CAP_eta_im), (int)k_GL,
                                    reinterpret_cast<std::complex<double>*>(H));
+    });
+}
+
+int bs2e_host_setup_radial_dip(int64_t k, int64_t n_knots, const double* knots, int64_t k_GL, int64_t gauge,
+                               double* A, double* B)
+{
+    return guarded("bs2e_host_setup_radial_dip", [&] {
+        if (!knots || !A || (gauge == 'v' && !B)) throw Error("null argument");
+        std::vector<double> t(knots, knots + n_knots);
+        try {
+            host::setup_radial_dip((int)k, t, (int)k_GL, (int)gauge, reinterpret_cast<std::complex<double>*>(A),
+                                   reinterpret_cast<std::complex<double>*>(B));
+        } catch (const std::invalid_argument& e) {
+            throw Error(e.what());
+        }
     });
 }
 

@@ -110,6 +110,21 @@ void Writer::block_diag_header(long long n_blocks, const int64_t* block_rows)
     raw_record(shape, sizeof(shape));
     impl->blocks_expected = n_blocks;
 }
+// CS_block_store header (D_q.dat, block_tools.f90:386-396): 'CSR', block_shape(2), shape(2) with
+// shape = sums over the diagonal blocks (compute_shape_block_CS, :127-140); the blocks follow in
+// column-major order (j outer, i inner), each written like a block of the block-diagonal file
+void Writer::block_matrix_header(long long nbr, long long nbc, const int64_t* block_rows, const int64_t* block_cols)
+{
+    raw_record("CSR", 3);
+    const int64_t bshape[2] = {nbr, nbc};
+    int64_t r = 0, c = 0;
+    for (long long q = 0; q < nbr; ++q) r += block_rows[q];
+    for (long long q = 0; q < nbc; ++q) c += block_cols[q];
+    const int64_t shape[2] = {r, c};
+    raw_record(bshape, sizeof(bshape));
+    raw_record(shape, sizeof(shape));
+    impl->blocks_expected = nbr * nbc;
+}
 // one block: shape(2); nnz; if nnz > 0: index_ptr; indices; data   (block_tools.f90:472-481)
 void Writer::csr_block(long long rows, long long cols, long long nnz, const int64_t* index_ptr,
                        const int64_t* indices, const double* data)

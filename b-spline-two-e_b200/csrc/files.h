@@ -18,6 +18,7 @@ public:
     Writer& operator=(const Writer&) = delete;
     void raw_record(const void* p, size_t n);
     void block_diag_header(long long n_blocks, const int64_t* block_rows);
+    void block_matrix_header(long long nbr, long long nbc, const int64_t* block_rows, const int64_t* block_cols);
     void csr_block(long long rows, long long cols, long long nnz, const int64_t* index_ptr,
                    const int64_t* indices, const double* data);
     void csr_block_fragments(long long rows, long long cols, int nfrag, const long long* frag_rows,

@@ -150,6 +150,40 @@ void setup_S(int ks, const std::vector<double>& t, int k_GL, std::complex<double
     }
 }
 
+// mat_els.f90:120-170 setup_radial_dip with :348-390: gauge 'l': A = r_mat = int B_i r B_j;
+// gauge 'v': A = dr_mat = -i int B_i B_j', B = r_inv_mat = -i int B_i B_j / r
+void setup_radial_dip(int ks, const std::vector<double>& t, int k_GL, int gauge, std::complex<double>* A,
+                      std::complex<double>* Bm)
+{
+    if (gauge != 'l' && gauge != 'v') throw std::invalid_argument("setup_radial_dip: gauge must be 'l' or 'v'");
+    const int n = (int)t.size() - ks, nb = n - 2, cells = n - ks + 1;
+    for (long long q = 0; q < (long long)nb * nb; ++q) A[q] = 0.0;
+    if (gauge == 'v') for (long long q = 0; q < (long long)nb * nb; ++q) Bm[q] = 0.0;
+    std::vector<double> x(k_GL), w(k_GL);
+    double B[kMaxOrder], D1[kMaxOrder];
+    const std::complex<double> mi(0.0, -1.0);
+    for (int v = 1; v <= cells; ++v) {
+        gauss_legendre(k_GL, t[ks - 1 + v - 1], t[ks - 1 + v], x.data(), w.data());
+        for (int q = 0; q < k_GL; ++q) {
+            const double r = x[q];
+            bspline_values(t.data(), ks, v, r, B);
+            if (gauge == 'v') spline_derivs(t, ks, v, r, 1, D1);
+            for (int s2 = 0; s2 < ks; ++s2)
+                for (int s = 0; s < ks; ++s) {
+                    const int i = v + s - 1, j = v + s2 - 1;
+                    if (i < 1 || i > nb || j < 1 || j > nb) continue;
+                    const size_t at = (size_t)(i - 1) + (size_t)nb * (j - 1);
+                    if (gauge == 'l') {
+                        A[at] += w[q] * r * B[s] * B[s2];
+                    } else {
+                        A[at] += mi * (w[q] * B[s] * D1[s2]);
+                        Bm[at] += mi * (w[q] * B[s] * B[s2] / r);
+                    }
+                }
+        }
+    }
+}
+
 // mat_els.f90:47-83,294-327; V(r,l) = l(l+1)/(2 r^2) - Z/r; CAP = -i eta (r-r0)^order
 void setup_H_one_particle(int ks, const std::vector<double>& t, int Z, int l, int CAP_order,
                           double CAP_r_0, std::complex<double> CAP_eta, int k_GL,

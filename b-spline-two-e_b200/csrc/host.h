@@ -16,6 +16,8 @@ void setup_S(int ks, const std::vector<double>& knots, int k_GL, std::complex<do
 void setup_H_one_particle(int ks, const std::vector<double>& knots, int Z, int l, int CAP_order,
                           double CAP_r_0, std::complex<double> CAP_eta, int k_GL,
                           std::complex<double>* H);
+void setup_radial_dip(int ks, const std::vector<double>& knots, int k_GL, int gauge, std::complex<double>* A,
+                      std::complex<double>* B);
 void count_configs(int L, bool pi, int max_l_1p, int n_b, int k_spline, int max_n_b, int n_all_l,
                    int l_2_max, std::vector<int64_t>& conf_n, std::vector<int64_t>& conf_l,
                    std::vector<int64_t>& conf_eqv);

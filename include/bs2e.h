@@ -178,6 +178,11 @@ int bs2e_dip_block_fill(bs2e_ctx *ctx, int64_t q, const int64_t *sym1, int64_t n
 typedef struct bs2e_file bs2e_file;
 int bs2e_file_create_block_diag(const char *path, int64_t n_blocks,
                                 const int64_t *block_rows, bs2e_file **f);
+/* D_q.dat: block_CS%store (src/tools/block_tools.f90:386-415); the blocks are then written
+ * with bs2e_file_write_block in column-major order (block column outer, block row inner) */
+int bs2e_file_create_block_matrix(const char *path, int64_t n_block_rows, int64_t n_block_cols,
+                                  const int64_t *block_rows, const int64_t *block_cols,
+                                  bs2e_file **f);
 int bs2e_file_write_block(bs2e_file *f, int64_t rows, int64_t cols, int64_t nnz,
                           const int64_t *index_ptr, const int64_t *indices,
                           const double *data);
@@ -224,6 +229,9 @@ int bs2e_host_setup_S(int64_t k, int64_t n_knots, const double *knots, int64_t k
 int bs2e_host_setup_H_one_particle(int64_t k, int64_t n_knots, const double *knots,
                                    int64_t Z, int64_t l, int64_t CAP_order, double CAP_r_0,
                                    double CAP_eta_re, double CAP_eta_im, int64_t k_GL, double *H);
+/* mat_els.f90:120-170 setup_radial_dip: gauge 'l' (108): A = r_mat; 'v' (118): A = dr_mat, B = r_inv_mat */
+int bs2e_host_setup_radial_dip(int64_t k, int64_t n_knots, const double *knots, int64_t k_GL,
+                               int64_t gauge, double *A, double *B);
 /* orbital_tools.f90:245-343 init_basis (two_el): symmetry list, then
  * count_configs (:119-216) per symmetry.                                    */
 int64_t bs2e_host_basis_syms(int64_t max_L, int64_t z_pol, int64_t *sym_l,

@@ -168,3 +168,37 @@ def test_gpu_dipole_reference_grid_and_errors():
     assert_csr_equal(G, D, what="D_0 1S^e -> 1P^o")
     assert ctx.construct_dip_block_tensor(s0, s0, 0).nnz == 0    # same parity: forbidden
     ctx.close()
+
+
+def test_host_radial_dipole_companion_matches_oracle():
+    """csrc/host.cpp setup_radial_dip (tabulated splines) vs the oracle's de Boor restatement"""
+    import bs2e
+    run = O.OracleRun(**DIP_CASES["zpol_k5"])
+    for gauge in ("l", "v"):
+        rd = O.setup_radial_dip(run.bs, run.p["k_GL"], gauge)
+        A, B = bs2e.setup_radial_dip(run.p["k"], run.grid, run.p["k_GL"], gauge)
+        assert np.abs(A - rd.A).max() <= 1e-13 * np.abs(rd.A).max()
+        if gauge == "v":
+            assert np.abs(B - rd.B).max() <= 1e-13 * np.abs(rd.B).max()
+        else:
+            assert B is None
+
+
+@pytest.mark.gpu
+def test_gpu_driver_writes_dipole_files(tmp_path):
+    from bs2e import driver, files as F
+    p = dict(DIP_CASES["zpol_k5"], gauge="l")
+    driver.run_basis_setup(str(tmp_path), dipoles=True, **p)
+    run = O.OracleRun(**DIP_CASES["zpol_k5"])
+    run.one_particle(); run.basis()
+    rd = O.setup_radial_dip(run.bs, run.p["k_GL"], "l")
+    n = [s.n_config for s in run.syms]
+    for q in (-1, 0, 1):
+        bshape, shape, blocks = F.read_block_matrix(tmp_path / f"D_{q}.dat")
+        assert bshape == (len(n), len(n)) and shape == (sum(n), sum(n))
+        for (i, j), G in blocks.items():
+            D = O.construct_dip_block_tensor(run.bs, rd, run.S, run.syms[i], run.syms[j], q,
+                                             compute=run.p["full"] or i <= j)
+            assert G.nnz == D.nnz
+            if D.nnz:
+                assert_csr_equal(G, D, scale_tol=5e-12, what=f"D_{q}.dat block ({i},{j})")
