@@ -113,6 +113,36 @@ module bs2e_gpu_c
             complex(c_double_complex), intent(out) :: H_dat(*), S_dat(*)
             integer(c_int) :: rc
         end function bs2e_block_fill
+        function bs2e_set_radial_dipole(ctx, gauge, A, B) bind(C, name="bs2e_set_radial_dipole") result(rc)
+            import :: c_ptr, c_int, c_int64_t, c_double_complex
+            type(c_ptr), value :: ctx
+            integer(c_int64_t), value :: gauge
+            complex(c_double_complex), intent(in) :: A(*)
+            type(c_ptr), value :: B                       ! r_inv_mat or c_null_ptr (length gauge)
+            integer(c_int) :: rc
+        end function bs2e_set_radial_dipole
+
+        function bs2e_dip_block_count(ctx, q, sym1, n_config1, conf_n1, conf_l1, sym2, n_config2, conf_n2, &
+                                      conf_l2, compute, nnz) bind(C, name="bs2e_dip_block_count") result(rc)
+            import :: c_ptr, c_int, c_int64_t
+            type(c_ptr), value :: ctx
+            integer(c_int64_t), value :: q, n_config1, n_config2, compute
+            integer(c_int64_t), intent(in) :: sym1(3), sym2(3), conf_n1(*), conf_l1(*), conf_n2(*), conf_l2(*)
+            integer(c_int64_t), intent(out) :: nnz
+            integer(c_int) :: rc
+        end function bs2e_dip_block_count
+
+        function bs2e_dip_block_fill(ctx, q, sym1, n_config1, conf_n1, conf_l1, sym2, n_config2, conf_n2, &
+                                     conf_l2, compute, index_ptr, indices, data) &
+                                     bind(C, name="bs2e_dip_block_fill") result(rc)
+            import :: c_ptr, c_int, c_int64_t, c_double_complex
+            type(c_ptr), value :: ctx
+            integer(c_int64_t), value :: q, n_config1, n_config2, compute
+            integer(c_int64_t), intent(in) :: sym1(3), sym2(3), conf_n1(*), conf_l1(*), conf_n2(*), conf_l2(*)
+            integer(c_int64_t), intent(out) :: index_ptr(*), indices(*)
+            complex(c_double_complex), intent(out) :: data(*)
+            integer(c_int) :: rc
+        end function bs2e_dip_block_fill
     end interface
 
 contains
@@ -152,12 +182,14 @@ module bs2e_gpu
     implicit none
     private
     public :: setup_Slater_integrals, compute_R_k_map, construct_block_tensor, bs2e_gpu_finalize
+    public :: construct_dip_block_tensor
 
     ! device-resident basis + R^k tensor; the Nd_DOK object of the caller stays
     ! an empty shell (nothing outside these three routines reads it,
     ! src/apps/main_basis_setup.f90:120)
     type(c_ptr), save :: ctx = c_null_ptr
     logical, save :: one_particle_set = .false.
+    logical, save :: radial_dip_set = .false.
 
 contains
 
@@ -271,6 +303,63 @@ contains
         write(6,*) "Time to construct H_block (s): ", t_2 - t_1
         !$omp end critical(bs2e_gpu_block)
     end subroutine construct_block_tensor
+
+    ! stands in for dipole::construct_dip_block_tensor (src/mat_els/dipole.f90:8-47), same
+    ! dummies (type(radial_dipole) comes from mat_els).  Called from inside "!$omp parallel
+    ! do" (main_basis_setup.f90:131-148): one critical section.  The overlap matrix is the
+    ! one construct_block_tensor already sent (one_particle_set).
+    subroutine construct_dip_block_tensor(syms, q, b_splines, S, radial_dip, dip_block, compute)
+        use mat_els, only: radial_dipole
+        type(sym), dimension(2), intent(in) :: syms
+        integer, intent(in) :: q
+        type(b_spline), intent(in) :: b_splines
+        double complex, dimension(:,:), intent(in) :: S
+        type(radial_dipole), intent(in) :: radial_dip
+        type(CSR_matrix), intent(out) :: dip_block
+        logical, intent(in) :: compute
+
+        integer(c_int64_t), allocatable :: cn1(:,:), cl1(:,:), cn2(:,:), cl2(:,:)
+        complex(c_double_complex), allocatable, target :: A(:,:), B(:,:)
+        integer(c_int64_t) :: s1(3), s2(3), nnz, c_compute
+        integer :: i
+
+        allocate(cn1(2,syms(1)%n_config), cl1(2,syms(1)%n_config), cn2(2,syms(2)%n_config), cl2(2,syms(2)%n_config))
+        do i = 1, syms(1)%n_config
+            cn1(:,i) = int(syms(1)%configs(i)%n, c_int64_t)
+            cl1(:,i) = int(syms(1)%configs(i)%l, c_int64_t)
+        end do
+        do i = 1, syms(2)%n_config
+            cn2(:,i) = int(syms(2)%configs(i)%n, c_int64_t)
+            cl2(:,i) = int(syms(2)%configs(i)%l, c_int64_t)
+        end do
+        s1 = [int(syms(1)%l, c_int64_t), int(syms(1)%m, c_int64_t), merge(1_c_int64_t, 0_c_int64_t, syms(1)%pi)]
+        s2 = [int(syms(2)%l, c_int64_t), int(syms(2)%m, c_int64_t), merge(1_c_int64_t, 0_c_int64_t, syms(2)%pi)]
+        c_compute = merge(1_c_int64_t, 0_c_int64_t, compute)
+
+        !$omp critical(bs2e_gpu_block)
+        if (.not. radial_dip_set) then
+            if (radial_dip%gauge == 'l') then
+                A = radial_dip%r_mat
+                call bs2e_check(bs2e_set_radial_dipole(ctx, int(iachar('l'), c_int64_t), A, c_null_ptr), "set_radial_dipole")
+            else
+                A = radial_dip%dr_mat
+                B = radial_dip%r_inv_mat
+                call bs2e_check(bs2e_set_radial_dipole(ctx, int(iachar('v'), c_int64_t), A, c_loc(B)), "set_radial_dipole")
+            end if
+            radial_dip_set = .true.
+        end if
+        call bs2e_check(bs2e_dip_block_count(ctx, int(q, c_int64_t), s1, int(syms(1)%n_config, c_int64_t), cn1, cl1, &
+                                             s2, int(syms(2)%n_config, c_int64_t), cn2, cl2, c_compute, nnz), &
+                        "dip_block_count")
+        call dip_block%init([syms(1)%n_config, syms(2)%n_config], int(nnz))
+        if (nnz > 0) then
+            call bs2e_check(bs2e_dip_block_fill(ctx, int(q, c_int64_t), s1, int(syms(1)%n_config, c_int64_t), cn1, cl1, &
+                                                s2, int(syms(2)%n_config, c_int64_t), cn2, cl2, c_compute, &
+                                                dip_block%index_ptr, dip_block%indices, dip_block%data), &
+                            "dip_block_fill")
+        end if
+        !$omp end critical(bs2e_gpu_block)
+    end subroutine construct_dip_block_tensor
 
     subroutine bs2e_gpu_finalize()
         if (c_associated(ctx)) call bs2e_check(bs2e_ctx_destroy(ctx), "ctx_destroy")
