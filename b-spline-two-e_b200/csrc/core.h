@@ -446,10 +446,6 @@ BS2E_HD Cplx band_H(const Geom& g, const OneBody& ob, int l, int n, int np)
 
 struct Element { Cplx H, S; bool storeS; };
 
-// ---- element formulas -------------------------------------------------------
-//   mat_els.f90:552-571 r_12_tens, :608-633 c_mat_neq_tens,
-//   :664-678 S_mat_neq, :697-715 H_1p_neq; hamiltonian.f90:183-193
-
 // k ranges of a pair in packed form: direct terms k = dlo + 2i, i < nkd; exchange likewise
 struct PairK { int dlo, nkd, xlo, nkx; };
 BS2E_HD PairK pair_k(KRange kr)
@@ -462,33 +458,9 @@ BS2E_HD PairK pair_k(KRange kr)
     return p;
 }
 
-// sum_i rp[i*stride] * wa[i] in ascending order (the k sum of r_12_tens, mat_els.f90:566-570)
-template <int NK>
-BS2E_HD double k_dot_n(const double* rp, int stride, const double* wa)
-{
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < NK; ++i) acc += rp[i * stride] * wa[i];
-    return acc;
-}
-BS2E_HD double k_dot(const double* rp, int stride, const double* wa, int nk)
-{
-    switch (nk) {  // nk is uniform over a (row, column block) pair
-    case 0: return 0.0;
-    case 1: return k_dot_n<1>(rp, stride, wa);
-    case 2: return k_dot_n<2>(rp, stride, wa);
-    case 3: return k_dot_n<3>(rp, stride, wa);
-    case 4: return k_dot_n<4>(rp, stride, wa);
-    case 5: return k_dot_n<5>(rp, stride, wa);
-    case 6: return k_dot_n<6>(rp, stride, wa);
-    case 7: return k_dot_n<7>(rp, stride, wa);
-    case 8: return k_dot_n<8>(rp, stride, wa);
-    default: break;
-    }
-    double acc = k_dot_n<8>(rp, stride, wa);
-    for (int i = 8; i < nk; ++i) acc += rp[i * stride] * wa[i];
-    return acc;
-}
+// ---- element formulas -------------------------------------------------------
+//   mat_els.f90:552-571 r_12_tens, :608-633 c_mat_neq_tens,
+//   :664-678 S_mat_neq, :697-715 H_1p_neq; hamiltonian.f90:183-193
 
 // one-body and overlap part of an entry whose column block equals the row block
 // (H_1p_neq, S_mat_neq); lc, ld = l values of the column block (= those of the row)
@@ -516,40 +488,7 @@ BS2E_HD void one_body_terms(const Geom& g, const Plan& pl, const OneBody& ob, co
     *sout = s;
 }
 
-// value of the (i,j) entry, j = (bj, nc, nd).
-// Rd[i*sd], i < pk.nkd : R^k(n_a n_b; n_c n_d) for k = pk.dlo + 2i;
-// Rx[i*sx], i < pk.nkx : R^k(n_a n_b; n_d n_c), read through the electron-exchange
-// symmetry R^k(ab;dc) = R^k(ba;cd); wa_d / wa_x: the matching angular factors of the
-// (bi,bj) pair (exchange already multiplied by (-1)^(lc+ld+L)).  The pointers may refer
-// to global memory (row kernel) or to the staged site window in shared memory.
-BS2E_HD Element element_value_at(const Geom& g, const Plan& pl, const OneBody& ob,
-                                 const double* Rd, int sd, const double* Rx, int sx,
-                                 const double* wa_d, const double* wa_x, PairK pk,
-                                 const RowInfo& r, const Coupling& c, int bj, int nc, int nd,
-                                 bool sup, bool sup_ex)
-{
-    Element e;
-    e.H = Cplx{0.0, 0.0};
-    e.S = Cplx{0.0, 0.0};
-    const bool allowed = (sup && c.dirany) || (sup_ex && c.exany);
-    if (allowed) {
-        double res = 0.0;
-        if (sup) res += k_dot(Rd, sd, wa_d, pk.nkd);
-        if (sup_ex) res += k_dot(Rx, sx, wa_x, pk.nkx);
-        e.H.re = res;
-    }
-    e.storeS = (sup && c.same) || (sup_ex && c.samex);
-    if (e.storeS) {
-        const BlockDesc bc = pl.blk[bj];
-        Cplx h, s;
-        one_body_terms(g, pl, ob, r, c.same, c.samex, bc.l1, bc.l2, nc, nd, &h, &s);
-        e.H = cadd(e.H, h);
-        e.S = s;
-    }
-    return e;
-}
-
-// the same with R^k gathered from the global tensor R[k][p1][p2] (row kernel); the
+// value of the (i,j) entry, j = (bj, nc, nd), with R^k gathered from the global tensor R[k][p1][p2] (row kernel); the
 // stride between consecutive terms of one parity is two planes
 BS2E_HD Element element_value(const Geom& g, const Plan& pl, const OneBody& ob,
                               const double* R, const RowInfo& r, const Coupling& c,
