@@ -140,7 +140,9 @@ __host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G
     b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                      // T
     b += sizeof(RowRec) * (size_t)nblk * G;                             // rlist
     b += sizeof(RowCache) * (size_t)G;                                  // rcache
-    if (cfsm) b += sizeof(double) * (size_t)G * nblk * (wx ? 2 : 1) * nkp;  // cfs (direct half only without X)
+    // cfs: packed factors (direct half only without X) of all pairs of the group, or, when those do
+    // not fit, of the rows of one column block at a time
+    b += sizeof(double) * (size_t)G * (cfsm ? nblk : 1) * (wx ? 2 : 1) * nkp;
     b += sizeof(uchar4) * (size_t)((nblk + 3) & ~3);                    // gcnt
     b += sizeof(unsigned) * (size_t)((G * nblk + 3) & ~3);              // pm
     b += sizeof(int) * ((ncmax + 1 + 3) & ~3);                          // cprefix
@@ -195,8 +197,8 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     RowRec* rlist = reinterpret_cast<RowRec*>(T + (size_t)nblk * ncmax);
     RowCache* rcache = reinterpret_cast<RowCache*>(rlist + (size_t)nblk * G);
     double* cfs = reinterpret_cast<double*>(rcache + G);
-    constexpr int CFS = CFSM ? (WX ? 2 * NKP : NKP) : 2 * NKP;  // doubles per pair where the factors are read
-    uchar4* gcnt = reinterpret_cast<uchar4*>(cfs + (CFSM ? (size_t)G * nblk * CFS : 0));
+    constexpr int CFS = WX ? 2 * NKP : NKP;  // staged doubles per pair (direct half only without X)
+    uchar4* gcnt = reinterpret_cast<uchar4*>(cfs + (size_t)G * (CFSM ? nblk : 1) * CFS);
     unsigned* pm = reinterpret_cast<unsigned*>(gcnt + ((nblk + 3) & ~3));
     int* cprefix = reinterpret_cast<int*>(pm + ((G * nblk + 3) & ~3));
     unsigned short* hp = reinterpret_cast<unsigned short*>(cprefix + ((ncmax + 1 + 3) & ~3));
@@ -347,18 +349,30 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
         }
         __syncthreads();
         // ---- phase 4: fill ----
-        const double* const cfbase = CFSM ? cfs : pl.angP;
         const int nc_all = site_num_cand(s, cprefix, wantX);
         for (int t0 = 0; t0 < nc_all; t0 += NT) {
             const int t = t0 + tid;
             const bool act = t < nc_all;
             if (!(prefetched && t0 == 0)) load_cand(t, act);
-            if (__ballot_sync(0xffffffffu, act) == 0u) continue;  // warp without candidates
+            const bool warp_has_cand = __ballot_sync(0xffffffffu, act) != 0u;
+            if (CFSM && !warp_has_cand) continue;  // (with per-block staging every warp must reach the barriers)
             for (int bj = 0; bj < nblk; ++bj) {
                 const uchar4 gc = gcnt[bj];
                 if ((gc.x | gc.y | gc.z | gc.w) == 0) continue;
-                const SiteEntry e = T[bj * ncmax + c.q];
                 const RowRec* rl = rlist + bj * G;
+                if (!CFSM) {  // stage the packed factors of the rows of this column block (list order)
+                    const int nlist = gc.x + gc.y + gc.z + gc.w;
+                    __syncthreads();   // the previous tile has been consumed
+                    for (int idx = tid; idx < nlist * (CFS / 2); idx += NT) {
+                        const int row = idx / (CFS / 2), l = idx - row * (CFS / 2);
+                        const double2* src = reinterpret_cast<const double2*>(pl.angP + (size_t)rl[row].cf * (2 * NKP));
+                        reinterpret_cast<double2*>(cfs)[idx] = __ldg(src + l);
+                    }
+                    __syncthreads();
+                    if (!warp_has_cand) continue;
+                }
+                const SiteEntry e = T[bj * ncmax + c.q];
+                const RowRec* const rl0 = rl;
 #pragma unroll
                 for (int mode = 0; mode < kModes; ++mode) {
                     if (!WX && (mode == kModeX || mode == kModeDX)) continue;  // no such pairs without exchange windows
@@ -377,18 +391,18 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                         for (int i = 0; i < nrow; ++i) {
                             const RowRec rec = rm[i];
                             const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
-                            const double* cf = cfbase + (size_t)rec.cf * CFS;
+                            const double* cf = cfs + (size_t)(CFSM ? rec.cf : (int)(rm - rl0) + i) * CFS;
                             double res = 0.0;
                             if (mode != kModeX) {
                                 double cD[NKP];
-                                load_coefs<NKP, CFSM>(cf, cD);
+                                load_coefs<NKP, true>(cf, cD);
                                 const double d = site_dot_par<KMAX>(cD, Rd, pd);
                                 res += ms.sup ? d : 0.0;
                             }
                             if constexpr (WX) {
                                 if (mode != kModeD) {
                                     double cX[NKP];
-                                    load_coefs<NKP, CFSM>(cf + NKP, cX);
+                                    load_coefs<NKP, true>(cf + NKP, cX);
                                     const double x = site_dot_par<KMAX>(cX, Rx, px);
                                     res += ms.sup_ex ? x : 0.0;
                                 }
@@ -403,15 +417,15 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                         const RowRec rec = rm[0];
                         const RowCache rc = rcache[rec.meta >> 8];
                         const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
-                        const double* cf = cfbase + (size_t)rec.cf * CFS;
+                        const double* cf = cfs + (size_t)(CFSM ? rec.cf : (int)(rm - rl0)) * CFS;
                         double cD[NKP];
-                        load_coefs<NKP, CFSM>(cf, cD);
+                        load_coefs<NKP, true>(cf, cD);
                         const double d = site_dot_par<KMAX>(cD, Rd, pd);
                         double res = 0.0;
                         res += ms.sup ? d : 0.0;
                         if constexpr (WX) {
                             double cX[NKP];
-                            load_coefs<NKP, CFSM>(cf + NKP, cX);
+                            load_coefs<NKP, true>(cf + NKP, cX);
                             const double x = site_dot_par<KMAX>(cX, Rx, px);
                             res += ms.sup_ex ? x : 0.0;
                         }
@@ -665,6 +679,8 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
         lay.ncmax = site_max_nc(g);
         lay.G = std::min(32, nblk);   // a site has at most one row per (l1,l2) block
         lay.cfsm = sizeof(double) * (size_t)lay.G * nblk * 2 * nkp <= kSiteCoefSmem;
+        const char* cmode = getenv("BS2E_SITE_COEFS");   // "block": force the per-column-block staging (tests)
+        if (cmode && strcmp(cmode, "block") == 0) lay.cfsm = 0;
         lay.nl = c->lmax_1p + 1;
         lay.bytes = site_smem_bytes(g, nblk, lay.G, nkp, lay.cfsm != 0, lay.nl, true);
         if (lay.bytes > kSiteSmemLimit) use_site = false;

@@ -396,3 +396,18 @@ def test_driver_writes_result_files_streamed_and_whole(tmp_path):
         H, S, _ = run.block(s)
         assert_csr_equal(Hg, H, scale_tol=5e-12, what=f"file H L={s.l}")
         assert_csr_equal(Sg, S, scale_tol=5e-12, what=f"file S L={s.l}")
+
+
+def test_per_block_factor_staging_is_bit_identical(case, monkeypatch):
+    """large bases stage the packed angular factors one column block at a time (they do not fit
+    shared memory for the whole site): same results as the whole-site staging"""
+    run, ctx = case
+    syms = [s for s in run.syms if s.n_config > 0]
+    ref = []
+    for s in syms:
+        b = ctx.block_plan(s, False); b.assemble(); ref.append(b.download()); b.free()
+    monkeypatch.setenv("BS2E_SITE_COEFS", "block")
+    for s, (H0, S0) in zip(syms, ref):
+        b = ctx.block_plan(s, False); b.assemble(); H, S = b.download(); b.free()
+        assert np.array_equal(H.indices, H0.indices) and np.array_equal(H.data, H0.data)
+        assert np.array_equal(S.indices, S0.indices) and np.array_equal(S.data, S0.data)
