@@ -58,7 +58,7 @@ def exchange_cost(max_k):
     without (the fill kernel keeps the R^k values of both windows in registers there:
     128 / 168 / 248 registers per thread for <= 13 / 21 / 31 multipoles)."""
     k1 = max_k + 1
-    return 1.4 if k1 <= 13 else 2.0 if k1 <= 21 else 2.7
+    return 1.4 if k1 <= 13 else 2.0 if k1 <= 21 else 2.3
 
 
 def site_partition(conf_n, weights, parts, k_spline=None, x_cost=1.0):
