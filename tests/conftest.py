@@ -25,6 +25,13 @@ SMALL_CASES = {
                      full=False, z_pol=False),
     "wide_k6": dict(k=6, m=3, Z=2, h_max=0.8, r_max=10.0, k_GL=12, max_k=5, max_L=3, max_l_1p=3,
                     max_l2=3, r_2_max=6.0, CAP_eta=1e-3 + 0j, CAP_r_0=7.0, full=False, z_pol=True),
+    # spline order above the BASELINE configs: more than 32 n_c slots per site and more than 256
+    # candidate columns (several candidate passes, chunked warp scans)
+    "order10": dict(k=10, m=2, Z=1, h_max=1.0, r_max=9.0, k_GL=13, max_k=2, max_L=1, max_l_1p=1, max_l2=1,
+                    CAP_eta=1e-3 + 0j, CAP_r_0=6.0, full=False, z_pol=True),
+    # s waves only, one multipole: the smallest angular structure (one (l1,l2) group, one symmetry)
+    "swave_k0": dict(k=5, m=2, Z=2, h_max=1.0, r_max=7.0, k_GL=8, max_k=0, max_L=0, max_l_1p=0, max_l2=0,
+                     CAP_eta=0j, CAP_r_0=5.0, full=False, z_pol=True),
     # many multipoles on a tiny basis: the 21- and 31-register instantiations of the site kernel
     # (max_k of BASELINE configs 4 and 5), with k_GL >= k + max_k/2 so that the inner rule is exact
     "multipoles20_k5": dict(k=5, m=2, Z=1, h_max=1.0, r_max=6.0, k_GL=15, max_k=20, max_L=2, max_l_1p=3,
