@@ -9,7 +9,11 @@ Metric: 2e matrix elements/s = sum_sym (nnz_H+nnz_S)
 divided by the time of stage C (count pass + CSR build + fill); the R^k
 integrals/s of stages A+B is reported beside it ("rk_integrals_per_s").
 
-  value : inputs resident in HBM, device time (CUDA events on the library's stream)
+  value : inputs resident in HBM, device time (CUDA events on the library's stream);
+          stage C goes through bs2e_blocks_run (count pass + scan + fill of every block,
+          consecutive blocks pipelined over internal streams)
+  roofline : the fill of each block alone on the stream, timed in extra passes after the
+          timed steps; algorithmic bytes = 24 B per stored element
   e2e   : the same metric through the C ABI with HOST buffers
           (bs2e_set_one_particle / bs2e_block_count / bs2e_block_fill with
           pinned host arrays; H2D and D2H inside the timed region)
