@@ -50,6 +50,9 @@ ABI = {
     "bs2e_block_fill": (C.c_int, [vp, i64, i64, _pi, _pi, i64, vp, vp, vp, vp, vp, vp]),
     "bs2e_block_plan": (C.c_int, [vp, i64, i64, _pi, _pi, i64, i64, i64, C.POINTER(vp)]),
     "bs2e_block_plan_ranges": (C.c_int, [vp, i64, i64, _pi, _pi, i64, i64, _pi, _pi, C.POINTER(vp)]),
+    "bs2e_configs_upload": (C.c_int, [vp, i64, _pi, _pi, C.POINTER(vp)]),
+    "bs2e_configs_free": (C.c_int, [vp]),
+    "bs2e_block_plan_dev": (C.c_int, [vp, i64, vp, i64, i64, vp, vp, C.POINTER(vp)]),
     "bs2e_block_nnz": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "bs2e_block_row_counts": (C.c_int, [vp, vp, vp]),
     "bs2e_block_recount": (C.c_int, [vp]),
@@ -244,8 +247,8 @@ class Block:
 
     def __init__(self, ctx, handle, n_config, ranges):
         self.ctx, self.h = ctx, handle
-        self.n_config, self.ranges = n_config, [(int(a), int(b)) for a, b in ranges]
-        self.row_lo, self.row_hi = self.ranges[0][0], self.ranges[-1][1]
+        self.n_config, self.ranges = n_config, [(int(a), int(b)) for a, b in ranges if b >= a]
+        self.row_lo, self.row_hi = (self.ranges[0][0], self.ranges[-1][1]) if self.ranges else (1, 0)
         a, b = i64(), i64()
         _chk(lib().bs2e_block_nnz(self.h, C.byref(a), C.byref(b)))
         self.nnz_H, self.nnz_S = int(a.value), int(b.value)
@@ -284,6 +287,24 @@ class Block:
     def free(self):
         if self.h:
             lib().bs2e_block_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceConfigs:
+    """handle of a configuration list resident on the device"""
+
+    def __init__(self, handle, sym):
+        self.h, self.sym = handle, sym
+
+    def free(self):
+        if self.h:
+            lib().bs2e_configs_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -431,11 +452,29 @@ class Context:
         arr = (vp * len(blocks))(*[b.h for b in blocks])
         _chk(lib().bs2e_blocks_run(self.h, len(blocks), arr, int(bool(recount))))
 
-    def block_plan(self, sym, full, rows=None, ranges=None) -> Block:
-        """rows=(lo,hi): one row range; ranges=[(lo,hi),...]: a union of ascending row ranges
-        (the multi-GPU partition, bs2e.sharding.site_partition)."""
+    def configs_upload(self, sym) -> "DeviceConfigs":
+        """term%configs of a symmetry kept resident on the device (bs2e_configs_upload)"""
         cn, cl = self._conf(sym)
         h = vp()
+        _chk(lib().bs2e_configs_upload(self.h, sym.n_config, cn, cl, C.byref(h)))
+        return DeviceConfigs(h, sym)
+
+    def block_plan(self, sym, full, rows=None, ranges=None, cfg=None) -> Block:
+        """rows=(lo,hi): one row range; ranges=[(lo,hi),...]: a union of ascending row ranges
+        (the multi-GPU partition, bs2e.sharding.site_partition); cfg: the symmetry's
+        configuration list already on the device (configs_upload)."""
+        h = vp()
+        if cfg is not None:
+            if rows is not None:
+                ranges = [rows]
+            if ranges is None:
+                ranges = [(1, sym.n_config)] if sym.n_config > 0 else []
+            lo = np.ascontiguousarray([r[0] for r in ranges], np.int64)
+            hi = np.ascontiguousarray([r[1] for r in ranges], np.int64)
+            _chk(lib().bs2e_block_plan_dev(self.h, sym.l, cfg.h, int(bool(full)), len(lo), _ptr(lo), _ptr(hi),
+                                           C.byref(h)))
+            return Block(self, h, sym.n_config, list(zip(lo.tolist(), hi.tolist())))
+        cn, cl = self._conf(sym)
         if ranges is not None:
             lo = np.ascontiguousarray([r[0] for r in ranges], np.int64)
             hi = np.ascontiguousarray([r[1] for r in ranges], np.int64)

@@ -40,10 +40,43 @@ static int guarded(const char* where, F&& f)
 }
 
 static void use_device(const bs2e_ctx* c) { BS2E_CUDA(cudaSetDevice(c->device)); }
+void purge_parked(bs2e_ctx* c);
 
 }  // namespace bs2e
 
 using namespace bs2e;
+
+// count_nnz / construct_block_tensor shaped calls.  The plan made by the count
+// call is parked so that the fill call that follows (hamiltonian.f90:137-139:
+// count, allocate, fill) does not repeat the count pass.
+namespace {
+struct ParkKey {
+    bs2e_ctx* c; int64_t L, n, full; uint64_t h;
+    bool operator<(const ParkKey& o) const
+    {
+        return std::tie(c, L, n, full, h) < std::tie(o.c, o.L, o.n, o.full, o.h);
+    }
+};
+std::mutex g_park_mu;
+std::map<ParkKey, bs2e_block*> g_parked;
+
+}  // namespace
+
+namespace bs2e {
+void purge_parked(bs2e_ctx* c)
+{
+    std::vector<bs2e_block*> dead;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        for (auto it = g_parked.begin(); it != g_parked.end();) {
+            if (it->first.c == c) { dead.push_back(it->second); it = g_parked.erase(it); }
+            else ++it;
+        }
+    }
+    for (bs2e_block* b : dead) block_free(b);
+}
+}  // namespace bs2e
+
 
 extern "C" {
 
@@ -118,6 +151,9 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         if (!c) return;
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
+        purge_parked(c);          // plans parked by bs2e_block_count that no fill call collected
+        stager_destroy(c);
+        ctx_release_plan_state(c);
         cudaFree(c->d_t); cudaFree(c->d_bp); cudaFree(c->d_glx); cudaFree(c->d_glw);
         cudaFree(c->d_rowoff); cudaFree(c->d_pair);
         cudaFree(c->d_mom_rk); cudaFree(c->d_mom_rmk); cudaFree(c->d_pre); cudaFree(c->d_sufx);
@@ -319,7 +355,7 @@ int bs2e_block_plan(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
     return guarded("bs2e_block_plan", [&] {
         if (!c || !conf_n || !conf_l || !blk) throw Error("null argument");
         use_device(c);
-        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &row_lo, &row_hi);
+        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, nullptr, full != 0, 1, &row_lo, &row_hi);
     });
 }
 
@@ -330,7 +366,39 @@ int bs2e_block_plan_ranges(bs2e_ctx* c, int64_t L, int64_t n_config, const int64
     return guarded("bs2e_block_plan_ranges", [&] {
         if (!c || !conf_n || !conf_l || !blk || !range_lo || !range_hi) throw Error("null argument");
         use_device(c);
-        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, n_ranges, range_lo, range_hi);
+        *blk = block_plan(c, (int)L, n_config, conf_n, conf_l, nullptr, full != 0, n_ranges, range_lo, range_hi);
+    });
+}
+
+int bs2e_configs_upload(bs2e_ctx* c, int64_t n_config, const int64_t* conf_n, const int64_t* conf_l,
+                        bs2e_configs** cfg)
+{
+    return guarded("bs2e_configs_upload", [&] {
+        if (!c || !cfg || (n_config > 0 && (!conf_n || !conf_l))) throw Error("null argument");
+        use_device(c);
+        *cfg = configs_upload(c, n_config, conf_n, conf_l);
+    });
+}
+
+int bs2e_configs_free(bs2e_configs* cfg)
+{
+    return guarded("bs2e_configs_free", [&] {
+        if (!cfg) return;
+        cudaSetDevice(cfg->ctx->device);
+        cudaStreamSynchronize(cfg->ctx->stream);
+        configs_free(cfg);
+    });
+}
+
+int bs2e_block_plan_dev(bs2e_ctx* c, int64_t L, bs2e_configs* cfg, int64_t full, int64_t n_ranges,
+                        const int64_t* range_lo, const int64_t* range_hi, bs2e_block** blk)
+{
+    return guarded("bs2e_block_plan_dev", [&] {
+        if (!c || !cfg || !blk) throw Error("null argument");
+        use_device(c);
+        const int64_t one = 1, all = cfg->n;
+        if (n_ranges <= 0 || !range_lo || !range_hi) { n_ranges = 1; range_lo = &one; range_hi = &all; }
+        *blk = block_plan(c, (int)L, cfg->n, nullptr, nullptr, cfg, full != 0, n_ranges, range_lo, range_hi);
     });
 }
 
@@ -408,20 +476,7 @@ int bs2e_block_free(bs2e_block* b)
     });
 }
 
-// count_nnz / construct_block_tensor shaped calls.  The plan made by the count
-// call is parked so that the fill call that follows (hamiltonian.f90:137-139:
-// count, allocate, fill) does not repeat the count pass.
 namespace {
-struct ParkKey {
-    bs2e_ctx* c; int64_t L, n, full; uint64_t h;
-    bool operator<(const ParkKey& o) const
-    {
-        return std::tie(c, L, n, full, h) < std::tie(o.c, o.L, o.n, o.full, o.h);
-    }
-};
-std::mutex g_park_mu;
-std::map<ParkKey, bs2e_block*> g_parked;
-
 uint64_t conf_hash(int64_t n, const int64_t* a, const int64_t* b)
 {
     uint64_t h = 1469598103934665603ull;
@@ -437,12 +492,12 @@ int bs2e_block_count(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* co
                      const int64_t* conf_l, int64_t full, int64_t* nnz_H, int64_t* nnz_S)
 {
     return guarded("bs2e_block_count", [&] {
-        if (!c || !conf_n || !conf_l) throw Error("null argument");
+        if (!c || (n_config > 0 && (!conf_n || !conf_l))) throw Error("null argument");
         use_device(c);
         const int64_t one = 1;
         const bool trace = getenv("BS2E_TRACE") != nullptr;
         const auto tc0 = std::chrono::steady_clock::now();
-        bs2e_block* b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &one, &n_config);
+        bs2e_block* b = block_plan(c, (int)L, n_config, conf_n, conf_l, nullptr, full != 0, 1, &one, &n_config);
         if (trace)
             fprintf(stderr, "bs2e_block_count L=%lld: %.2f ms\n", (long long)L,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
@@ -465,7 +520,7 @@ int bs2e_block_fill(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
                     double* H_dat, int64_t* S_ptr, int64_t* S_idx, double* S_dat)
 {
     return guarded("bs2e_block_fill", [&] {
-        if (!c || !conf_n || !conf_l) throw Error("null argument");
+        if (!c || (n_config > 0 && (!conf_n || !conf_l))) throw Error("null argument");
         use_device(c);
         const ParkKey key{c, L, n_config, full != 0, conf_hash(n_config, conf_n, conf_l)};
         bs2e_block* b = nullptr;
@@ -478,7 +533,7 @@ int bs2e_block_fill(bs2e_ctx* c, int64_t L, int64_t n_config, const int64_t* con
         const bool trace = getenv("BS2E_TRACE") != nullptr;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();
-        if (!b) b = block_plan(c, (int)L, n_config, conf_n, conf_l, full != 0, 1, &one, &n_config);
+        if (!b) b = block_plan(c, (int)L, n_config, conf_n, conf_l, nullptr, full != 0, 1, &one, &n_config);
         double t1 = 0, t2 = 0, t3 = 0;
         try {
             t1 = now();

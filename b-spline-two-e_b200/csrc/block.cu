@@ -6,24 +6,22 @@
 // src/mat_els/mat_els.f90:552-571,608-633,664-715.  The reference scans all
 // n_config^2 configuration pairs twice and evaluates 3j/6j symbols for every
 // pair; here
-//   * the angular factors are tabulated once per pair of (l1,l2) blocks on
-//     the host (exact arithmetic, wigner.cpp) and uploaded,
-//   * the band partners of a row are GENERATED from the block structure of
-//     the configuration list (no pair scan): site_count_kernel counts them
-//     in closed form per radial site, an exclusive scan builds index_ptr, and
-//     site_fill_kernel (one CTA per radial site, one thread per candidate
-//     column) writes indices and values; block_count_kernel / block_fill_kernel
-//     (one thread / one warp per row) remain as the general fallback.
-// Bound: HBM (24 B written per stored element + R^k gathers).
+//   * the angular factors are tabulated once per pair of (l1,l2) groups on
+//     the host (exact arithmetic, wigner.cpp) and kept on the device,
+//   * the group structure, the radial sites and the row counts are built on
+//     the device (plan_dev.cu),
+//   * the band partners of a row are GENERATED from that structure (no pair
+//     scan): site_count_kernel counts them in closed form per radial site, an
+//     exclusive scan builds index_ptr, and site_fill_kernel (one CTA per
+//     radial site, one thread per candidate column) writes indices and
+//     values; block_count_kernel / block_fill_kernel (one thread / one warp
+//     per row) remain as the general fallback.
+// Bound: HBM (24 B written per stored element + R^k read once per site).
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <mutex>
-#include <set>
-#include <unordered_map>
 
 #include "ctx.h"
 #include "plan.h"
@@ -32,7 +30,8 @@
 namespace bs2e {
 
 // ---------------------------------------------------------------------------
-// kernels
+// row-wise fallback kernels (max_k beyond the site kernel's instantiations, or
+// tables that do not fit shared memory); they need the per-row tables of the plan
 // ---------------------------------------------------------------------------
 __global__ void block_count_kernel(Geom g, Plan pl, long long nrows,
                                    long long* __restrict__ cntH, long long* __restrict__ cntS)
@@ -40,7 +39,7 @@ __global__ void block_count_kernel(Geom g, Plan pl, long long nrows,
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx > nrows) return;
     long long h = 0, s = 0;
-    if (idx < nrows) row_count(g, pl, pl.rows[idx], &h, &s);
+    if (idx < nrows) row_count(g, pl, row_of_local(pl.rr, (int)idx), &h, &s);
     cntH[idx] = h;  // slot nrows holds 0 so that the scan yields the total
     cntS[idx] = s;
 }
@@ -58,7 +57,7 @@ block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R,
     if (wrow >= nrows) return;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const RowInfo r = row_info(pl, pl.rows[wrow]);
+    const RowInfo r = row_info(pl, row_of_local(pl.rr, (int)wrow));
     long long hpos = Hptr[wrow] - 1, spos = Sptr[wrow] - 1;
 
     for_each_chunk(g, pl, r, [&](int bj, int nc, const Segment& s, const Coupling& c, int base, int hi) {
@@ -88,26 +87,32 @@ block_fill_kernel(Geom g, Plan pl, OneBody ob, const double* __restrict__ R,
 // ---------------------------------------------------------------------------
 // site-centric fill: one CTA per radial site (n_a,n_b), see site_core.h.
 // All rows (l_a,l_b; n_a,n_b) of the site read the same R^k values; only the
-// angular factors and the clipping by the column block differ.
-//   phase 1  per column block bj and n_c slot: clipped windows T[bj][q]
+// angular factors and the clipping by the column group differ.
+//   phase 0  the rows of the site, derived from the group tables (one row per
+//            (l1,l2) group that holds the configuration (n_a,n_b))
+//   phase 1  per column group bj and n_c slot: clipped windows T[bj][q]
 //   phase 2  per (bj, storage mode): prefix over the n_c slots of the number of
 //            stored entries, hp[bj][mode][q] (mode: D, X, D+X, diagonal pair)
-//   phase 3  per row of the site: storage mode, k parity and offset inside the
-//            row of each of its column blocks (pm); per (bj, mode) the bit mask
-//            of the rows that store that list (gmask)
-//   phase 4  THREAD t OWNS CANDIDATE COLUMN t of the site: it loads the R^k
-//            values of the column for all multipoles into registers once (both
-//            windows) and then walks the column blocks; per (bj, mode) it works
-//            out once whether / where the column is stored, then for every row
-//            of the mask sum_k ang_k R^k with the packed factors read as
-//            broadcast loads -- per stored element ~K1/2 FP64 FMAs, K1/4 loads,
-//            two stores.  R^k is read from HBM exactly once per site.
+//   phase 3  per row of the site: storage mode, multipole parity and offset
+//            inside the row of each of its column groups; the (row, column
+//            group) pairs are filed as 16-byte records by (parity, mode) and
+//            cut into CHUNKS whose packed angular factors fit one staging buffer
+//   phase 4  THREAD t OWNS CANDIDATE COLUMN t of the site.  The multipoles of a
+//            pair have one parity (wigner_tools.f90:131), so the work is done in
+//            two parity passes: the thread loads the R^k values of its column
+//            for that parity (both windows) into registers and walks the records
+//            of that parity; per (bj, mode) it works out once whether / where
+//            the column is stored, then per record sum_k ang_k R^k with the
+//            factors read as broadcast loads from the staged chunk -- two
+//            records at a time so that their FP64 chains overlap.
+//   The factor chunks are moved by the bulk-copy engine (cp.async.bulk +
+//   mbarrier, one copy per record) into a double buffer, the next chunk while
+//   the current one is consumed; a site whose records fit two chunks runs
+//   phase 4 without any block-wide barrier.  R^k is read once per site.
 // ---------------------------------------------------------------------------
 struct SiteList {
-    const unsigned* key;  // [nsites]  n_a << 16 | n_b
-    const int* ptr;       // [nsites+1] into rows
-    const int* rows;      // 1-based configuration (row) indices, ascending per site
-    int nsites;
+    const unsigned long long* key;  // sorted site keys (plan.h: site_sort_key): n_a << 16 | n_b in the low word
+    const int* count;               // [0] number of sites, [1] those with exchange windows
 };
 
 struct alignas(16) RowCache {  // per row of the group
@@ -115,10 +120,14 @@ struct alignas(16) RowCache {  // per row of the group
     int bi, la, lb, pad;
 };
 
-struct alignas(16) RowRec {    // one (row, column block) pair of the group, filed under (bj, mode)
+struct alignas(16) RowRec {    // one (row, column group) pair of the group, filed under (bj, parity, mode)
     long long hpos;            // 0-based position of the pair's first H entry
     int cf;                    // index of the pair's packed factors (units of 2*NKP doubles)
-    int meta;                  // pd | px << 1 | ri << 8
+    int meta;                  // ri << 8 | kDirAny / kExAny of the pair
+};
+
+struct alignas(8) SiteChunk {  // consecutive column groups of one parity whose records share a staging buffer
+    short par, bj0, bj1, nrec;
 };
 
 constexpr int kSiteThreads = 128;   // sites with exchange windows
@@ -127,28 +136,33 @@ constexpr int kSiteThreadsD = 256;  // sites without: one pass over the <= (2w+1
 struct SiteSmem {   // element counts of the dynamic shared memory carve-up
     int ncmax;      // n_c slots
     int G;          // rows per group (<= 32)
-    int cfsm;       // packed factors of the group's pairs staged in shared memory
+    int chrec;      // records per staging buffer
     int nl;         // l_max + 1 of the one-particle matrices
     size_t bytes;
 };
 
-__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G, int nkp, bool cfsm, int nl, bool wx)
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G, int nkp, int chrec, int nl, bool wx)
 {
     const size_t ncmax = (size_t)site_max_nc(g);
+    const size_t cfs = (size_t)(wx ? 2 : 1) * nkp;
     size_t b = 0;
-    b += sizeof(double) * (size_t)site_1p_doubles(g, nl);               // band rows of H_l and S
-    b += sizeof(SiteEntry) * (size_t)nblk * ncmax;                      // T
-    b += sizeof(RowRec) * (size_t)nblk * G;                             // rlist
-    b += sizeof(RowCache) * (size_t)G;                                  // rcache
-    // cfs: packed factors (direct half only without X) of all pairs of the group, or, when those do
-    // not fit, of the rows of one column block at a time
-    b += sizeof(double) * (size_t)G * (cfsm ? nblk : 1) * (wx ? 2 : 1) * nkp;
-    b += sizeof(uchar4) * (size_t)((nblk + 3) & ~3);                    // gcnt
-    b += sizeof(unsigned) * (size_t)((G * nblk + 3) & ~3);              // pm
-    b += sizeof(int) * ((ncmax + 1 + 3) & ~3);                          // cprefix
-    b += sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1);  // hp
-    b += sizeof(unsigned short) * (size_t)nblk * (ncmax + 1);           // sp
-    return b + 16;
+    b += align16(sizeof(double) * 2 * (size_t)chrec * cfs);                      // two staging buffers
+    b += align16(sizeof(double) * (size_t)site_1p_doubles(g, nl));               // band rows of H_l and S
+    b += align16(sizeof(SiteEntry) * (size_t)nblk * ncmax);                      // T
+    b += align16(sizeof(RowRec) * (size_t)nblk * G);                             // rlist
+    b += align16(sizeof(RowCache) * (size_t)G);                                  // rcache
+    b += align16(sizeof(SiteChunk) * (size_t)(2 * nblk + 2));                    // chunk table
+    b += align16(sizeof(uchar4) * 2 * (size_t)nblk);                             // gcnt[2][nblk]
+    b += align16(sizeof(unsigned) * (size_t)G * nblk);                           // pm
+    b += align16(sizeof(int) * (ncmax + 1));                                     // cprefix
+    b += align16(sizeof(int) * 2 * (size_t)nblk);                                // srow_bi, srow_local
+    b += align16(sizeof(unsigned short) * 2 * (size_t)nblk);                     // cfoff[2][nblk]
+    b += align16(sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1));  // hp
+    b += align16(sizeof(unsigned short) * (size_t)nblk * (ncmax + 1));           // sp
+    b += 64;                                                                     // mbarriers, counters
+    return b;
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
@@ -161,88 +175,165 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
-constexpr size_t kSiteSmemLimit = 160 * 1024;
-constexpr size_t kSiteCoefSmem = 48 * 1024;  // stage the packed factors when they fit this
-
-// the packed factors of one (row block, column block) pair and window: NKP doubles
-template <int NKP, bool SM>
-__device__ __forceinline__ void load_coefs(const double* __restrict__ cf, double* out)
+// ---- mbarrier + bulk copy (TMA engine, linear form) ------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
-#pragma unroll
-    for (int i = 0; i < NKP; i += 2) {
-        const double2 v = SM ? *reinterpret_cast<const double2*>(cf + i)
-                             : __ldg(reinterpret_cast<const double2*>(cf + i));
-        out[i] = v.x;
-        out[i + 1] = v.y;
-    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr size_t kSiteSmemLimit = 200 * 1024;
+
+// sum over the NKH multipoles of one parity, ascending k (mat_els.f90:566-570); cf in shared memory
+template <int NKH>
+__device__ __forceinline__ double site_dot(const double* __restrict__ cf, const double (&R)[NKH])
+{
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NKH; i += 2) {
+        const double2 c = *reinterpret_cast<const double2*>(cf + i);
+        acc += c.x * R[i];
+        if (i + 1 < NKH) acc += c.y * R[i + 1];
+    }
+    return acc;
+}
+
+template <int KMAX, bool WX>
+struct SiteLaunch {   // threads per CTA and CTAs per SM of an instantiation
+    static constexpr int NT = WX ? kSiteThreads : kSiteThreadsD;
+    static constexpr int per_sm = WX ? (KMAX <= 13 ? 768 : KMAX <= 21 ? 512 : 384) : (KMAX <= 13 ? 768 : 512);
+    static constexpr int min_blocks = per_sm / NT;
+};
 
 // WX: the sites of this launch have exchange windows (site_wants_X); the sites that
 // have none run a leaner instantiation (no exchange registers, half the n_c slots).
-template <int NT, int KMAX, bool CFSM, bool WX>
-__global__ void __launch_bounds__(NT, (WX ? (KMAX <= 13 ? 512 : KMAX <= 21 ? 384 : 256) : (KMAX <= 13 ? 768 : 512)) / NT)
+template <int KMAX, bool WX>
+__global__ void __launch_bounds__(SiteLaunch<KMAX, WX>::NT, SiteLaunch<KMAX, WX>::min_blocks)
 site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int site_off, const double* __restrict__ R,
                  const long long* __restrict__ Hptr,
                  const long long* __restrict__ Sptr, long long* __restrict__ Hidx,
                  double2* __restrict__ Hdat, long long* __restrict__ Sidx,
                  double2* __restrict__ Sdat)
 {
+    constexpr int NT = SiteLaunch<KMAX, WX>::NT;
     constexpr int NW = NT / 32;
-    constexpr int NKP = (((KMAX + 1) / 2) + 1) & ~1;  // = site_nkp(KMAX)
+    constexpr int NKP = (((KMAX + 1) / 2) + 1) & ~1;  // = site_nkp(KMAX): packed factors per window
+    constexpr int NKH = (KMAX + 1) / 2;               // multipoles of one parity
+    constexpr int CFS = WX ? 2 * NKP : NKP;           // staged doubles per record (direct half only without X)
     extern __shared__ __align__(16) unsigned char smraw[];
-    const int K1 = g.K1, ncmax = lay.ncmax, G = lay.G;
+    const int K1 = g.K1, ncmax = lay.ncmax, G = lay.G, chrec = lay.chrec;
     const int nblk = pl.nblk;
-    double* ob_s = reinterpret_cast<double*>(smraw);
-    SiteEntry* T = reinterpret_cast<SiteEntry*>(ob_s + site_1p_doubles(g, lay.nl));
-    RowRec* rlist = reinterpret_cast<RowRec*>(T + (size_t)nblk * ncmax);
-    RowCache* rcache = reinterpret_cast<RowCache*>(rlist + (size_t)nblk * G);
-    double* cfs = reinterpret_cast<double*>(rcache + G);
-    constexpr int CFS = WX ? 2 * NKP : NKP;  // staged doubles per pair (direct half only without X)
-    uchar4* gcnt = reinterpret_cast<uchar4*>(cfs + (size_t)G * (CFSM ? nblk : 1) * CFS);
-    unsigned* pm = reinterpret_cast<unsigned*>(gcnt + ((nblk + 3) & ~3));
-    int* cprefix = reinterpret_cast<int*>(pm + ((G * nblk + 3) & ~3));
-    unsigned short* hp = reinterpret_cast<unsigned short*>(cprefix + ((ncmax + 1 + 3) & ~3));
-    unsigned short* sp = hp + (size_t)nblk * kModes * (ncmax + 1);
+    unsigned char* sp_ = smraw;
+    auto carve = [&](size_t bytes) { unsigned char* p = sp_; sp_ += align16(bytes); return p; };
+    double* cfs = reinterpret_cast<double*>(carve(sizeof(double) * 2 * (size_t)chrec * CFS));
+    double* ob_s = reinterpret_cast<double*>(carve(sizeof(double) * (size_t)site_1p_doubles(g, lay.nl)));
+    SiteEntry* T = reinterpret_cast<SiteEntry*>(carve(sizeof(SiteEntry) * (size_t)nblk * ncmax));
+    RowRec* rlist = reinterpret_cast<RowRec*>(carve(sizeof(RowRec) * (size_t)nblk * G));
+    RowCache* rcache = reinterpret_cast<RowCache*>(carve(sizeof(RowCache) * (size_t)G));
+    SiteChunk* chunks = reinterpret_cast<SiteChunk*>(carve(sizeof(SiteChunk) * (size_t)(2 * nblk + 2)));
+    uchar4* gcnt = reinterpret_cast<uchar4*>(carve(sizeof(uchar4) * 2 * (size_t)nblk));
+    unsigned* pm = reinterpret_cast<unsigned*>(carve(sizeof(unsigned) * (size_t)G * nblk));
+    int* cprefix = reinterpret_cast<int*>(carve(sizeof(int) * (ncmax + 1)));
+    int* srow_bi = reinterpret_cast<int*>(carve(sizeof(int) * 2 * (size_t)nblk));
+    int* srow_local = srow_bi + nblk;
+    unsigned short* cfoff = reinterpret_cast<unsigned short*>(carve(sizeof(unsigned short) * 2 * (size_t)nblk));
+    unsigned short* hp = reinterpret_cast<unsigned short*>(carve(sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1)));
+    unsigned short* sp = reinterpret_cast<unsigned short*>(carve(sizeof(unsigned short) * (size_t)nblk * (ncmax + 1)));
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(carve(16));
+    int* misc = reinterpret_cast<int*>(carve(16));   // [0] rows of the site, [1] chunks of the group
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sidx = blockIdx.x + site_off;
-    const unsigned key = sl.key[sidx];
+    const unsigned key = (unsigned)(sl.key[sidx] & 0xffffffffull);
     const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), WX);
-    const int* srows = sl.rows + sl.ptr[sidx];
-    const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
     const int nnc = s.nnc;
     constexpr bool wantX = WX;
     const size_t plane = (size_t)g.P * g.ldP;
+    const int pi = (pl.blk[0].l1 + pl.blk[0].l2) & 1;   // parity of l1+l2, the same for every group of a symmetry
 
-    // The candidate column this thread owns and its R^k values (all multipoles, both
-    // windows), read once and streaming.  Without exchange windows the candidate list
-    // is known up front, so the loads of the first pass are issued here and complete
-    // behind phases 1-3.
+    // The candidate column this thread owns and its R^k values of one multipole parity
+    // (both windows), read once and streaming.  Direct terms of parity `par` pair with
+    // exchange terms of parity par ^ pi.
     OwnCand c;
-    double Rd[KMAX], Rx[WX ? KMAX : 1];
-    auto load_cand = [&](int t, bool act) {
-        c = site_own_cand(g, s, cprefix, wantX, act ? t : 0);
+    double Rd[NKH], Rx[WX ? NKH : 1];
+    auto load_R = [&](bool act, int par) {
         const double* pD = R + (size_t)c.rowD * g.ldP + c.colD;
         const double* pX = R + (size_t)c.rowX * g.ldP + c.colX;
         const bool onD = act && c.inD, onX = act && c.inX;
+        const int parx = par ^ pi;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            Rd[k] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
-            if constexpr (WX) Rx[k] = (onX && k < K1) ? __ldcs(pX + (size_t)k * plane) : 0.0;
+        for (int i = 0; i < NKH; ++i) {
+            const int k = 2 * i + par, kx = 2 * i + parx;
+            Rd[i] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
+            if constexpr (WX) Rx[i] = (onX && kx < K1) ? __ldcs(pX + (size_t)kx * plane) : 0.0;
         }
         if constexpr (!WX) Rx[0] = 0.0;
     };
-    const bool prefetched = !WX && s.nD <= NT && nr <= G;
-    if (prefetched) load_cand(tid, tid < s.nD);
+    // without exchange windows the candidate list is known up front: the loads of the
+    // first pass are issued here and complete behind phases 0-3
+    const bool prefetched = !WX && s.nD <= NT;
+    if (prefetched) {
+        c = site_own_cand(g, s, cprefix, false, tid < s.nD ? tid : 0);
+        load_R(tid < s.nD, 0);
+    }
 
-    // ---- phase 1: clipped windows per column block; slot prefix of the candidate list ----
+    // ---- phase 0: rows of the site; phase 1: clipped windows, candidate prefix, band rows ----
+    if (warp == 0) {
+        int run = 0;
+        for (int b0 = 0; b0 < nblk; b0 += 32) {
+            const int bi = b0 + lane;
+            int local = -1;
+            if (bi < nblk) {
+                const int row = config_index(g, pl, bi, s.na, s.nb);
+                if (row > 0) local = row_local_of(pl.rr, row);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, local >= 0);
+            if (local >= 0) {
+                const int pos = run + __popc(m & ((1u << lane) - 1u));
+                srow_bi[pos] = bi;
+                srow_local[pos] = local;
+            }
+            run += __popc(m);
+        }
+        if (lane == 0) misc[0] = run;
+    }
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (warp == NW - 1 && wantX) {
         int run = 0;
         for (int q0 = 0; q0 < nnc; q0 += 32) {
             const int q = q0 + lane;
-            const int c = q < nnc ? site_cand_DX_count(s, q) : 0;
-            const int inc = warp_incl_scan(c, lane);
-            if (q < nnc) cprefix[q] = run + inc - c;
+            const int cq = q < nnc ? site_cand_DX_count(s, q) : 0;
+            const int inc = warp_incl_scan(cq, lane);
+            if (q < nnc) cprefix[q] = run + inc - cq;
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (lane == 0) cprefix[nnc] = run;
@@ -255,6 +346,7 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     }
     const SiteOneBody so{ob_s, ob_s + (size_t)lay.nl * 2 * (2 * g.w + 1) * 2};
     __syncthreads();
+    const int nr = misc[0];
     // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode);
     //      one thread per (bj, mode), serial over the slots ----
     for (int task = tid; task < nblk * kModes; task += NT) {
@@ -281,176 +373,237 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
 
     double* const Hd = reinterpret_cast<double*>(Hdat);
     double* const Sd = reinterpret_cast<double*>(Sdat);
+    unsigned mphase = 0;          // phase parity of the two staging barriers (bit b)
+    int resident0 = -1, resident1 = -1;   // chunk held by each staging buffer (of the current group)
+    bool pending0 = false, pending1 = false;
 
     for (int g0 = 0; g0 < nr; g0 += G) {
         const int gr = imin(G, nr - g0);
         __syncthreads();  // phase 2 / previous group finished
-        // ---- phase 3a: coupled column blocks of each row and their offsets inside the row ----
+        // ---- phase 3a: coupled column groups of each row and their offsets inside the row ----
         for (int ri = warp; ri < gr; ri += NW) {
-            const int rowi = srows[g0 + ri];
-            const RowInfo r = row_info(pl, rowi);
+            const int bi = srow_bi[g0 + ri];
+            const BlockDesc bd = pl.blk[bi];
+            const RowInfo r{0, bi, s.na, s.nb, bd.l1, bd.l2};
             if (lane == 0) {
-                const long long wrow = pl.row_local[rowi - 1];
-                rcache[ri] = RowCache{Hptr[wrow] - 1, Sptr[wrow] - 1, r.bi, r.la, r.lb, 0};
+                const long long wrow = srow_local[g0 + ri];
+                rcache[ri] = RowCache{Hptr[wrow] - 1, Sptr[wrow] - 1, bi, bd.l1, bd.l2, 0};
             }
             int run = 0;
             for (int b0 = 0; b0 < nblk; b0 += 32) {
                 const int bj = b0 + lane;
-                int c = 0, mode = -1;
+                int cnt = 0, mode = -1;
                 if (bj < nblk) {
                     mode = pair_mode(pl, r, bj);
                     if (mode >= 0) {
                         const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
                         mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
-                        c = (wantX || mode != kModeX) ? hb[mode * (ncmax + 1)] : 0;
+                        cnt = (wantX || mode != kModeX) ? hb[mode * (ncmax + 1)] : 0;
                     }
                 }
-                const int inc = warp_incl_scan(c, lane);
+                const int inc = warp_incl_scan(cnt, lane);
                 if (bj < nblk)
-                    pm[ri * nblk + bj] = c > 0 ? pm_pack(run + inc - c, mode, (r.la + pl.blk[bj].l1) & 1) : 0u;
+                    pm[ri * nblk + bj] = cnt > 0 ? pm_pack(run + inc - cnt, mode, (r.la + pl.blk[bj].l1) & 1) : 0u;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
         __syncthreads();
-        // ---- phase 3b: the pairs of each column block, filed by storage mode ----
+        // ---- phase 3b: the pairs of each column group, filed by (parity, storage mode) ----
         for (int bj = tid; bj < nblk; bj += NT) {
-            int cnt[kModes] = {0, 0, 0, 0};
-            for (int ri = 0; ri < gr; ++ri) {
-                const unsigned v = pm[ri * nblk + bj];
-                if (pm_valid(v)) ++cnt[pm_mode(v)];
-            }
-            gcnt[bj] = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2],
-                                   (unsigned char)cnt[3]);
-            int pos[kModes] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+            int cnt[2 * kModes] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int ri = 0; ri < gr; ++ri) {
                 const unsigned v = pm[ri * nblk + bj];
                 if (!pm_valid(v)) continue;
-                const int mode = pm_mode(v);
-                int where = 0;  // pos[mode]++ without dynamic indexing of a register array
+                const int slot = pm_pd(v) * kModes + pm_mode(v);
 #pragma unroll
-                for (int q = 0; q < kModes; ++q)
-                    if (q == mode) where = pos[q]++;
-                const RowCache rc = rcache[ri];
-                const int px = pm_pd(v) ^ ((pl.blk[bj].l1 + pl.blk[bj].l2) & 1);
-                rlist[bj * G + where] = RowRec{rc.hbase + pm_off(v), CFSM ? ri * nblk + bj : rc.bi * nblk + bj,
-                                               pm_pd(v) | (px << 1) | (ri << 8)};
+                for (int q = 0; q < 2 * kModes; ++q)
+                    if (q == slot) ++cnt[q];
             }
-        }
-        if (CFSM) {  // packed factors of the group's pairs -> shared memory (16-byte units)
-            const int per = CFS / 2;  // double2 per pair
-            for (int idx = tid; idx < gr * nblk * per; idx += NT) {
-                const int pair = idx / per, l = idx - pair * per;
-                const int ri = pair / nblk, bj = pair - ri * nblk;
-                if (!pm_valid(pm[pair])) continue;
-                const double2* src = reinterpret_cast<const double2*>(
-                    pl.angP + ((size_t)rcache[ri].bi * nblk + bj) * (2 * NKP));
-                reinterpret_cast<double2*>(cfs)[(size_t)pair * per + l] = __ldg(src + l);
+            gcnt[bj] = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2], (unsigned char)cnt[3]);
+            gcnt[nblk + bj] = make_uchar4((unsigned char)cnt[4], (unsigned char)cnt[5], (unsigned char)cnt[6], (unsigned char)cnt[7]);
+            int pos[2 * kModes];
+            pos[0] = 0;
+#pragma unroll
+            for (int q = 1; q < 2 * kModes; ++q) pos[q] = pos[q - 1] + cnt[q - 1];
+            for (int ri = 0; ri < gr; ++ri) {
+                const unsigned v = pm[ri * nblk + bj];
+                if (!pm_valid(v)) continue;
+                const int slot = pm_pd(v) * kModes + pm_mode(v);
+                int where = 0;  // pos[slot]++ without dynamic indexing of a register array
+#pragma unroll
+                for (int q = 0; q < 2 * kModes; ++q)
+                    if (q == slot) where = pos[q]++;
+                const RowCache rc = rcache[ri];
+                const int fl = pl.flags[(size_t)rc.bi * nblk + bj] & (kDirAny | kExAny);
+                rlist[bj * G + where] = RowRec{rc.hbase + pm_off(v), rc.bi * nblk + bj, fl | (ri << 8)};
             }
         }
         __syncthreads();
+        // ---- phase 3c: chunks of consecutive column groups whose factors fit a staging buffer ----
+        if (tid == 0) {
+            int nch = 0;
+            for (int par = 0; par < 2; ++par) {
+                int cur = 0, bj0 = 0;
+                for (int bj = 0; bj < nblk; ++bj) {
+                    const uchar4 gc = gcnt[par * nblk + bj];
+                    const int n = gc.x + gc.y + gc.z + gc.w;
+                    if (cur + n > chrec) {
+                        chunks[nch++] = SiteChunk{(short)par, (short)bj0, (short)bj, (short)cur};
+                        cur = 0;
+                        bj0 = bj;
+                    }
+                    cfoff[par * nblk + bj] = (unsigned short)cur;
+                    cur += n;
+                }
+                if (cur > 0) chunks[nch++] = SiteChunk{(short)par, (short)bj0, (short)nblk, (short)cur};
+            }
+            misc[1] = nch;
+        }
+        __syncthreads();
+        const int nch = misc[1];
+        resident0 = resident1 = -1;   // the buffers hold chunks of the previous group
+        // chunk ch -> staging buffer bsel: one bulk copy per record, issued by all threads
+        auto stage = [&](int ch, int bsel) {
+            const SiteChunk cc = chunks[ch];
+            unsigned long long* bar = &mbar[bsel];
+            if (tid == 0) mbar_expect_tx(bar, (unsigned)cc.nrec * CFS * 8u);
+            double* dst = cfs + (size_t)bsel * chrec * CFS;
+            for (int bj = cc.bj0 + warp; bj < cc.bj1; bj += NW) {
+                const uchar4 g0c = gcnt[bj], gpc = gcnt[cc.par * nblk + bj];
+                const int first = cc.par ? g0c.x + g0c.y + g0c.z + g0c.w : 0;
+                const int n = gpc.x + gpc.y + gpc.z + gpc.w;
+                const int off = cfoff[cc.par * nblk + bj];
+                for (int i = lane; i < n; i += 32) {
+                    const RowRec rec = rlist[bj * G + first + i];
+                    bulk_g2s(dst + (size_t)(off + i) * CFS, pl.angP + (size_t)rec.cf * (2 * NKP), CFS * 8u, bar);
+                }
+            }
+            if (bsel) { resident1 = ch; pending1 = true; } else { resident0 = ch; pending0 = true; }
+        };
+        auto wait_buf = [&](int bsel) {
+            if (!(bsel ? pending1 : pending0)) return;
+            mbar_wait(&mbar[bsel], (mphase >> bsel) & 1u);
+            mphase ^= 1u << bsel;
+            if (bsel) pending1 = false; else pending0 = false;
+        };
+        int cur = 0;   // staging buffer of the chunk being consumed; the sequence of chunks alternates buffers
+        if (nch > 0) stage(0, 0);
         // ---- phase 4: fill ----
         const int nc_all = site_num_cand(s, cprefix, wantX);
-        for (int t0 = 0; t0 < nc_all; t0 += NT) {
-            const int t = t0 + tid;
+        const int npass = nch > 0 ? (nc_all + NT - 1) / NT : 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int t = pass * NT + tid;
             const bool act = t < nc_all;
-            if (!(prefetched && t0 == 0)) load_cand(t, act);
+            const bool keepR = prefetched && pass == 0 && g0 == 0;   // parity-0 values already in registers
+            if (!keepR) c = site_own_cand(g, s, cprefix, wantX, act ? t : 0);
             const bool warp_has_cand = __ballot_sync(0xffffffffu, act) != 0u;
-            if (CFSM && !warp_has_cand) continue;  // (with per-block staging every warp must reach the barriers)
-            for (int bj = 0; bj < nblk; ++bj) {
-                const uchar4 gc = gcnt[bj];
-                if ((gc.x | gc.y | gc.z | gc.w) == 0) continue;
-                const RowRec* rl = rlist + bj * G;
-                if (!CFSM) {  // stage the packed factors of the rows of this column block (list order)
-                    const int nlist = gc.x + gc.y + gc.z + gc.w;
-                    __syncthreads();   // the previous tile has been consumed
-                    for (int idx = tid; idx < nlist * (CFS / 2); idx += NT) {
-                        const int row = idx / (CFS / 2), l = idx - row * (CFS / 2);
-                        const double2* src = reinterpret_cast<const double2*>(pl.angP + (size_t)rl[row].cf * (2 * NKP));
-                        reinterpret_cast<double2*>(cfs)[idx] = __ldg(src + l);
-                    }
-                    __syncthreads();
-                    if (!warp_has_cand) continue;
+            int rpar = keepR ? 0 : -1;   // parity of the values in Rd / Rx
+            for (int ch = 0; ch < nch; ++ch) {
+                // next chunk of the cyclic sequence into the other buffer (all threads take the same branch)
+                const int nxt = ch + 1 < nch ? ch + 1 : (pass + 1 < npass ? 0 : -1);
+                const bool flip = nxt >= 0 && nxt != ch;
+                if (flip && ((cur ^ 1) ? resident1 : resident0) != nxt) {
+                    __syncthreads();   // every thread is done with the chunk that buffer held
+                    stage(nxt, cur ^ 1);
                 }
-                const SiteEntry e = T[bj * ncmax + c.q];
-                const RowRec* const rl0 = rl;
+                wait_buf(cur);
+                const double* cbuf = cfs + (size_t)cur * chrec * CFS;
+                if (flip) cur ^= 1;
+                if (!warp_has_cand) continue;
+                const SiteChunk cc = chunks[ch];
+                const int par = cc.par;
+                if (rpar != par) { load_R(act, par); rpar = par; }
+                for (int bj = cc.bj0; bj < cc.bj1; ++bj) {
+                    const uchar4 gc = gcnt[par * nblk + bj];
+                    if ((gc.x | gc.y | gc.z | gc.w) == 0) continue;
+                    const uchar4 g0c = gcnt[bj];
+                    const RowRec* rl = rlist + bj * G + (par ? g0c.x + g0c.y + g0c.z + g0c.w : 0);
+                    const double* cfm = cbuf + (size_t)cfoff[par * nblk + bj] * CFS;
+                    const SiteEntry e = T[bj * ncmax + c.q];
 #pragma unroll
-                for (int mode = 0; mode < kModes; ++mode) {
-                    if (!WX && (mode == kModeX || mode == kModeDX)) continue;  // no such pairs without exchange windows
-                    const int nrow = mode == 0 ? gc.x : mode == 1 ? gc.y : mode == 2 ? gc.z : gc.w;
-                    if (nrow == 0) continue;
-                    const RowRec* rm = rl;
-                    rl += nrow;
-                    const bool diag = mode == kModeDiag;
-                    const ModeSlot ms = site_mode_slot(s, c, e, hp + (bj * kModes + mode) * (ncmax + 1), mode,
-                                                       diag && !pl.full);
-                    const bool stored = act && (ms.sup || ms.sup_ex);
-                    if (__ballot_sync(0xffffffffu, stored) == 0u) continue;
-                    const long long jcol = ms.jcol;
-                    if (!diag) {
-#pragma unroll 2
-                        for (int i = 0; i < nrow; ++i) {
-                            const RowRec rec = rm[i];
-                            const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
-                            const double* cf = cfs + (size_t)(CFSM ? rec.cf : (int)(rm - rl0) + i) * CFS;
-                            double res = 0.0;
-                            if (mode != kModeX) {
-                                double cD[NKP];
-                                load_coefs<NKP, true>(cf, cD);
-                                const double d = site_dot_par<KMAX>(cD, Rd, pd);
-                                res += ms.sup ? d : 0.0;
-                            }
-                            if constexpr (WX) {
-                                if (mode != kModeD) {
-                                    double cX[NKP];
-                                    load_coefs<NKP, true>(cf + NKP, cX);
-                                    const double x = site_dot_par<KMAX>(cX, Rx, px);
-                                    res += ms.sup_ex ? x : 0.0;
+                    for (int mode = 0; mode < kModes; ++mode) {
+                        if (!WX && (mode == kModeX || mode == kModeDX)) continue;  // no such pairs without exchange windows
+                        const int nrow = mode == 0 ? gc.x : mode == 1 ? gc.y : mode == 2 ? gc.z : gc.w;
+                        if (nrow == 0) continue;
+                        const RowRec* rm = rl;
+                        const double* cf = cfm;
+                        rl += nrow;
+                        cfm += (size_t)nrow * CFS;
+                        const bool diag = mode == kModeDiag;
+                        const ModeSlot ms = site_mode_slot(s, c, e, hp + (bj * kModes + mode) * (ncmax + 1), mode,
+                                                           diag && !pl.full);
+                        const bool stored = act && (ms.sup || ms.sup_ex);
+                        if (__ballot_sync(0xffffffffu, stored) == 0u) continue;
+                        const long long jcol = ms.jcol;
+                        if (!diag) {
+                            // two records at a time: independent FP64 chains (an odd tail is computed twice, stored once)
+                            for (int i = 0; i < nrow; i += 2) {
+                                const bool two = i + 1 < nrow;
+                                const RowRec rec0 = rm[i], rec1 = rm[two ? i + 1 : i];
+                                const double* cf0 = cf + (size_t)i * CFS;
+                                const double* cf1 = cf0 + (two ? CFS : 0);
+                                double res0 = 0.0, res1 = 0.0;
+                                if (mode != kModeX) {
+                                    const double d0 = site_dot<NKH>(cf0, Rd), d1 = site_dot<NKH>(cf1, Rd);
+                                    res0 += ms.sup ? d0 : 0.0;
+                                    res1 += ms.sup ? d1 : 0.0;
+                                }
+                                if constexpr (WX) {
+                                    if (mode != kModeD) {
+                                        const double x0 = site_dot<NKH>(cf0 + NKP, Rx), x1 = site_dot<NKH>(cf1 + NKP, Rx);
+                                        res0 += ms.sup_ex ? x0 : 0.0;
+                                        res1 += ms.sup_ex ? x1 : 0.0;
+                                    }
+                                }
+                                if (stored) {
+                                    const long long p0 = rec0.hpos + ms.rank;
+                                    Hidx[p0] = jcol;
+                                    *reinterpret_cast<double2*>(Hd + 2 * p0) = make_double2(res0, 0.0);
+                                    if (two) {
+                                        const long long p1 = rec1.hpos + ms.rank;
+                                        Hidx[p1] = jcol;
+                                        *reinterpret_cast<double2*>(Hd + 2 * p1) = make_double2(res1, 0.0);
+                                    }
                                 }
                             }
+                        } else {  // exactly one row: the row whose own group is bj (parity 0)
+                            const RowRec rec = rm[0];
+                            const RowCache rc = rcache[rec.meta >> 8];
+                            const double d = site_dot<NKH>(cf, Rd);
+                            double res = 0.0;
+                            res += ms.sup ? d : 0.0;
+                            if constexpr (WX) {
+                                const double x = site_dot<NKH>(cf + NKP, Rx);
+                                res += ms.sup_ex ? x : 0.0;
+                            }
+                            // hamiltonian.f90:183: the r_12 sums enter only when a supported window has a factor above 5e-15
+                            const bool allowed = (ms.sup && (rec.meta & kDirAny)) || (ms.sup_ex && (rec.meta & kExAny));
+                            if (!allowed) res = 0.0;
                             if (stored) {
+                                double re = res, im = 0.0;
+                                site_diag_terms(g, pl, so, s, rc.la, rc.lb, c, ms, rc.la == rc.lb, sp + bj * (ncmax + 1),
+                                                rc.sbase, &re, &im, Sidx, Sd);
                                 const long long pos = rec.hpos + ms.rank;
                                 Hidx[pos] = jcol;
-                                *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(res, 0.0);
+                                *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(re, im);
                             }
-                        }
-                    } else {  // exactly one row: the row whose own block is bj
-                        const RowRec rec = rm[0];
-                        const RowCache rc = rcache[rec.meta >> 8];
-                        const int pd = rec.meta & 1, px = (rec.meta >> 1) & 1;
-                        const double* cf = cfs + (size_t)(CFSM ? rec.cf : (int)(rm - rl0)) * CFS;
-                        double cD[NKP];
-                        load_coefs<NKP, true>(cf, cD);
-                        const double d = site_dot_par<KMAX>(cD, Rd, pd);
-                        double res = 0.0;
-                        res += ms.sup ? d : 0.0;
-                        if constexpr (WX) {
-                            double cX[NKP];
-                            load_coefs<NKP, true>(cf + NKP, cX);
-                            const double x = site_dot_par<KMAX>(cX, Rx, px);
-                            res += ms.sup_ex ? x : 0.0;
-                        }
-                        if (stored) {
-                            double re = res, im = 0.0;
-                            site_diag_terms(g, pl, so, s, rc.la, rc.lb, c, ms, rc.la == rc.lb, sp + bj * (ncmax + 1),
-                                            rc.sbase, &re, &im, Sidx, Sd);
-                            const long long pos = rec.hpos + ms.rank;
-                            Hidx[pos] = jcol;
-                            *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(re, im);
                         }
                     }
                 }
             }
         }
+        // a staging copy that was issued must land before the buffers are reused or the CTA exits
+        wait_buf(0);
+        wait_buf(1);
     }
 }
 
 // Count pass on the site tables.  The row count of a row is the sum over its coupled
-// column blocks of the stored entries of the pair's storage mode, which depend on the
-// site and the column block only.  One WARP per site, no block-wide barrier: lane = column
-// block, one pass over the n_c slots gives the totals of all four storage modes; then
-// lane = column block again for each row of the site.  (block_count_kernel, one thread
+// column groups of the stored entries of the pair's storage mode, which depend on the
+// site and the column group only.  One WARP per site, no block-wide barrier: lane = column
+// group, one pass over the n_c slots gives the totals of all four storage modes; then
+// lane = column group again for each row of the site.  (block_count_kernel, one thread
 // per row, is kept for plans without a site list.)
-struct CountSmem { int stride; size_t bytes; };
 constexpr int kCountWarps = 4;
 
 __host__ __device__ inline size_t count_smem_bytes(int nblk)
@@ -465,15 +618,13 @@ site_count_kernel(Geom g, Plan pl, SiteList sl, long long* __restrict__ cntH, lo
     const int nblk = pl.nblk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned short* tot = reinterpret_cast<unsigned short*>(smraw) + (size_t)warp * (kModes + 1) * nblk;
-    unsigned short* stot = tot + (size_t)kModes * nblk;   // S entries of the diagonal pair of block bj
+    unsigned short* stot = tot + (size_t)kModes * nblk;   // S entries of the diagonal pair of group bj
     const int sidx = blockIdx.x * kCountWarps + warp;
     if (blockIdx.x == 0 && threadIdx.x == 0) { cntH[pl.nrows] = 0; cntS[pl.nrows] = 0; }  // the scan yields the totals there
-    if (sidx >= sl.nsites) return;
-    const unsigned key = sl.key[sidx];
+    if (sidx >= sl.count[0]) return;
+    const unsigned key = (unsigned)(sl.key[sidx] & 0xffffffffull);
     const bool wantX = site_wants_X(g, pl.max_nd, (int)(key >> 16));
     const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), wantX);
-    const int* srows = sl.rows + sl.ptr[sidx];
-    const int nr = sl.ptr[sidx + 1] - sl.ptr[sidx];
     const int nnc = s.nnc;
     for (int bj = lane; bj < nblk; bj += 32) {
         const bool samex = pl.blk[bj].l1 == pl.blk[bj].l2;
@@ -494,9 +645,13 @@ site_count_kernel(Geom g, Plan pl, SiteList sl, long long* __restrict__ cntH, lo
         stot[bj] = (unsigned short)cS;
     }
     __syncwarp();
-    for (int ri = 0; ri < nr; ++ri) {
-        const int rowi = srows[ri];
-        const RowInfo r = row_info(pl, rowi);
+    for (int bi = 0; bi < nblk; ++bi) {   // the rows of the site: one per group that holds (n_a, n_b)
+        const int rowi = config_index(g, pl, bi, s.na, s.nb);
+        if (rowi == 0) continue;
+        const int wrow = row_local_of(pl.rr, rowi);
+        if (wrow < 0) continue;
+        const BlockDesc bd = pl.blk[bi];
+        const RowInfo r{rowi, bi, s.na, s.nb, bd.l1, bd.l2};
         int run = 0, srun = 0;
         for (int bj = lane; bj < nblk; bj += 32) {
             int mode = pair_mode(pl, r, bj);
@@ -512,7 +667,6 @@ site_count_kernel(Geom g, Plan pl, SiteList sl, long long* __restrict__ cntH, lo
             srun += __shfl_xor_sync(0xffffffffu, srun, o);
         }
         if (lane == 0) {
-            const int wrow = pl.row_local[rowi - 1];
             cntH[wrow] = run;
             cntS[wrow] = srun;
         }
@@ -534,19 +688,67 @@ __global__ void checksum_kernel(long long n, const long long* __restrict__ idx,
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-// count pass + exclusive scan -> 1-based index_ptr of the planned rows
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+// staging-buffer size of the site kernel: large enough for the records of a typical
+// whole site, bounded so that the launch keeps its CTAs per SM (BS2E_SITE_CHUNK_KB overrides)
+int site_chunk_records(const Geom& g, int nblk, int G, int nkp, bool wx)
+{
+    size_t cap_kb = wx ? 24 : 32;
+    if (const char* e = getenv("BS2E_SITE_CHUNK_KB")) cap_kb = (size_t)std::max(1, atoi(e));
+    const size_t per = sizeof(double) * (wx ? 2 : 1) * nkp;
+    size_t rec = std::min((size_t)G * nblk, cap_kb * 1024 / per);
+    rec = std::max(rec, (size_t)G);   // a column group's records (<= G) must fit one buffer
+    return (int)rec;
+}
+
+SiteSmem site_layout(const bs2e_ctx* c, int nblk, bool wx)
+{
+    const Geom& g = c->hg;
+    SiteSmem lay{};
+    const int kmax = site_kmax_for(g.K1);
+    const int nkp = site_nkp(kmax);
+    lay.ncmax = site_max_nc(g);
+    lay.G = std::min(32, nblk);   // a site has at most one row per (l1,l2) group
+    lay.nl = c->lmax_1p + 1;
+    lay.chrec = site_chunk_records(g, nblk, lay.G, nkp, wx);
+    lay.bytes = site_smem_bytes(g, nblk, lay.G, nkp, lay.chrec, lay.nl > 0 ? lay.nl : 1, wx);
+    return lay;
+}
+}  // namespace
+
+// site kernels unless max_k exceeds their largest instantiation or their tables do
+// not fit shared memory; BS2E_FILL=row asks for the row kernels (A/B measurements)
+bool site_kernel_usable(const bs2e_ctx* c, int nblk, int lmax)
+{
+    const Geom& g = c->hg;
+    const char* mode = getenv("BS2E_FILL");
+    if (mode && strcmp(mode, "row") == 0) return false;
+    const int kmax = site_kmax_for(g.K1);
+    if (kmax <= 0) return false;
+    if (site_max_slots(g) > 65535 || (size_t)nblk * site_max_slots(g) >= (1u << 24)) return false;
+    if (nblk > 255) return false;   // per-group record counts are bytes
+    if (count_smem_bytes(nblk) > 48 * 1024) return false;
+    const int G = std::min(32, nblk), nkp = site_nkp(kmax);
+    const int nl = std::max(c->lmax_1p, lmax) + 1;   // band rows of H_l for every l of the one-particle input
+    return site_smem_bytes(g, nblk, G, nkp, site_chunk_records(g, nblk, G, nkp, true), nl, true) <= kSiteSmemLimit;
+}
+
 BlockStreams default_streams(bs2e_ctx* c) { return BlockStreams{c->stream, c->side, c->ev_fork, c->ev_join}; }
 
+// count pass + exclusive scan -> 1-based index_ptr of the planned rows
 void block_count_scan(bs2e_block* b, bool read_totals, const BlockStreams* bsp)
 {
     bs2e_ctx* c = b->ctx;
     cudaStream_t st = bsp ? bsp->main : c->stream;
     const long long nrows = b->nrows;
-    const char* cmode = getenv("BS2E_COUNT");
-    const size_t cbytes = count_smem_bytes(b->dplan.nblk);
-    if (b->nsites > 0 && cbytes <= 48 * 1024 && !(cmode && strcmp(cmode, "row") == 0)) {
-        const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
-        site_count_kernel<<<(unsigned)((b->nsites + kCountWarps - 1) / kCountWarps), kCountWarps * 32, cbytes, st>>>(
+    if (b->n_config == 0) return;
+    if (b->use_site) {
+        const SiteList sl{b->d_site_key, b->d_counters};
+        const size_t cbytes = count_smem_bytes(b->dplan.nblk);
+        site_count_kernel<<<(unsigned)((b->site_cap + kCountWarps - 1) / kCountWarps), kCountWarps * 32, cbytes, st>>>(
             c->dg, b->dplan, sl, b->d_cntH, b->d_cntS);
     } else {
         block_count_kernel<<<(unsigned)((nrows + 1 + 127) / 128), 128, 0, st>>>(
@@ -571,90 +773,25 @@ void block_count_scan(bs2e_block* b, bool read_totals, const BlockStreams* bsp)
     }
 }
 
-// ---------------------------------------------------------------------------
-// plan: derive the block structure from the configuration list, count, scan
-// ---------------------------------------------------------------------------
-bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
-                       const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
-                       const int64_t* range_hi)
+template <int KMAX, bool WX>
+static void launch_site_fill(bs2e_block* b, const SiteSmem& lay, cudaStream_t st, int first, int count)
 {
-    HostPlan hp;
-    try {
-        hp = build_host_plan(c->hg, L, n_config, conf_n, conf_l, full, n_ranges, range_lo, range_hi);
-    } catch (const std::invalid_argument& e) {
-        throw Error(e.what());
-    }
-    const int nblk = hp.nblk;
-    bs2e_block* b = new bs2e_block();
-    b->ctx = c;
-    b->L = L;
-    b->full = full ? 1 : 0;
-    b->n_config = n_config;
-    b->nrows = (long long)hp.rows.size();
-    b->lmax = hp.lmax;
-    try {
-        cudaStream_t st = c->stream;
-        b->d_blk = dev_upload(hp.blocks, st);
-        b->d_ncrow = dev_upload(hp.ncrow, st);
-        b->d_flags = dev_upload(hp.flags, st);
-        b->d_krange = dev_upload(hp.krange, st);
-        b->d_angD = dev_upload(hp.angD, st);
-        b->d_angX = dev_upload(hp.angX, st);
-        if (hp.nkp > 0) b->d_angP = dev_upload(hp.angP, st);
-        b->d_row_n1 = dev_upload(hp.row_n1, st);
-        b->d_row_n2 = dev_upload(hp.row_n2, st);
-        b->d_row_blk = dev_upload(hp.row_blk, st);
-        b->d_rows = dev_upload(hp.rows, st);
-        b->d_row_local = dev_upload(hp.row_local, st);
-        b->nsites = (int)hp.site_key.size();
-        b->nsites_x = hp.nsites_x;
-        if (b->nsites > 0) {
-            b->d_site_key = dev_upload(hp.site_key, st);
-            b->d_site_ptr = dev_upload(hp.site_ptr, st);
-            b->d_site_rows = dev_upload(hp.site_rows, st);
-        }
-        Plan& pl = b->dplan;
-        pl.nblk = nblk;
-        pl.n_config = (int)n_config;
-        pl.full = b->full;
-        pl.L = L;
-        pl.blk = b->d_blk;
-        pl.ncrow = b->d_ncrow;
-        pl.flags = b->d_flags;
-        pl.krange = b->d_krange;
-        pl.angD = b->d_angD;
-        pl.angX = b->d_angX;
-        pl.angP = b->d_angP;
-        pl.nkp = hp.nkp;
-        pl.row_n1 = b->d_row_n1;
-        pl.row_n2 = b->d_row_n2;
-        pl.row_blk = b->d_row_blk;
-        pl.nrows = (int)hp.rows.size();
-        pl.rows = b->d_rows;
-        pl.row_local = b->d_row_local;
-        pl.max_nd = hp.max_nd;
-
-        const long long nrows = b->nrows;
-        b->d_cntH = dev_alloc<long long>(nrows + 1);
-        b->d_cntS = dev_alloc<long long>(nrows + 1);
-        b->d_Hptr = dev_alloc<long long>(nrows + 1);
-        b->d_Sptr = dev_alloc<long long>(nrows + 1);
-        size_t tmp = 0;
-        BS2E_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp, b->d_cntH, b->d_Hptr, cub::Sum(), 1LL, nrows + 1, st));
-        b->scan_tmp_bytes = tmp;
-        BS2E_CUDA(cudaMalloc(&b->d_scan_tmp, tmp ? tmp : 1));
-        block_count_scan(b, true);
-    } catch (...) {
-        block_free(b);
-        throw;
-    }
-    return b;
+    if (count <= 0) return;
+    bs2e_ctx* c = b->ctx;
+    auto kern = site_fill_kernel<KMAX, WX>;
+    const SiteList sl{b->d_site_key, b->d_counters};
+    BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    kern<<<(unsigned)count, SiteLaunch<KMAX, WX>::NT, lay.bytes, st>>>(
+        c->dg, b->dplan, c->one_body(), sl, lay, first, c->d_R, b->d_Hptr, b->d_Sptr, b->d_Hidx,
+        reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
+    BS2E_LAUNCHED();
 }
 
 void block_assemble(bs2e_block* b, const BlockStreams* bsp)
 {
     bs2e_ctx* c = b->ctx;
     const BlockStreams bs = bsp ? *bsp : default_streams(c);
+    if (b->n_config == 0 || b->nrows == 0) { b->assembled = true; return; }
     if (!c->have_R) throw Error("block_assemble: call bs2e_rk_build first");
     if (!c->have_1p) throw Error("block_assemble: call bs2e_set_one_particle first");
     if (b->lmax > c->lmax_1p) throw Error("block_assemble: configuration l exceeds max_l_1p of H_vec");
@@ -665,28 +802,13 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
         b->d_Sdat = dev_alloc_async<double>(2 * (size_t)b->nnzS, bs.main);
     }
     const long long nrows = b->nrows;
-    // site kernel unless max_k exceeds its largest instantiation or its tables do
-    // not fit shared memory; BS2E_FILL=row asks for the row kernel (A/B measurements)
     const Geom& g = c->dg;
-    const char* mode = getenv("BS2E_FILL");
     const int nblk = b->dplan.nblk;
-    const int kmax = site_kmax_for(g.K1);
-    bool use_site = b->nsites > 0 && b->d_angP && !(mode && strcmp(mode, "row") == 0) && kmax > 0 &&
-                    site_max_slots(g) <= 65535 && (size_t)nblk * site_max_slots(g) < (1u << 24);
-    SiteSmem lay{};
-    if (use_site) {
-        const int nkp = site_nkp(kmax);
-        lay.ncmax = site_max_nc(g);
-        lay.G = std::min(32, nblk);   // a site has at most one row per (l1,l2) block
-        lay.cfsm = sizeof(double) * (size_t)lay.G * nblk * 2 * nkp <= kSiteCoefSmem;
-        const char* cmode = getenv("BS2E_SITE_COEFS");   // "block": force the per-column-block staging (tests)
-        if (cmode && strcmp(cmode, "block") == 0) lay.cfsm = 0;
-        lay.nl = c->lmax_1p + 1;
-        lay.bytes = site_smem_bytes(g, nblk, lay.G, nkp, lay.cfsm != 0, lay.nl, true);
-        if (lay.bytes > kSiteSmemLimit) use_site = false;
-    }
-    if (use_site) {
-        const SiteList sl{b->d_site_key, b->d_site_ptr, b->d_site_rows, b->nsites};
+    if (b->use_site) {
+        const int kmax = site_kmax_for(g.K1);
+        const SiteSmem layX = site_layout(c, nblk, true), layD = site_layout(c, nblk, false);
+        if (layX.bytes > kSiteSmemLimit || layD.bytes > kSiteSmemLimit)
+            throw Error("block_assemble: site tables exceed shared memory (max_l_1p above the planned bound)");
         // the launch without exchange windows goes to the side stream so that it fills
         // the SMs the other launch leaves idle in its last wave
         const bool fork = b->nsites_x > 0 && b->nsites_x < b->nsites;
@@ -694,33 +816,15 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
             BS2E_CUDA(cudaEventRecord(bs.fork, bs.main));
             BS2E_CUDA(cudaStreamWaitEvent(bs.side, bs.fork, 0));
         }
-        auto launch = [&](auto kern, int nt, bool wx, int first, int count) {
-            if (count <= 0) return;
-            cudaStream_t st = (fork && !wx) ? bs.side : bs.main;
-            const size_t bytes = site_smem_bytes(g, nblk, lay.G, site_nkp(kmax), lay.cfsm != 0, lay.nl, wx);
-            BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            kern<<<(unsigned)count, nt, bytes, st>>>(
-                c->dg, b->dplan, c->one_body(), sl, lay, first, c->d_R, b->d_Hptr, b->d_Sptr,
-                b->d_Hidx, reinterpret_cast<double2*>(b->d_Hdat), b->d_Sidx, reinterpret_cast<double2*>(b->d_Sdat));
-            BS2E_LAUNCHED();
-        };
-        constexpr int NT = kSiteThreads, NTD = kSiteThreadsD;
+        cudaStream_t stD = fork ? bs.side : bs.main;
         const int nx = b->nsites_x, nd = b->nsites - b->nsites_x;
-#define BS2E_SITE(KM)                                                          \
-    case KM:                                                                   \
-        if (lay.cfsm) {                                                        \
-            launch(site_fill_kernel<NT, KM, true, true>, NT, true, 0, nx);           \
-            launch(site_fill_kernel<NTD, KM, true, false>, NTD, false, nx, nd);         \
-        } else {                                                               \
-            launch(site_fill_kernel<NT, KM, false, true>, NT, true, 0, nx);          \
-            launch(site_fill_kernel<NTD, KM, false, false>, NTD, false, nx, nd);        \
-        }                                                                      \
-        break;
         switch (kmax) {
-            BS2E_SITE(7) BS2E_SITE(13) BS2E_SITE(21) BS2E_SITE(31)
+        case 7: launch_site_fill<7, true>(b, layX, bs.main, 0, nx); launch_site_fill<7, false>(b, layD, stD, nx, nd); break;
+        case 13: launch_site_fill<13, true>(b, layX, bs.main, 0, nx); launch_site_fill<13, false>(b, layD, stD, nx, nd); break;
+        case 21: launch_site_fill<21, true>(b, layX, bs.main, 0, nx); launch_site_fill<21, false>(b, layD, stD, nx, nd); break;
+        case 31: launch_site_fill<31, true>(b, layX, bs.main, 0, nx); launch_site_fill<31, false>(b, layD, stD, nx, nd); break;
         default: throw Error("block_assemble: no site kernel for this max_k");
         }
-#undef BS2E_SITE
         if (fork) {
             BS2E_CUDA(cudaEventRecord(bs.join, bs.side));
             BS2E_CUDA(cudaStreamWaitEvent(bs.main, bs.join, 0));
@@ -739,20 +843,24 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
 // count pass (optional) + fill of several blocks of one context, consecutive blocks on
 // different stream pairs; everything is ordered after the work already queued on the
 // context's stream and the context's stream waits for all of it.
+static void ensure_lanes(bs2e_ctx* c)
+{
+    if (c->have_lanes) return;
+    for (auto& ln : c->lanes) {
+        BS2E_CUDA(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+        BS2E_CUDA(cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking));
+        BS2E_CUDA(cudaEventCreateWithFlags(&ln.fork, cudaEventDisableTiming));
+        BS2E_CUDA(cudaEventCreateWithFlags(&ln.join, cudaEventDisableTiming));
+        BS2E_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
+    BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    c->have_lanes = true;
+}
+
 void blocks_run(bs2e_ctx* c, long long n, bs2e_block** blks, bool recount)
 {
     if (n <= 0) return;
-    if (!c->have_lanes) {
-        for (auto& ln : c->lanes) {
-            BS2E_CUDA(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
-            BS2E_CUDA(cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking));
-            BS2E_CUDA(cudaEventCreateWithFlags(&ln.fork, cudaEventDisableTiming));
-            BS2E_CUDA(cudaEventCreateWithFlags(&ln.join, cudaEventDisableTiming));
-            BS2E_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-        }
-        BS2E_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-        c->have_lanes = true;
-    }
+    ensure_lanes(c);
     for (long long i = 0; i < n; ++i)
         if (!blks[i] || blks[i]->ctx != c) throw Error("bs2e_blocks_run: block of another context");
     BS2E_CUDA(cudaEventRecord(c->ev_start, c->stream));
@@ -774,10 +882,15 @@ void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat
                     int64_t* S_idx, double* S_dat)
 {
     if (!b->assembled) throw Error("block_download: call bs2e_block_assemble first");
-    cudaStream_t st = b->ctx->stream;
+    bs2e_ctx* c = b->ctx;
     const long long nrows = b->nrows;
+    if (b->n_config == 0 || nrows == 0) {   // empty block: index_ptr = [1]
+        if (H_ptr) H_ptr[0] = 1;
+        if (S_ptr) S_ptr[0] = 1;
+        return;
+    }
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
-        if (dst && bytes) BS2E_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        if (dst && bytes) download_to_host(c, dst, src, bytes);
     };
     d2h(H_ptr, b->d_Hptr, sizeof(long long) * (nrows + 1));
     d2h(S_ptr, b->d_Sptr, sizeof(long long) * (nrows + 1));
@@ -785,13 +898,14 @@ void block_download(bs2e_block* b, int64_t* H_ptr, int64_t* H_idx, double* H_dat
     d2h(S_idx, b->d_Sidx, sizeof(long long) * b->nnzS);
     d2h(H_dat, b->d_Hdat, sizeof(double) * 2 * b->nnzH);
     d2h(S_dat, b->d_Sdat, sizeof(double) * 2 * b->nnzS);
-    BS2E_CUDA(cudaStreamSynchronize(st));
+    download_flush(c);
 }
 
 void block_row_counts(bs2e_block* b, int64_t* cH, int64_t* cS)
 {
     cudaStream_t st = b->ctx->stream;
     const long long nrows = b->nrows;
+    if (nrows == 0) return;
     if (cH) BS2E_CUDA(cudaMemcpyAsync(cH, b->d_cntH, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, st));
     if (cS) BS2E_CUDA(cudaMemcpyAsync(cS, b->d_cntS, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, st));
     BS2E_CUDA(cudaStreamSynchronize(st));
@@ -827,12 +941,6 @@ void block_checksum(bs2e_block* b, uint64_t* sH, uint64_t* sS)
 void block_free(bs2e_block* b)
 {
     if (!b) return;
-    cudaFree(b->d_blk); cudaFree(b->d_ncrow); cudaFree(b->d_flags); cudaFree(b->d_krange);
-    cudaFree(b->d_angD); cudaFree(b->d_angX); cudaFree(b->d_angP);
-    cudaFree(b->d_row_n1); cudaFree(b->d_row_n2); cudaFree(b->d_row_blk);
-    cudaFree(b->d_rows); cudaFree(b->d_row_local);
-    cudaFree(b->d_site_key); cudaFree(b->d_site_ptr); cudaFree(b->d_site_rows);
-    cudaFree(b->d_cntH); cudaFree(b->d_cntS); cudaFree(b->d_Hptr); cudaFree(b->d_Sptr);
     {   // stream-ordered: returns at once, the pool keeps the pages for the next block
         cudaStream_t st = b->ctx ? b->ctx->stream : nullptr;
         if (b->d_Hidx) cudaFreeAsync(b->d_Hidx, st);
@@ -840,7 +948,8 @@ void block_free(bs2e_block* b)
         if (b->d_Hdat) cudaFreeAsync(b->d_Hdat, st);
         if (b->d_Sdat) cudaFreeAsync(b->d_Sdat, st);
     }
-    cudaFree(b->d_scan_tmp);
+    b->arena1.release();
+    b->arena0.release();
     delete b;
 }
 

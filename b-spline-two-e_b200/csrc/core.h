@@ -251,6 +251,40 @@ constexpr unsigned kExAny = 2u;   // same for the exchange ordering (l_d,l_c)
 
 struct KRange { signed char dlo, dhi, xlo, xhi; };  // k ranges (step 2) with non-zero factors
 
+// The planned rows of a block: a union of ascending, disjoint, inclusive 1-based row
+// ranges (the whole block, a row range, or the share of one GPU: bs2e_block_plan_ranges).
+// Local row = position inside the union; no per-row table is kept.
+struct RowRanges {
+    int n;           // number of ranges (n == 0: nothing planned)
+    const int* lo;   // [n]
+    const int* hi;   // [n]
+    const int* off;  // [n] local index of row lo[q]
+};
+
+// local index of configuration `row` (1-based), -1 when the row is not planned
+BS2E_HD int row_local_of(const RowRanges& rr, int row)
+{
+    int a = 0, n = rr.n;  // largest q with lo[q] <= row
+    if (n == 0 || row < rr.lo[0]) return -1;
+    while (n > 1) {
+        const int half = n >> 1;
+        if (rr.lo[a + half] <= row) a += half;
+        n -= half;
+    }
+    return row <= rr.hi[a] ? rr.off[a] + (row - rr.lo[a]) : -1;
+}
+// configuration index (1-based) of local row `local`
+BS2E_HD int row_of_local(const RowRanges& rr, int local)
+{
+    int a = 0, n = rr.n;
+    while (n > 1) {
+        const int half = n >> 1;
+        if (rr.off[a + half] <= local) a += half;
+        n -= half;
+    }
+    return rr.lo[a] + (local - rr.off[a]);
+}
+
 struct Plan {
     int nblk;
     int n_config;
@@ -265,14 +299,22 @@ struct Plan {
     const double* angX;          // [nblk][nblk][K1]   exchange * (-1)^(lc+ld+L)
     const double* angP;          // [nblk][nblk][2*nkp] the same packed by parity (site_core.h)
     int nkp;
+    // per-row tables: only built for the row-wise kernels (fallback fill, dipole blocks);
+    // the site kernels derive the rows of a radial site from ncrow
     const unsigned short* row_n1;   // [n_config]
     const unsigned short* row_n2;   // [n_config]
     const unsigned short* row_blk;  // [n_config]
-    // the planned rows (a union of ascending row ranges of the block)
+    // the planned rows
     int nrows;
-    const int* rows;       // [nrows]    local row -> configuration index (1-based)
-    const int* row_local;  // [n_config] configuration index - 1 -> local row, -1: not planned
+    RowRanges rr;
 };
+
+// configuration index (1-based) of (block bi; n_a, n_b), 0 when there is no such configuration
+BS2E_HD int config_index(const Geom& g, const Plan& pl, int bi, int na, int nb)
+{
+    const NcRow r = pl.ncrow[(size_t)bi * (g.nb + 1) + na];
+    return (nb >= r.nd_lo && nb <= r.nd_hi) ? r.start + (nb - r.nd_lo) : 0;
+}
 
 // union of two closed integer intervals as <= 2 disjoint ascending intervals
 struct Union2 { int lo[2], hi[2]; int n; };

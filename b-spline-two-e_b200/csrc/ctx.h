@@ -3,12 +3,16 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "core.h"
 #include "geom_host.h"
+#include "plan.h"
 
 namespace bs2e {
 
@@ -60,7 +64,59 @@ T* dev_upload(const std::vector<T>& v, cudaStream_t st)
     return p;
 }
 
+// One stream-ordered allocation carved into aligned pieces (the plan tables of a block).
+struct DevArena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    cudaStream_t st = nullptr;
+    void reserve(size_t bytes, cudaStream_t s)
+    {
+        release();
+        st = s;
+        size = bytes + 256;
+        BS2E_CUDA(cudaMallocAsync(&base, size, st));
+        used = 0;
+    }
+    template <class T>
+    T* take(size_t n)
+    {
+        const size_t at = (used + 255) & ~(size_t)255;
+        const size_t bytes = sizeof(T) * (n ? n : 1);
+        if (at + bytes > size) throw Error("internal: plan arena overflow");
+        used = at + bytes;
+        return reinterpret_cast<T*>(base + at);
+    }
+    static size_t need(size_t bytes) { return ((bytes ? bytes : 1) + 255) & ~(size_t)255; }
+    void release()
+    {
+        if (base) cudaFreeAsync(base, st);
+        base = nullptr;
+        size = used = 0;
+    }
+};
+
+// angular tables of one (L, list of (l1,l2) groups, max_k): computed once per context with
+// exact arithmetic on the host and kept on the device ("tabulated on the host, uploaded once")
+struct AngDev {
+    AngTables host;
+    unsigned char* flags = nullptr;
+    KRange* krange = nullptr;
+    double *angD = nullptr, *angX = nullptr, *angP = nullptr;
+    ~AngDev()
+    {
+        cudaFree(flags); cudaFree(krange); cudaFree(angD); cudaFree(angX); cudaFree(angP);
+    }
+};
+
 }  // namespace bs2e
+
+struct bs2e_ctx;
+// a configuration list resident on the device (bs2e_configs_upload)
+struct bs2e_configs {
+    bs2e_ctx* ctx = nullptr;
+    long long n = 0;
+    long long *d_n = nullptr, *d_l = nullptr;  // (2, n) each, as given by the caller
+};
 
 struct bs2e_ctx {
     int device = 0;
@@ -78,6 +134,17 @@ struct bs2e_ctx {
     cudaEvent_t ev_start = nullptr;
     bool have_lanes = false;
     int max_k = 0;
+
+    // plan state shared by the calls on this context (serialised by plan_mu)
+    std::mutex plan_mu;
+    std::map<std::vector<int>, std::shared_ptr<bs2e::AngDev>> ang_cache;
+    int* h_pin = nullptr;        // pinned staging for the small read-backs of a plan
+    size_t h_pin_bytes = 0;
+    // copy stream + pinned bounce buffers for downloads into pageable memory (download.cu)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    struct Stager;
+    Stager* stager = nullptr;
 
     // host copy of the basis geometry
     bs2e::HostGeom host;
@@ -120,19 +187,18 @@ struct bs2e_block {
     bs2e_ctx* ctx = nullptr;
     int L = 0, full = 0, lmax = 0;
     long long n_config = 0, nrows = 0;   // nrows: planned rows (union of row ranges)
-    bs2e::Plan dplan{};  // device pointers
-    // device-side plan storage
-    bs2e::BlockDesc* d_blk = nullptr;
-    bs2e::NcRow* d_ncrow = nullptr;
-    unsigned char* d_flags = nullptr;
-    bs2e::KRange* d_krange = nullptr;
-    double *d_angD = nullptr, *d_angX = nullptr, *d_angP = nullptr;
-    unsigned short *d_row_n1 = nullptr, *d_row_n2 = nullptr, *d_row_blk = nullptr;
-    int *d_rows = nullptr, *d_row_local = nullptr;
-    // rows grouped by radial site (site kernel)
-    unsigned* d_site_key = nullptr;
-    int *d_site_ptr = nullptr, *d_site_rows = nullptr;
+    bs2e::Plan dplan{};                  // device pointers
+    // device-side plan storage: two stream-ordered arenas (before / after the structure read-back)
+    bs2e::DevArena arena0, arena1;
+    std::shared_ptr<bs2e::AngDev> ang;   // shared through the context's cache
+    const long long *d_conf_n = nullptr, *d_conf_l = nullptr;   // configuration list on the device (owned by arena0 or by a bs2e_configs)
+    int* d_blk_start = nullptr;          // [nblk+1] first configuration (0-based) of each (l1,l2) group
+    // radial sites of the planned rows, sorted (plan.h: site_sort_key); counters[0] = nsites, [1] = nsites_x
+    unsigned long long* d_site_key = nullptr;
+    int* d_counters = nullptr;
+    int site_cap = 0;
     int nsites = 0, nsites_x = 0;
+    bool use_site = false;               // site kernels (else: row-wise fallback with per-row tables)
     // CSR fragment (device)
     long long *d_cntH = nullptr, *d_cntS = nullptr;  // [nrows+1] counts
     long long *d_Hptr = nullptr, *d_Sptr = nullptr;  // [nrows+1] 1-based
@@ -154,9 +220,20 @@ void fetch_r_d_k(bs2e_ctx* c, double* r_d_k, int64_t* iv, int64_t* i, int64_t* j
 void fetch_rk_keys(bs2e_ctx* c, long long n_keys, const int64_t* keys, double* vals);
 void fetch_rk_plane(bs2e_ctx* c, int k, double* out);
 
+// conf_n / conf_l: HOST arrays (uploaded) when cfg == nullptr, else the device-resident list cfg
 bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n,
-                       const int64_t* conf_l, int full, long long n_ranges, const int64_t* range_lo,
-                       const int64_t* range_hi);
+                       const int64_t* conf_l, const bs2e_configs* cfg, int full, long long n_ranges,
+                       const int64_t* range_lo, const int64_t* range_hi);
+bs2e_configs* configs_upload(bs2e_ctx* c, long long n_config, const int64_t* conf_n, const int64_t* conf_l);
+void configs_free(bs2e_configs* cfg);
+void ctx_release_plan_state(bs2e_ctx* c);
+// per-row tables (row_n1 / row_n2 / row_blk) of a configuration list, built on the device
+void build_row_tables(cudaStream_t st, long long n_config, const long long* d_conf_n, int nblk,
+                      const int* d_blk_start, unsigned short* row_n1, unsigned short* row_n2,
+                      unsigned short* row_blk);
+void download_to_host(bs2e_ctx* c, void* dst, const void* d_src, size_t bytes);   // pinned or pageable destination
+void download_flush(bs2e_ctx* c);
+void stager_destroy(bs2e_ctx* c);
 // the streams a block's work is issued on (default: the context's own pair)
 struct BlockStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
 BlockStreams default_streams(bs2e_ctx* c);

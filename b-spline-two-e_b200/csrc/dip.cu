@@ -23,9 +23,9 @@ __global__ void dip_count_kernel(Geom g, Plan plC, DipTables dt, long long* __re
 constexpr int kDipWarps = 8;
 
 namespace {
-struct DevArena {   // device arrays of one call, released on every exit path
+struct DipArena {   // device arrays of one call, released on every exit path
     std::vector<void*> p;
-    ~DevArena() { for (void* q : p) cudaFree(q); }
+    ~DipArena() { for (void* q : p) cudaFree(q); }
     template <class T> T* up(const std::vector<T>& v, cudaStream_t s) { T* d = dev_upload(v, s); p.push_back(d); return d; }
     template <class T> T* alloc(size_t n) { T* d = dev_alloc<T>(n); p.push_back(d); return d; }
 };
@@ -66,7 +66,7 @@ long long dip_block_run(bs2e_ctx* c, int q, const int64_t* sym1, long long n1, c
     }
     if (hp.empty) return 0;   // dip_block%init(shape, 0): no arrays are written (dipole.f90:26-30)
     cudaStream_t st = c->stream;
-    DevArena dev;
+    DipArena dev;
     Plan plC{};
     plC.nblk = hp.cols.nblk;
     plC.n_config = (int)n2;

@@ -40,9 +40,12 @@ HostDipPlan build_dip_plan(const Geom& hg, int gauge, int q, const int64_t* sym1
     dp.ang = three_j(L1, 1, L2, -M1, q, M2);
     if ((L1 - M1) & 1) dp.ang = -dp.ang;
     if (std::fabs(dp.ang) < 5.e-16 || !parity_allowed || !compute) return dp;   // dipole.f90:26-30
+    if (n1 <= 0 || n2 <= 0) return dp;   // a symmetry without configurations: empty block
     dp.empty = false;
-    dp.rows = build_host_plan(hg, L1, n1, conf_n1, conf_l1, 1, 1, n1);
-    dp.cols = build_host_plan(hg, L2, n2, conf_n2, conf_l2, 1, 1, n2);
+    const int64_t n1r = n1, n2r = n2;
+    const int64_t one = 1;
+    dp.rows = build_host_plan(hg, L1, n1, conf_n1, conf_l1, 1, 1, &one, &n1r, 0u);   // structure only
+    dp.cols = build_host_plan(hg, L2, n2, conf_n2, conf_l2, 1, 1, &one, &n2r, 0u);
     const int nR = dp.rows.nblk, nC = dp.cols.nblk;
     dp.flag.assign((size_t)nR * nC, 0);
     dp.coef.assign((size_t)nR * nC * 8, 0.0);

@@ -120,6 +120,19 @@ int bs2e_block_plan_ranges(bs2e_ctx *ctx, int64_t L, int64_t n_config,
                            const int64_t *conf_n, const int64_t *conf_l, int64_t full,
                            int64_t n_ranges, const int64_t *range_lo,
                            const int64_t *range_hi, bs2e_block **blk);
+/* A configuration list kept resident on the device (both arrays (2, n_config) as above),
+ * for pipelines whose inputs already live in HBM: bs2e_block_plan_dev plans the rows
+ * [range_lo[q], range_hi[q]] (n_ranges = 0: the whole block) without touching host copies
+ * of the list.  The plan itself is built on the device in every case (group structure,
+ * radial sites, row counts); the only host arithmetic is the 3j/6j table of the (l1,l2)
+ * group pairs, cached per context.                                                    */
+typedef struct bs2e_configs bs2e_configs;
+int bs2e_configs_upload(bs2e_ctx *ctx, int64_t n_config, const int64_t *conf_n,
+                        const int64_t *conf_l, bs2e_configs **cfg);
+int bs2e_configs_free(bs2e_configs *cfg);
+int bs2e_block_plan_dev(bs2e_ctx *ctx, int64_t L, bs2e_configs *cfg, int64_t full,
+                        int64_t n_ranges, const int64_t *range_lo, const int64_t *range_hi,
+                        bs2e_block **blk);
 int bs2e_block_nnz(bs2e_block *blk, int64_t *nnz_H, int64_t *nnz_S);
 /* per-row entry counts of the planned rows (one value per planned row each) */
 int bs2e_block_row_counts(bs2e_block *blk, int64_t *cnt_H, int64_t *cnt_S);

@@ -398,15 +398,15 @@ def test_driver_writes_result_files_streamed_and_whole(tmp_path):
         assert_csr_equal(Sg, S, scale_tol=5e-12, what=f"file S L={s.l}")
 
 
-def test_per_block_factor_staging_is_bit_identical(case, monkeypatch):
-    """large bases stage the packed angular factors one column block at a time (they do not fit
-    shared memory for the whole site): same results as the whole-site staging"""
+def test_small_factor_chunks_are_bit_identical(case, monkeypatch):
+    """large bases stage the packed angular factors of a site in several chunks (double-buffered
+    bulk copies); forcing tiny chunks on the small cases must give the same bits as one chunk"""
     run, ctx = case
     syms = [s for s in run.syms if s.n_config > 0]
     ref = []
     for s in syms:
         b = ctx.block_plan(s, False); b.assemble(); ref.append(b.download()); b.free()
-    monkeypatch.setenv("BS2E_SITE_COEFS", "block")
+    monkeypatch.setenv("BS2E_SITE_CHUNK_KB", "1")
     for s, (H0, S0) in zip(syms, ref):
         b = ctx.block_plan(s, False); b.assemble(); H, S = b.download(); b.free()
         assert np.array_equal(H.indices, H0.indices) and np.array_equal(H.data, H0.data)
