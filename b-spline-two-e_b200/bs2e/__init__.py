@@ -15,7 +15,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libbs2e_gpu.so")
+# BS2E_LIB: another build of the same library (kernel-variant A/B measurements)
+LIB_PATH = os.environ.get("BS2E_LIB") or os.path.join(_PKG, "lib", "libbs2e_gpu.so")
 
 i64 = C.c_int64
 f64 = C.c_double
@@ -79,6 +80,7 @@ ABI = {
     "bs2e_file_record_data": (C.c_int, [vp, vp, i64]),
     "bs2e_file_set_max_subrecord": (C.c_int, [i64]),
     "bs2e_launch_count": (i64, []),
+    "bs2e_debug_site_phase_cycles": (C.c_int, [vp, i64]),
     "bs2e_host_generate_grid": (i64, [i64, i64, i64, f64, f64, vp, i64]),
     "bs2e_host_gauss_legendre": (C.c_int, [i64, f64, f64, _pd, _pd]),
     "bs2e_host_find_max_n_b": (i64, [i64, i64, _pd, f64]),
@@ -126,6 +128,12 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(lib().bs2e_launch_count())
+
+
+def site_phase_cycles(reset=True):
+    out = np.zeros(8, np.uint64)
+    _chk(lib().bs2e_debug_site_phase_cycles(_ptr(out), int(reset)))
+    return out
 
 
 # ---------------------------------------------------------------------------

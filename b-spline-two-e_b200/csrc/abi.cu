@@ -621,6 +621,14 @@ int bs2e_host_free(void* ptr)
 
 int64_t bs2e_launch_count(void) { return g_launches.load(); }
 
+int bs2e_debug_site_phase_cycles(uint64_t* out8, int64_t reset)
+{
+    return guarded("bs2e_debug_site_phase_cycles", [&] {
+        if (!out8) throw Error("null argument");
+        site_phase_cycles(reinterpret_cast<unsigned long long*>(out8), reset != 0);
+    });
+}
+
 // ---- result files (host only) ----------------------------------------------
 struct bs2e_file {
     std::unique_ptr<files::Writer> w;

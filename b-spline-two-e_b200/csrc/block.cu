@@ -130,9 +130,6 @@ struct alignas(8) SiteChunk {  // consecutive column groups of one parity whose 
     short par, bj0, bj1, nrec;
 };
 
-constexpr int kSiteThreads = 128;   // sites with exchange windows
-constexpr int kSiteThreadsD = 256;  // sites without: one pass over the <= (2w+1)^2 candidates
-
 struct SiteSmem {   // element counts of the dynamic shared memory carve-up
     int ncmax;      // n_c slots
     int G;          // rows per group (<= 32)
@@ -143,9 +140,11 @@ struct SiteSmem {   // element counts of the dynamic shared memory carve-up
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
+__host__ __device__ inline int site_ncmax(const Geom& g, bool wx) { return wx ? site_max_nc(g) : 2 * g.w + 1; }
+
 __host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G, int nkp, int chrec, int nl, bool wx)
 {
-    const size_t ncmax = (size_t)site_max_nc(g);
+    const size_t ncmax = (size_t)site_ncmax(g, wx);
     const size_t cfs = (size_t)(wx ? 2 : 1) * nkp;
     size_t b = 0;
     b += align16(sizeof(double) * 2 * (size_t)chrec * cfs);                      // two staging buffers
@@ -153,6 +152,8 @@ __host__ __device__ inline size_t site_smem_bytes(const Geom& g, int nblk, int G
     b += align16(sizeof(SiteEntry) * (size_t)nblk * ncmax);                      // T
     b += align16(sizeof(RowRec) * (size_t)nblk * G);                             // rlist
     b += align16(sizeof(RowCache) * (size_t)G);                                  // rcache
+    b += align16(sizeof(BlockDesc) * (size_t)nblk);                              // sblk
+    b += align16((size_t)G * nblk);                                              // sfl
     b += align16(sizeof(SiteChunk) * (size_t)(2 * nblk + 2));                    // chunk table
     b += align16(sizeof(uchar4) * 2 * (size_t)nblk);                             // gcnt[2][nblk]
     b += align16(sizeof(unsigned) * (size_t)G * nblk);                           // pm
@@ -209,25 +210,81 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 
 constexpr size_t kSiteSmemLimit = 200 * 1024;
 
-// sum over the NKH multipoles of one parity, ascending k (mat_els.f90:566-570); cf in shared memory
+// RB dot products at once, each over the NKH multipoles of one parity in ascending k
+// (mat_els.f90:566-570); factors in shared memory, read as 16-byte broadcasts; the RB
+// accumulation chains are independent, which hides the FP64 latency
+#ifndef BS2E_RB
+#define BS2E_RB 2
+#endif
+constexpr int kSiteRB = BS2E_RB;   // records per step of the inner loop
+
+template <int NKH, int RB>
+__device__ __forceinline__ void site_dot_n(const double* const (&cf)[RB], int shift, const double (&R)[NKH], double (&acc)[RB])
+{
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NKH; i += 2) {
+        double2 c[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) c[r] = *reinterpret_cast<const double2*>(cf[r] + shift + i);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] += c[r].x * R[i];
+        if (i + 1 < NKH) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[r] += c[r].y * R[i + 1];
+        }
+    }
+}
+
 template <int NKH>
 __device__ __forceinline__ double site_dot(const double* __restrict__ cf, const double (&R)[NKH])
 {
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < NKH; i += 2) {
-        const double2 c = *reinterpret_cast<const double2*>(cf + i);
-        acc += c.x * R[i];
-        if (i + 1 < NKH) acc += c.y * R[i + 1];
-    }
-    return acc;
+    const double* const one[1] = {cf};
+    double acc[1];
+    site_dot_n<NKH, 1>(one, 0, R, acc);
+    return acc[0];
 }
 
+#ifdef BS2E_PHASE_TIMING
+__device__ unsigned long long g_site_phase_cycles[8];   // debug build: cycles per phase, summed over CTAs (thread 0)
+#define BS2E_PHASE_MARK(q)                                                      \
+    do {                                                                        \
+        if (threadIdx.x == 0) {                                                 \
+            const long long now_ = clock64();                                   \
+            atomicAdd(&g_site_phase_cycles[q], (unsigned long long)(now_ - t_phase_)); \
+            t_phase_ = now_;                                                    \
+        }                                                                       \
+    } while (0)
+#else
+#define BS2E_PHASE_MARK(q) do { } while (0)
+#endif
+
+// launch shapes (macros: kernel-variant builds for A/B measurements)
+#ifndef BS2E_D_NT
+#define BS2E_D_NT 256   // threads per CTA, sites without exchange windows
+#endif
+#ifndef BS2E_D_RC
+#define BS2E_D_RC 1     // candidate columns per thread
+#endif
+#ifndef BS2E_X_NT
+#define BS2E_X_NT 128   // sites with exchange windows
+#endif
+#ifndef BS2E_X_RC
+#define BS2E_X_RC 1
+#endif
+#ifndef BS2E_D_REGS
+#define BS2E_D_REGS 128  // register budget per thread (sets the CTAs per SM of the launch bounds)
+#endif
+#ifndef BS2E_X_REGS
+#define BS2E_X_REGS 128
+#endif
 template <int KMAX, bool WX>
-struct SiteLaunch {   // threads per CTA and CTAs per SM of an instantiation
-    static constexpr int NT = WX ? kSiteThreads : kSiteThreadsD;
-    static constexpr int per_sm = WX ? (KMAX <= 13 ? 768 : KMAX <= 21 ? 512 : 384) : (KMAX <= 13 ? 768 : 512);
-    static constexpr int min_blocks = per_sm / NT;
+struct SiteLaunch {   // threads per CTA, candidates per thread and CTAs per SM of an instantiation
+    static constexpr int NT = WX ? BS2E_X_NT : BS2E_D_NT;
+    static constexpr int RC = WX ? (KMAX <= 13 ? 2 : BS2E_X_RC) : BS2E_D_RC;
+    static constexpr int regs = WX ? (KMAX <= 21 ? BS2E_X_REGS : 168) : BS2E_D_REGS;
+    static constexpr int min_blocks = 65536 / (regs * NT);
 };
 
 // WX: the sites of this launch have exchange windows (site_wants_X); the sites that
@@ -241,6 +298,7 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                  double2* __restrict__ Sdat)
 {
     constexpr int NT = SiteLaunch<KMAX, WX>::NT;
+    constexpr int RC = SiteLaunch<KMAX, WX>::RC;
     constexpr int NW = NT / 32;
     constexpr int NKP = (((KMAX + 1) / 2) + 1) & ~1;  // = site_nkp(KMAX): packed factors per window
     constexpr int NKH = (KMAX + 1) / 2;               // multipoles of one parity
@@ -255,6 +313,7 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     SiteEntry* T = reinterpret_cast<SiteEntry*>(carve(sizeof(SiteEntry) * (size_t)nblk * ncmax));
     RowRec* rlist = reinterpret_cast<RowRec*>(carve(sizeof(RowRec) * (size_t)nblk * G));
     RowCache* rcache = reinterpret_cast<RowCache*>(carve(sizeof(RowCache) * (size_t)G));
+    BlockDesc* sblk = reinterpret_cast<BlockDesc*>(carve(sizeof(BlockDesc) * (size_t)nblk));
     SiteChunk* chunks = reinterpret_cast<SiteChunk*>(carve(sizeof(SiteChunk) * (size_t)(2 * nblk + 2)));
     uchar4* gcnt = reinterpret_cast<uchar4*>(carve(sizeof(uchar4) * 2 * (size_t)nblk));
     unsigned* pm = reinterpret_cast<unsigned*>(carve(sizeof(unsigned) * (size_t)G * nblk));
@@ -264,45 +323,56 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
     unsigned short* cfoff = reinterpret_cast<unsigned short*>(carve(sizeof(unsigned short) * 2 * (size_t)nblk));
     unsigned short* hp = reinterpret_cast<unsigned short*>(carve(sizeof(unsigned short) * (size_t)nblk * kModes * (ncmax + 1)));
     unsigned short* sp = reinterpret_cast<unsigned short*>(carve(sizeof(unsigned short) * (size_t)nblk * (ncmax + 1)));
+    unsigned char* sfl = reinterpret_cast<unsigned char*>(carve((size_t)G * nblk));   // flags of the group's (row, column group) pairs
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(carve(16));
     int* misc = reinterpret_cast<int*>(carve(16));   // [0] rows of the site, [1] chunks of the group
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef BS2E_PHASE_TIMING
+    long long t_phase_ = clock64();
+#endif
     const int sidx = blockIdx.x + site_off;
     const unsigned key = (unsigned)(sl.key[sidx] & 0xffffffffull);
     const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), WX);
     const int nnc = s.nnc;
     constexpr bool wantX = WX;
     const size_t plane = (size_t)g.P * g.ldP;
-    const int pi = (pl.blk[0].l1 + pl.blk[0].l2) & 1;   // parity of l1+l2, the same for every group of a symmetry
 
-    // The candidate column this thread owns and its R^k values of one multipole parity
-    // (both windows), read once and streaming.  Direct terms of parity `par` pair with
-    // exchange terms of parity par ^ pi.
-    OwnCand c;
-    double Rd[NKH], Rx[WX ? NKH : 1];
-    auto load_R = [&](bool act, int par) {
-        const double* pD = R + (size_t)c.rowD * g.ldP + c.colD;
-        const double* pX = R + (size_t)c.rowX * g.ldP + c.colX;
-        const bool onD = act && c.inD, onX = act && c.inX;
-        const int parx = par ^ pi;
+    // The RC candidate columns this thread owns (candidate pass*NT*RC + rc*NT + tid) and
+    // their R^k values of one multipole parity (both windows), read once and streaming.
+    // Direct terms of parity `par` pair with exchange terms of parity par ^ pi.
+    OwnCand c[RC];
+    bool act[RC];
+    double Rd[RC][NKH], Rx[RC][WX ? NKH : 1];
+    auto load_R = [&](int par, int pi) {
 #pragma unroll
-        for (int i = 0; i < NKH; ++i) {
-            const int k = 2 * i + par, kx = 2 * i + parx;
-            Rd[i] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
-            if constexpr (WX) Rx[i] = (onX && kx < K1) ? __ldcs(pX + (size_t)kx * plane) : 0.0;
+        for (int rc = 0; rc < RC; ++rc) {
+            const double* pD = R + (size_t)c[rc].rowD * g.ldP + c[rc].colD;
+            const double* pX = R + (size_t)c[rc].rowX * g.ldP + c[rc].colX;
+            const bool onD = act[rc] && c[rc].inD, onX = act[rc] && c[rc].inX;
+            const int parx = par ^ pi;
+#pragma unroll
+            for (int i = 0; i < NKH; ++i) {
+                const int k = 2 * i + par, kx = 2 * i + parx;
+                Rd[rc][i] = (onD && k < K1) ? __ldcs(pD + (size_t)k * plane) : 0.0;
+                if constexpr (WX) Rx[rc][i] = (onX && kx < K1) ? __ldcs(pX + (size_t)kx * plane) : 0.0;
+            }
+            if constexpr (!WX) Rx[rc][0] = 0.0;
         }
-        if constexpr (!WX) Rx[0] = 0.0;
     };
     // without exchange windows the candidate list is known up front: the loads of the
-    // first pass are issued here and complete behind phases 0-3
-    const bool prefetched = !WX && s.nD <= NT;
+    // first pass (parity 0) are issued here and complete behind phases 0-3
+    const bool prefetched = !WX && s.nD <= NT * RC;
     if (prefetched) {
-        c = site_own_cand(g, s, cprefix, false, tid < s.nD ? tid : 0);
-        load_R(tid < s.nD, 0);
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) {
+            act[rc] = rc * NT + tid < s.nD;
+            c[rc] = site_own_cand(g, s, cprefix, false, act[rc] ? rc * NT + tid : 0);
+        }
+        load_R(0, 0);
     }
 
-    // ---- phase 0: rows of the site; phase 1: clipped windows, candidate prefix, band rows ----
+    // ---- phase 0: rows of the site; phase 1: clipped windows, candidate prefix, band rows, group table ----
     if (warp == 0) {
         int run = 0;
         for (int b0 = 0; b0 < nblk; b0 += 32) {
@@ -338,15 +408,20 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
         }
         if (lane == 0) cprefix[nnc] = run;
     }
-    for (int q = lane; q < nnc; q += 32)
-        for (int bj = warp; bj < nblk; bj += NW) T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+    for (int idx = tid; idx < nblk * nnc; idx += NT) {
+        const int bj = idx / nnc, q = idx - bj * nnc;
+        T[bj * ncmax + q] = site_entry(g, pl, s, bj, q);
+    }
+    for (int bj = tid; bj < nblk; bj += NT) sblk[bj] = pl.blk[bj];
     for (int idx = tid; idx < site_1p_doubles(g, lay.nl) / 2; idx += NT) {
         const Cplx v = site_1p_source(g, ob, s, lay.nl, idx);
         reinterpret_cast<double2*>(ob_s)[idx] = make_double2(v.re, v.im);
     }
     const SiteOneBody so{ob_s, ob_s + (size_t)lay.nl * 2 * (2 * g.w + 1) * 2};
     __syncthreads();
+    BS2E_PHASE_MARK(0);
     const int nr = misc[0];
+    const int pi = (sblk[0].l1 + sblk[0].l2) & 1;   // parity of l1+l2, the same for every group of a symmetry
     // ---- phase 2: prefix of stored entries over the n_c slots, per (bj, mode);
     //      one thread per (bj, mode), serial over the slots ----
     for (int task = tid; task < nblk * kModes; task += NT) {
@@ -354,7 +429,7 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
         if (!wantX && (mode == kModeX || mode == kModeDX)) continue;  // never read
         const bool useD = mode_useD(mode), useX = mode_useX(mode);
         const bool diag = mode == kModeDiag;
-        const bool samex = diag && pl.blk[bj].l1 == pl.blk[bj].l2;
+        const bool samex = diag && sblk[bj].l1 == sblk[bj].l2;
         unsigned short* hpq = hp + task * (ncmax + 1);
         unsigned short* spq = sp + bj * (ncmax + 1);
         int run = 0, srun = 0;
@@ -379,22 +454,30 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
 
     for (int g0 = 0; g0 < nr; g0 += G) {
         const int gr = imin(G, nr - g0);
-        __syncthreads();  // phase 2 / previous group finished
+        // the group's rows: first entries of the rows, flags of their (row, column group) pairs -- the
+        // only global loads of phase 3, all independent
+        for (int ri = tid; ri < gr; ri += NT) {
+            const int bi = srow_bi[g0 + ri];
+            const long long wrow = srow_local[g0 + ri];
+            rcache[ri] = RowCache{Hptr[wrow] - 1, Sptr[wrow] - 1, bi, sblk[bi].l1, sblk[bi].l2, 0};
+        }
+        for (int idx = tid; idx < gr * nblk; idx += NT) {
+            const int ri = idx / nblk, bj = idx - ri * nblk;
+            sfl[idx] = pl.flags[(size_t)srow_bi[g0 + ri] * nblk + bj];
+        }
+        __syncthreads();  // phase 2 / the group's tables
+        BS2E_PHASE_MARK(1);
         // ---- phase 3a: coupled column groups of each row and their offsets inside the row ----
         for (int ri = warp; ri < gr; ri += NW) {
-            const int bi = srow_bi[g0 + ri];
-            const BlockDesc bd = pl.blk[bi];
-            const RowInfo r{0, bi, s.na, s.nb, bd.l1, bd.l2};
-            if (lane == 0) {
-                const long long wrow = srow_local[g0 + ri];
-                rcache[ri] = RowCache{Hptr[wrow] - 1, Sptr[wrow] - 1, bi, bd.l1, bd.l2, 0};
-            }
+            const RowCache rc = rcache[ri];
             int run = 0;
             for (int b0 = 0; b0 < nblk; b0 += 32) {
                 const int bj = b0 + lane;
                 int cnt = 0, mode = -1;
-                if (bj < nblk) {
-                    mode = pair_mode(pl, r, bj);
+                if (bj < nblk && (pl.full || bj >= rc.bi)) {
+                    const unsigned f = sfl[ri * nblk + bj];
+                    mode = bj == rc.bi ? kModeDiag
+                           : (f & kDirAny) ? ((f & kExAny) ? kModeDX : kModeD) : ((f & kExAny) ? kModeX : -1);   // pair_mode
                     if (mode >= 0) {
                         const unsigned short* hb = hp + (bj * kModes) * (ncmax + 1) + nnc;
                         mode = effective_mode(mode, hb[kModeD * (ncmax + 1)], wantX ? hb[kModeX * (ncmax + 1)] : 0);
@@ -403,63 +486,80 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                 }
                 const int inc = warp_incl_scan(cnt, lane);
                 if (bj < nblk)
-                    pm[ri * nblk + bj] = cnt > 0 ? pm_pack(run + inc - cnt, mode, (r.la + pl.blk[bj].l1) & 1) : 0u;
+                    pm[ri * nblk + bj] = cnt > 0 ? pm_pack(run + inc - cnt, mode, (rc.la + sblk[bj].l1) & 1) : 0u;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
         __syncthreads();
-        // ---- phase 3b: the pairs of each column group, filed by (parity, storage mode) ----
-        for (int bj = tid; bj < nblk; bj += NT) {
-            int cnt[2 * kModes] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int ri = 0; ri < gr; ++ri) {
-                const unsigned v = pm[ri * nblk + bj];
-                if (!pm_valid(v)) continue;
-                const int slot = pm_pd(v) * kModes + pm_mode(v);
+        BS2E_PHASE_MARK(2);
+        // ---- phase 3b: the pairs of each column group, filed by (parity, storage mode);
+        //      one warp per column group, lane = row of the group ----
+        for (int bj = warp; bj < nblk; bj += NW) {
+            const unsigned v = lane < gr ? pm[lane * nblk + bj] : 0u;
+            const bool valid = pm_valid(v);
+            const int slot = valid ? pm_pd(v) * kModes + pm_mode(v) : -1;
+            int cnt[2 * kModes];
+            int where = 0, base = 0;
 #pragma unroll
-                for (int q = 0; q < 2 * kModes; ++q)
-                    if (q == slot) ++cnt[q];
+            for (int q = 0; q < 2 * kModes; ++q) {
+                const unsigned m = __ballot_sync(0xffffffffu, slot == q);
+                if (slot == q) where = base + __popc(m & ((1u << lane) - 1u));
+                cnt[q] = __popc(m);
+                base += cnt[q];
             }
-            gcnt[bj] = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2], (unsigned char)cnt[3]);
-            gcnt[nblk + bj] = make_uchar4((unsigned char)cnt[4], (unsigned char)cnt[5], (unsigned char)cnt[6], (unsigned char)cnt[7]);
-            int pos[2 * kModes];
-            pos[0] = 0;
-#pragma unroll
-            for (int q = 1; q < 2 * kModes; ++q) pos[q] = pos[q - 1] + cnt[q - 1];
-            for (int ri = 0; ri < gr; ++ri) {
-                const unsigned v = pm[ri * nblk + bj];
-                if (!pm_valid(v)) continue;
-                const int slot = pm_pd(v) * kModes + pm_mode(v);
-                int where = 0;  // pos[slot]++ without dynamic indexing of a register array
-#pragma unroll
-                for (int q = 0; q < 2 * kModes; ++q)
-                    if (q == slot) where = pos[q]++;
-                const RowCache rc = rcache[ri];
-                const int fl = pl.flags[(size_t)rc.bi * nblk + bj] & (kDirAny | kExAny);
-                rlist[bj * G + where] = RowRec{rc.hbase + pm_off(v), rc.bi * nblk + bj, fl | (ri << 8)};
+            if (lane == 0) {
+                gcnt[bj] = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2], (unsigned char)cnt[3]);
+                gcnt[nblk + bj] = make_uchar4((unsigned char)cnt[4], (unsigned char)cnt[5], (unsigned char)cnt[6], (unsigned char)cnt[7]);
+            }
+            if (valid) {
+                const RowCache rc = rcache[lane];
+                const int fl = sfl[lane * nblk + bj] & (kDirAny | kExAny);
+                rlist[bj * G + where] = RowRec{rc.hbase + pm_off(v), rc.bi * nblk + bj, fl | (lane << 8)};
             }
         }
         __syncthreads();
+        BS2E_PHASE_MARK(3);
         // ---- phase 3c: chunks of consecutive column groups whose factors fit a staging buffer ----
-        if (tid == 0) {
+        if (warp == 0) {
             int nch = 0;
             for (int par = 0; par < 2; ++par) {
-                int cur = 0, bj0 = 0;
-                for (int bj = 0; bj < nblk; ++bj) {
-                    const uchar4 gc = gcnt[par * nblk + bj];
-                    const int n = gc.x + gc.y + gc.z + gc.w;
-                    if (cur + n > chrec) {
-                        chunks[nch++] = SiteChunk{(short)par, (short)bj0, (short)bj, (short)cur};
-                        cur = 0;
-                        bj0 = bj;
-                    }
-                    cfoff[par * nblk + bj] = (unsigned short)cur;
-                    cur += n;
+                int run = 0;   // records of this parity; cfoff = offset of each column group inside ONE chunk
+                for (int b0 = 0; b0 < nblk; b0 += 32) {
+                    const int bj = b0 + lane;
+                    int n = 0;
+                    if (bj < nblk) { const uchar4 gc = gcnt[par * nblk + bj]; n = gc.x + gc.y + gc.z + gc.w; }
+                    const int inc = warp_incl_scan(n, lane);
+                    if (bj < nblk) cfoff[par * nblk + bj] = (unsigned short)(run + inc - n);
+                    run += __shfl_sync(0xffffffffu, inc, 31);
                 }
-                if (cur > 0) chunks[nch++] = SiteChunk{(short)par, (short)bj0, (short)nblk, (short)cur};
+                if (run == 0) continue;
+                if (run <= chrec) {
+                    if (lane == 0) chunks[nch] = SiteChunk{(short)par, 0, (short)nblk, (short)run};
+                    ++nch;
+                } else {   // greedy split, serial
+                    int add = 0;
+                    if (lane == 0) {
+                        int cur = 0, bj0 = 0;
+                        for (int bj = 0; bj < nblk; ++bj) {
+                            const uchar4 gc = gcnt[par * nblk + bj];
+                            const int n = gc.x + gc.y + gc.z + gc.w;
+                            if (cur + n > chrec) {
+                                chunks[nch + add++] = SiteChunk{(short)par, (short)bj0, (short)bj, (short)cur};
+                                cur = 0;
+                                bj0 = bj;
+                            }
+                            cfoff[par * nblk + bj] = (unsigned short)cur;
+                            cur += n;
+                        }
+                        if (cur > 0) chunks[nch + add++] = SiteChunk{(short)par, (short)bj0, (short)nblk, (short)cur};
+                    }
+                    nch += __shfl_sync(0xffffffffu, add, 0);
+                }
             }
-            misc[1] = nch;
+            if (lane == 0) misc[1] = nch;
         }
         __syncthreads();
+        BS2E_PHASE_MARK(4);
         const int nch = misc[1];
         resident0 = resident1 = -1;   // the buffers hold chunks of the previous group
         // chunk ch -> staging buffer bsel: one bulk copy per record, issued by all threads
@@ -490,13 +590,18 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
         if (nch > 0) stage(0, 0);
         // ---- phase 4: fill ----
         const int nc_all = site_num_cand(s, cprefix, wantX);
-        const int npass = nch > 0 ? (nc_all + NT - 1) / NT : 0;
+        const int npass = nch > 0 ? (nc_all + NT * RC - 1) / (NT * RC) : 0;
         for (int pass = 0; pass < npass; ++pass) {
-            const int t = pass * NT + tid;
-            const bool act = t < nc_all;
             const bool keepR = prefetched && pass == 0 && g0 == 0;   // parity-0 values already in registers
-            if (!keepR) c = site_own_cand(g, s, cprefix, wantX, act ? t : 0);
-            const bool warp_has_cand = __ballot_sync(0xffffffffu, act) != 0u;
+            if (!keepR) {
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc) {
+                    const int t = (pass * RC + rc) * NT + tid;
+                    act[rc] = t < nc_all;
+                    c[rc] = site_own_cand(g, s, cprefix, wantX, act[rc] ? t : 0);
+                }
+            }
+            const bool warp_has_cand = __ballot_sync(0xffffffffu, act[0]) != 0u;   // candidates of slot 0 come first
             int rpar = keepR ? 0 : -1;   // parity of the values in Rd / Rx
             for (int ch = 0; ch < nch; ++ch) {
                 // next chunk of the cyclic sequence into the other buffer (all threads take the same branch)
@@ -512,14 +617,16 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                 if (!warp_has_cand) continue;
                 const SiteChunk cc = chunks[ch];
                 const int par = cc.par;
-                if (rpar != par) { load_R(act, par); rpar = par; }
+                if (rpar != par) { load_R(par, pi); rpar = par; }
                 for (int bj = cc.bj0; bj < cc.bj1; ++bj) {
                     const uchar4 gc = gcnt[par * nblk + bj];
                     if ((gc.x | gc.y | gc.z | gc.w) == 0) continue;
                     const uchar4 g0c = gcnt[bj];
                     const RowRec* rl = rlist + bj * G + (par ? g0c.x + g0c.y + g0c.z + g0c.w : 0);
                     const double* cfm = cbuf + (size_t)cfoff[par * nblk + bj] * CFS;
-                    const SiteEntry e = T[bj * ncmax + c.q];
+                    SiteEntry e[RC];
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc) e[rc] = T[bj * ncmax + c[rc].q];
 #pragma unroll
                     for (int mode = 0; mode < kModes; ++mode) {
                         if (!WX && (mode == kModeX || mode == kModeDX)) continue;  // no such pairs without exchange windows
@@ -530,62 +637,82 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
                         rl += nrow;
                         cfm += (size_t)nrow * CFS;
                         const bool diag = mode == kModeDiag;
-                        const ModeSlot ms = site_mode_slot(s, c, e, hp + (bj * kModes + mode) * (ncmax + 1), mode,
-                                                           diag && !pl.full);
-                        const bool stored = act && (ms.sup || ms.sup_ex);
-                        if (__ballot_sync(0xffffffffu, stored) == 0u) continue;
-                        const long long jcol = ms.jcol;
+                        ModeSlot ms[RC];
+                        bool stored[RC];
+                        long long* pI[RC];   // &Hidx[rank], &Hd[2 rank]: the record adds its row offset
+                        double* pV[RC];
+                        bool any = false;
+#pragma unroll
+                        for (int rc = 0; rc < RC; ++rc) {
+                            ms[rc] = site_mode_slot(s, c[rc], e[rc], hp + (bj * kModes + mode) * (ncmax + 1), mode, diag && !pl.full);
+                            stored[rc] = act[rc] && (ms[rc].sup || ms[rc].sup_ex);
+                            pI[rc] = Hidx + ms[rc].rank;
+                            pV[rc] = Hd + 2 * (long long)ms[rc].rank;
+                            any = any || stored[rc];
+                        }
+                        if (__ballot_sync(0xffffffffu, any) == 0u) continue;
                         if (!diag) {
-                            // two records at a time: independent FP64 chains (an odd tail is computed twice, stored once)
-                            for (int i = 0; i < nrow; i += 2) {
-                                const bool two = i + 1 < nrow;
-                                const RowRec rec0 = rm[i], rec1 = rm[two ? i + 1 : i];
-                                const double* cf0 = cf + (size_t)i * CFS;
-                                const double* cf1 = cf0 + (two ? CFS : 0);
-                                double res0 = 0.0, res1 = 0.0;
-                                if (mode != kModeX) {
-                                    const double d0 = site_dot<NKH>(cf0, Rd), d1 = site_dot<NKH>(cf1, Rd);
-                                    res0 += ms.sup ? d0 : 0.0;
-                                    res1 += ms.sup ? d1 : 0.0;
+                            // RB records per step for each of the RC candidates: RB*RC independent FP64 chains
+                            // (a short tail repeats its last record, stored once)
+                            constexpr int RB = kSiteRB;
+                            for (int i = 0; i < nrow; i += RB) {
+                                const double* cfr[RB];
+                                long long hpos[RB];
+#pragma unroll
+                                for (int r = 0; r < RB; ++r) {
+                                    const int ii = imin(i + r, nrow - 1);
+                                    hpos[r] = rm[ii].hpos;
+                                    cfr[r] = cf + (size_t)ii * CFS;
                                 }
-                                if constexpr (WX) {
-                                    if (mode != kModeD) {
-                                        const double x0 = site_dot<NKH>(cf0 + NKP, Rx), x1 = site_dot<NKH>(cf1 + NKP, Rx);
-                                        res0 += ms.sup_ex ? x0 : 0.0;
-                                        res1 += ms.sup_ex ? x1 : 0.0;
+#pragma unroll
+                                for (int rc = 0; rc < RC; ++rc) {
+                                    double res[RB];
+                                    if (mode == kModeD) {
+                                        site_dot_n<NKH, RB>(cfr, 0, Rd[rc], res);   // stored == sup
+                                    } else {
+                                        double d[RB], x[RB];
+#pragma unroll
+                                        for (int r = 0; r < RB; ++r) d[r] = x[r] = 0.0;
+                                        if (mode != kModeX) site_dot_n<NKH, RB>(cfr, 0, Rd[rc], d);
+                                        if constexpr (WX) site_dot_n<NKH, RB>(cfr, NKP, Rx[rc], x);
+#pragma unroll
+                                        for (int r = 0; r < RB; ++r) res[r] = (ms[rc].sup ? d[r] : 0.0) + (ms[rc].sup_ex ? x[r] : 0.0);
                                     }
-                                }
-                                if (stored) {
-                                    const long long p0 = rec0.hpos + ms.rank;
-                                    Hidx[p0] = jcol;
-                                    *reinterpret_cast<double2*>(Hd + 2 * p0) = make_double2(res0, 0.0);
-                                    if (two) {
-                                        const long long p1 = rec1.hpos + ms.rank;
-                                        Hidx[p1] = jcol;
-                                        *reinterpret_cast<double2*>(Hd + 2 * p1) = make_double2(res1, 0.0);
+#ifdef BS2E_EXP_NOSTORE
+                                    if (stored[rc] && hpos[0] < 0) {   // experiment: never true
+#else
+                                    if (stored[rc]) {
+#endif
+#pragma unroll
+                                        for (int r = 0; r < RB; ++r) {
+                                            if (r > 0 && i + r >= nrow) break;
+                                            pI[rc][hpos[r]] = ms[rc].jcol;
+                                            *reinterpret_cast<double2*>(pV[rc] + 2 * hpos[r]) = make_double2(res[r], 0.0);
+                                        }
                                     }
                                 }
                             }
                         } else {  // exactly one row: the row whose own group is bj (parity 0)
                             const RowRec rec = rm[0];
-                            const RowCache rc = rcache[rec.meta >> 8];
-                            const double d = site_dot<NKH>(cf, Rd);
-                            double res = 0.0;
-                            res += ms.sup ? d : 0.0;
-                            if constexpr (WX) {
-                                const double x = site_dot<NKH>(cf + NKP, Rx);
-                                res += ms.sup_ex ? x : 0.0;
-                            }
-                            // hamiltonian.f90:183: the r_12 sums enter only when a supported window has a factor above 5e-15
-                            const bool allowed = (ms.sup && (rec.meta & kDirAny)) || (ms.sup_ex && (rec.meta & kExAny));
-                            if (!allowed) res = 0.0;
-                            if (stored) {
-                                double re = res, im = 0.0;
-                                site_diag_terms(g, pl, so, s, rc.la, rc.lb, c, ms, rc.la == rc.lb, sp + bj * (ncmax + 1),
-                                                rc.sbase, &re, &im, Sidx, Sd);
-                                const long long pos = rec.hpos + ms.rank;
-                                Hidx[pos] = jcol;
-                                *reinterpret_cast<double2*>(Hd + 2 * pos) = make_double2(re, im);
+                            const RowCache rc_ = rcache[rec.meta >> 8];
+#pragma unroll
+                            for (int rc = 0; rc < RC; ++rc) {
+                                const double d = site_dot<NKH>(cf, Rd[rc]);
+                                double res = ms[rc].sup ? d : 0.0;
+                                if constexpr (WX) {
+                                    const double x = site_dot<NKH>(cf + NKP, Rx[rc]);
+                                    res += ms[rc].sup_ex ? x : 0.0;
+                                }
+                                // hamiltonian.f90:183: the r_12 sums enter only when a supported window has a factor above 5e-15
+                                const bool allowed = (ms[rc].sup && (rec.meta & kDirAny)) || (ms[rc].sup_ex && (rec.meta & kExAny));
+                                if (!allowed) res = 0.0;
+                                if (stored[rc]) {
+                                    double re = res, im = 0.0;
+                                    site_diag_terms(g, pl, so, s, rc_.la, rc_.lb, c[rc], ms[rc], rc_.la == rc_.lb,
+                                                    sp + bj * (ncmax + 1), rc_.sbase, &re, &im, Sidx, Sd);
+                                    pI[rc][rec.hpos] = ms[rc].jcol;
+                                    *reinterpret_cast<double2*>(pV[rc] + 2 * rec.hpos) = make_double2(re, im);
+                                }
                             }
                         }
                     }
@@ -595,6 +722,8 @@ site_fill_kernel(Geom g, Plan pl, OneBody ob, SiteList sl, SiteSmem lay, int sit
         // a staging copy that was issued must land before the buffers are reused or the CTA exits
         wait_buf(0);
         wait_buf(1);
+        BS2E_PHASE_MARK(5);
+        if (g0 + G < nr) __syncthreads();   // the next group rewrites the tables
     }
 }
 
@@ -696,7 +825,7 @@ namespace {
 // whole site, bounded so that the launch keeps its CTAs per SM (BS2E_SITE_CHUNK_KB overrides)
 int site_chunk_records(const Geom& g, int nblk, int G, int nkp, bool wx)
 {
-    size_t cap_kb = wx ? 24 : 32;
+    size_t cap_kb = 8;
     if (const char* e = getenv("BS2E_SITE_CHUNK_KB")) cap_kb = (size_t)std::max(1, atoi(e));
     const size_t per = sizeof(double) * (wx ? 2 : 1) * nkp;
     size_t rec = std::min((size_t)G * nblk, cap_kb * 1024 / per);
@@ -710,7 +839,7 @@ SiteSmem site_layout(const bs2e_ctx* c, int nblk, bool wx)
     SiteSmem lay{};
     const int kmax = site_kmax_for(g.K1);
     const int nkp = site_nkp(kmax);
-    lay.ncmax = site_max_nc(g);
+    lay.ncmax = site_ncmax(g, wx);
     lay.G = std::min(32, nblk);   // a site has at most one row per (l1,l2) group
     lay.nl = c->lmax_1p + 1;
     lay.chrec = site_chunk_records(g, nblk, lay.G, nkp, wx);
@@ -936,6 +1065,22 @@ void block_checksum(bs2e_block* b, uint64_t* sH, uint64_t* sS)
     cudaFree(d);
     if (sH) *sH = h[0];
     if (sS) *sS = h[1];
+}
+
+// debug builds (-DBS2E_PHASE_TIMING): cycles spent per phase of site_fill_kernel, summed over CTAs
+void site_phase_cycles(unsigned long long* out8, bool reset)
+{
+#ifdef BS2E_PHASE_TIMING
+    BS2E_CUDA(cudaDeviceSynchronize());
+    BS2E_CUDA(cudaMemcpyFromSymbol(out8, g_site_phase_cycles, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {};
+        BS2E_CUDA(cudaMemcpyToSymbol(g_site_phase_cycles, z, sizeof(z)));
+    }
+#else
+    (void)reset;
+    for (int q = 0; q < 8; ++q) out8[q] = 0;
+#endif
 }
 
 void block_free(bs2e_block* b)

@@ -259,13 +259,15 @@ struct RowRanges {
     const int* lo;   // [n]
     const int* hi;   // [n]
     const int* off;  // [n] local index of row lo[q]
+    int lo0, hi0;    // the first range again, by value: a single range needs no table look-up
 };
 
 // local index of configuration `row` (1-based), -1 when the row is not planned
 BS2E_HD int row_local_of(const RowRanges& rr, int row)
 {
+    if (rr.n == 1) return (row >= rr.lo0 && row <= rr.hi0) ? row - rr.lo0 : -1;
     int a = 0, n = rr.n;  // largest q with lo[q] <= row
-    if (n == 0 || row < rr.lo[0]) return -1;
+    if (n == 0 || row < rr.lo0) return -1;
     while (n > 1) {
         const int half = n >> 1;
         if (rr.lo[a + half] <= row) a += half;
@@ -276,6 +278,7 @@ BS2E_HD int row_local_of(const RowRanges& rr, int row)
 // configuration index (1-based) of local row `local`
 BS2E_HD int row_of_local(const RowRanges& rr, int local)
 {
+    if (rr.n == 1) return rr.lo0 + local;
     int a = 0, n = rr.n;
     while (n > 1) {
         const int half = n >> 1;

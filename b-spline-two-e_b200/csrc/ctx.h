@@ -234,6 +234,7 @@ void build_row_tables(cudaStream_t st, long long n_config, const long long* d_co
 void download_to_host(bs2e_ctx* c, void* dst, const void* d_src, size_t bytes);   // pinned or pageable destination
 void download_flush(bs2e_ctx* c);
 void stager_destroy(bs2e_ctx* c);
+void site_phase_cycles(unsigned long long* out8, bool reset);
 // the streams a block's work is issued on (default: the context's own pair)
 struct BlockStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
 BlockStreams default_streams(bs2e_ctx* c);

@@ -256,7 +256,8 @@ Plan HostPlan::view() const
     pl.row_n2 = row_n2.data();
     pl.row_blk = row_blk.data();
     pl.nrows = nrows;
-    pl.rr = RowRanges{(int)range_lo.size(), range_lo.data(), range_hi.data(), range_off.data()};
+    pl.rr = RowRanges{(int)range_lo.size(), range_lo.data(), range_hi.data(), range_off.data(),
+                      range_lo.empty() ? 1 : range_lo[0], range_hi.empty() ? 0 : range_hi[0]};
     return pl;
 }
 

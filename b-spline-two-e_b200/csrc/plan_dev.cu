@@ -374,7 +374,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     pl.angP = b->ang->angP;
     pl.nkp = b->ang->host.nkp;
     pl.nrows = nrows;
-    pl.rr = RowRanges{nr, d_ranges, d_ranges + nr, d_ranges + 2 * nr};
+    pl.rr = RowRanges{nr, d_ranges, d_ranges + nr, d_ranges + 2 * nr, rlo[0], rhi[0]};
     {
         const size_t ncells = (size_t)nblk * stride;
         ncrow_init_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(ncells, d_ncrow);

@@ -224,6 +224,10 @@ int bs2e_file_set_max_subrecord(int64_t bytes);
 
 /* Number of kernels this library has launched since load (all contexts). */
 int64_t bs2e_launch_count(void);
+/* Profiling aid: cycles per phase of the site fill kernel summed over its CTAs (zeros unless the
+ * library was built with -DBS2E_PHASE_TIMING): [0] phases 0-1, [1] phase 2, [2] 3a, [3] 3b, [4] 3c,
+ * [5] phase 4.                                                                      */
+int bs2e_debug_site_phase_cycles(uint64_t *out8, int64_t reset);
 
 /* ---- host-side companions of the path (no GPU needed).  They restate the
  *      cheap reference routines whose OUTPUT feeds the hot path, so that a

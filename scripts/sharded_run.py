@@ -102,11 +102,13 @@ def main():
         my_elems += el
     wall = time.perf_counter() - t_wall
     total = sum(b["elements"] for b in per_block)
+    phases = bs2e.site_phase_cycles().tolist()
     if rank == 0:
         print(json.dumps({"workload": workload, "n_gpus": world, "elements": total, "csr_tb": 24e-12 * total,
                           "stage_C_ms": tot_ms, "elements_per_s": total / (tot_ms * 1e-3),
                           "stage_AB_ms": t_ab, "rk_integrals": n_rk, "rk_integrals_per_s": n_rk / (t_ab * 1e-3),
-                          "wall_s_incl_planning": wall, "checksum_xor_rank0": xor, "blocks": per_block}))
+                          "wall_s_incl_planning": wall, "checksum_xor_rank0": xor,
+                          "site_phase_cycles": phases if any(phases) else None, "blocks": per_block}))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
