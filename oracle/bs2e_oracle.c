@@ -55,6 +55,17 @@ int64_t orc_max_threads(void)
 #endif
 }
 
+/* The launcher of a multi-rank job (torchrun) exports OMP_NUM_THREADS=1; the timed
+ * CPU baseline states and sets its own thread count instead of inheriting that.  */
+void orc_set_threads(int64_t n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads((int)n);
+#else
+    (void)n;
+#endif
+}
+
 /* ======================================================================== */
 /* grid_tools.f90:6-55  generate_grid                                        */
 /* ======================================================================== */

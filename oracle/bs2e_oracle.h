@@ -160,6 +160,7 @@ int64_t orc_dip_block(const orc_bspline *bs, int gauge, const double *A, const d
                       int64_t compute, int64_t *index_ptr, int64_t *indices, double *data);
 
 int64_t orc_max_threads(void);
+void orc_set_threads(int64_t n);
 
 #ifdef __cplusplus
 }

@@ -35,14 +35,34 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_native = False
+
+
+def use_native_build():
+    """The timed CPU baseline (bench.py only): -O3 -march=native, compiled ON THE BOX that runs it
+    (the shipped checker build is portable code).  Must be called before the first lib()."""
+    global _native
+    if _lib is not None and not _native:
+        raise RuntimeError("oracle already loaded with the checker build")
+    _native = True
 
 
 def lib():
     global _lib
     if _lib is not None:
         return _lib
-    build()
-    L = C.CDLL(_LIB_PATH)
+    if _native:
+        path = os.path.join(_HERE, "_build", "libbs2e_oracle_native.so")
+        tag = path + ".host"
+        host = open("/proc/cpuinfo").read().split("flags")[1].split("\n")[0] if os.path.exists("/proc/cpuinfo") else ""
+        if not os.path.exists(path) or not os.path.exists(tag) or open(tag).read() != host or \
+                os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "bs2e_oracle.c")):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "native"], stdout=subprocess.DEVNULL)
+            open(tag, "w").write(host)
+        L = C.CDLL(path)
+    else:
+        build()
+        L = C.CDLL(_LIB_PATH)
     vp = C.c_void_p
     sig = {
         "orc_generate_grid": (i64, [i64, i64, i64, f64, f64, _pd, i64]),
@@ -79,6 +99,7 @@ def lib():
                                                  i64, _pi, _pi, _pd,
                                                  i64, _pi, _pi, _pd, _pi]),
         "orc_max_threads": (i64, []),
+        "orc_set_threads": (None, [i64]),
         "orc_three_j": (f64, [i64] * 6),
         "orc_setup_radial_dip": (C.c_int, [vp, i64, C.c_int, vp, vp]),
         "orc_dip_block": (i64, [vp, C.c_int, vp, vp, _pd, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi,

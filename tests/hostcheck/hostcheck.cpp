@@ -152,7 +152,7 @@ int hc_block_count(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
         long long accH = 1, accS = 1;
         for (int idx = 0; idx < pl.nrows; ++idx) {
             long long h, s;
-            row_count(c->hg.g, pl, pl.rows[idx], &h, &s);
+            row_count(c->hg.g, pl, row_of_local(pl.rr, idx), &h, &s);
             H_ptr[idx] = accH;
             S_ptr[idx] = accS;
             accH += h;
@@ -181,7 +181,7 @@ int hc_block_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
         const OneBody ob{c->Hb.data(), c->Sb.data()};
         const double* R = c->R.data();
         for (int wrow = 0; wrow < pl.nrows; ++wrow) {
-            const long long i = pl.rows[wrow];
+            const long long i = row_of_local(pl.rr, wrow);
             const RowInfo r = row_info(pl, (int)i);
             long long hpos = H_ptr[wrow] - 1, spos = S_ptr[wrow] - 1;
             for_each_chunk(g, pl, r, [&](int bj, int nc, const Segment& s, const Coupling& cp, int base, int hi) {
@@ -259,7 +259,7 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
     const int nsites = (int)hp_.site_key.size();
     long long rows_seen = 0;
     for (int sidx = 0; sidx < nsites; ++sidx) {
-        const unsigned key = hp_.site_key[sidx];
+        const unsigned key = (unsigned)(hp_.site_key[sidx] & 0xffffffffull);
         const bool wantX = site_wants_X(g, pl.max_nd, (int)(key >> 16));
         if (wantX != (sidx < hp_.nsites_x)) throw std::logic_error("site filed in the wrong launch class");
         const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), wantX);
@@ -304,8 +304,14 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
             hp[(size_t)task * (ncmax + 1) + nnc] = (unsigned short)hrun;
             if (diag) sp[(size_t)bj * (ncmax + 1) + nnc] = (unsigned short)srun;   // site_count_kernel
         }
-        const int* srows = hp_.site_rows.data() + hp_.site_ptr[sidx];
-        const int nr = hp_.site_ptr[sidx + 1] - hp_.site_ptr[sidx];
+        // phase 0: the rows of the site, one per (l1,l2) group that holds (n_a,n_b) among the planned rows
+        std::vector<int> srows;
+        for (int bi = 0; bi < nblk; ++bi) {
+            const int row = config_index(g, pl, bi, s.na, s.nb);
+            if (row > 0 && row_local_of(pl.rr, row) >= 0) srows.push_back(row);
+        }
+        const int nr = (int)srows.size();
+        if (nr != 1023 - (int)((hp_.site_key[sidx] >> 32) & 1023)) throw std::logic_error("site key row count");
         for (int g0 = 0; g0 < nr; g0 += G) {
             const int gr = std::min(G, nr - g0);
             // phase 3a
@@ -314,8 +320,8 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
                 ++rows_seen;
                 const RowInfo r = row_info(pl, rowi);
                 if (r.na != s.na || r.nb != s.nb) throw std::logic_error("row filed under the wrong site");
-                const long long wrow = pl.row_local[rowi - 1];
-                if (wrow < 0 || pl.rows[wrow] != rowi) throw std::logic_error("row map inconsistent");
+                const long long wrow = row_local_of(pl.rr, rowi);
+                if (wrow < 0 || row_of_local(pl.rr, (int)wrow) != rowi) throw std::logic_error("row map inconsistent");
                 rcache[ri] = RowC{H_ptr[wrow] - 1, S_ptr[wrow] - 1, r.bi, r.la, r.lb};
                 int run = 0, srun = 0;
                 for (int bj = 0; bj < nblk; ++bj) {
