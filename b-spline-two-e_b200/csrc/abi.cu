@@ -471,8 +471,7 @@ int bs2e_block_free(bs2e_block* b)
     return guarded("bs2e_block_free", [&] {
         if (!b) return;
         cudaSetDevice(b->ctx->device);
-        cudaStreamSynchronize(b->ctx->stream);
-        block_free(b);
+        block_free(b);   // stream-ordered on the context's stream: no host synchronisation
     });
 }
 

@@ -9,14 +9,17 @@ Metric: 2e matrix elements/s = sum_sym (nnz_H+nnz_S)
 divided by the time of stage C (count pass + CSR build + fill); the R^k
 integrals/s of stages A+B is reported beside it ("rk_integrals_per_s").
 
-  value : inputs resident in HBM, device time (CUDA events on the library's stream);
-          stage C goes through bs2e_blocks_run (count pass + scan + fill of every block,
-          consecutive blocks pipelined over internal streams)
-  roofline : the fill of each block alone on the stream, timed in extra passes after the
-          timed steps; algorithmic bytes = 24 B per stored element
+  value : configuration lists, one-particle matrices and R^k resident in HBM; device time
+          (CUDA events on the library's stream) of stage C = for every symmetry block the
+          PLAN (group structure, radial sites, count pass, scan -- built on the device, the
+          host reads the totals), the allocation of the CSR arrays and the fill; one block
+          at a time (the CSR of cfg4 is 159 GB), arrays recycled through the memory pool
+  roofline : the fill launches of every block bracketed by CUDA events inside the timed
+          steps; algorithmic bytes = 24 B per stored element
   e2e   : the same metric through the C ABI with HOST buffers
-          (bs2e_set_one_particle / bs2e_block_count / bs2e_block_fill with
-          pinned host arrays; H2D and D2H inside the timed region)
+          (bs2e_set_one_particle / bs2e_block_count / bs2e_block_fill; H2D and D2H inside
+          the timed region) -- into pinned arrays, and once into pageable arrays as the
+          Fortran caller allocates them
   --impl reference : the CPU oracle port of the reference path on the host cores
 
 N>1 (torchrun, one rank per GPU): strong scaling.  Every rank builds the R^k
@@ -44,7 +47,15 @@ for p in (ROOT, os.path.join(ROOT, "b-spline-two-e_b200")):
 
 METRIC = "2e matrix elements/s (R^k integrals/s alongside) on basis_setup two-electron path"
 UNIT = "matrix elements/s"
-DEFAULT_WORKLOAD = "cfg3"   # BASELINE.json configs[2]: largest config whose CSR output fits one GPU + host staging
+DEFAULT_WORKLOAD = "cfg4"   # BASELINE.json configs[3]: the largest configuration that runs on ONE GPU (block by block)
+# config.workload of both arms (sizes follow from the namelist; checked against the generated basis)
+WORKLOADS = {
+    "cfg1": "cfg1: k=8 n_b=96 k_GL=14 max_k=4 max_l_1p=3 max_L=2 n_sym=9 sum_n_config=129979",
+    "cfg2": "cfg2: k=7 n_b=105 k_GL=13 max_k=6 max_l_1p=3 max_L=2 n_sym=3 sum_n_config=91264",
+    "cfg3": "cfg3: k=8 n_b=206 k_GL=14 max_k=12 max_l_1p=6 max_L=4 n_sym=5 sum_n_config=501166",
+    "cfg4": "cfg4: k=8 n_b=307 k_GL=18 max_k=20 max_l_1p=10 max_L=8 n_sym=9 sum_n_config=2689060",
+    "cfg5": "cfg5: k=8 n_b=606 k_GL=23 max_k=30 max_l_1p=15 max_L=12 n_sym=13 sum_n_config=13493894",
+}
 
 
 def env_int(name, default):
@@ -151,23 +162,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if world == 1:
             return float(x)
         t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks = lambda x: reduce(x, dist.ReduceOp.MAX)
+    sum_over_ranks = lambda x: reduce(x, dist.ReduceOp.SUM)
 
     params = bs2e.CONFIGS[args.workload]
     setup = bs2e.BasisSetup(device=local, **params)
     S, H_vec, syms = setup.host_inputs()
+    if describe(args.workload, setup, syms) != WORKLOADS[args.workload]:
+        raise SystemExit(f"workload table out of date: {describe(args.workload, setup, syms)}")
     ctx = setup.open()
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -175,54 +184,56 @@ def run_ours(args):
     K1 = setup.p["max_k"] + 1
     n_rk = ctx.P * ctx.P * K1
 
-    # ---- untimed setup: device-resident inputs, plans, output arrays ----
+    # ---- untimed setup: the inputs of the path made resident in HBM ----
     ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(H_vec, S)
+    cfgs = [ctx.configs_upload(s) for s in syms]           # term%configs of every symmetry
     ranges = []
-    for s in syms:
+    for s, c in zip(syms, cfgs):
         if world == 1:
             ranges.append([(1, s.n_config)])
-        else:   # rows dealt by their first radial index (radial sites stay whole), balanced on
-                # the stored entries of the count pass
-            tmp = ctx.block_plan(s, full)
+        else:   # rows dealt by their first radial index (radial sites stay whole), balanced on the stored
+                # entries; the partition depends on the basis only and is computed once
+            tmp = ctx.block_plan(s, full, cfg=c)
             cH, cS = tmp.row_counts()
             tmp.free()
             mine = site_partition(s.conf_n, cH + cS, world, setup.k, exchange_cost(setup.p['max_k']))[rank]
             if not mine:
                 raise SystemExit(f"rank {rank}: empty share of block L={s.l} (more GPUs than radial indices)")
             ranges.append(mine)
-    blocks = [ctx.block_plan(s, full, ranges=r) for s, r in zip(syms, ranges)]
-    for b in blocks:
-        b.assemble()            # allocates the CSR fragment on the device
     ctx.sync()
-    my_elems = sum(b.nnz_H + b.nnz_S for b in blocks)
-    total_elems = sum_over_ranks(my_elems)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def ev():
-        return torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    elems_of_step = [0]
 
     def one_step(rec):
+        """stage A, stage B, then stage C block by block: plan (device-built, the host reads the totals),
+        allocation of the CSR arrays from the pool, fill, release"""
         with torch.cuda.stream(stream):
             flush.zero_()                                   # evict L2 between timed iterations
-            e0 = ev(); e0.record(stream)
+            e0 = ev()
             ctx.slater_cells()
-            ea = ev(); ea.record(stream)
+            ea = ev()
             ctx.rk_build()
-            e1 = ev(); e1.record(stream)
-            ctx.blocks_run(blocks, recount=True)            # count pass + scan + fill of every block
-            e2 = ev(); e2.record(stream)
+            e1 = ev()
+            per_block, el = [], 0
+            for s, c, r in zip(syms, cfgs, ranges):
+                blk = ctx.block_plan(s, full, ranges=r, cfg=c)
+                f0 = ev()
+                blk.assemble()                              # the two concurrent site_fill_kernel launches
+                f1 = ev()
+                n = blk.nnz_H + blk.nnz_S
+                per_block.append((f0, f1, n, blk.nnz_H, blk.nnz_S, blk.nrows))
+                blk.free()                                  # stream-ordered: the pool hands the pages to the next block
+                el += n
+            e2 = ev()
+        elems_of_step[0] = el
         if rec is not None:
-            rec.append((e0, ea, e1, e2))
-
-    def fill_only_step(rec):
-        """the fill of each block timed on its own (roofline of the dominant kernel)"""
-        with torch.cuda.stream(stream):
-            flush.zero_()
-            for b in blocks:
-                f0 = ev(); f0.record(stream)
-                b.assemble()                                # the two concurrent site_fill_kernel launches
-                f1 = ev(); f1.record(stream)
-                rec.append((f0, f1))
+            rec.append((e0, ea, e1, e2, per_block))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -243,17 +254,12 @@ def run_ours(args):
     launches = bs2e.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # separate pass: every block's fill alone on the stream (per-launch duration for the roofline)
-    frec = []
-    n_fill_steps = max(1, min(args.steps, 5))
-    for _ in range(n_fill_steps):
-        fill_only_step(frec)
-    barrier()
-
-    tA = sum(e0.elapsed_time(ea) for e0, ea, e1, e2 in rec)
-    tB = sum(ea.elapsed_time(e1) for e0, ea, e1, e2 in rec)
-    tC = sum(e1.elapsed_time(e2) for e0, ea, e1, e2 in rec)
-    fill_ms = [f0.elapsed_time(f1) for f0, f1 in frec]
+    my_elems = elems_of_step[0]
+    total_elems = sum_over_ranks(my_elems)
+    tA = sum(r[0].elapsed_time(r[1]) for r in rec)
+    tB = sum(r[1].elapsed_time(r[2]) for r in rec)
+    tC = sum(r[2].elapsed_time(r[3]) for r in rec)
+    fill_ms = [q[0].elapsed_time(q[1]) for r in rec for q in r[4]]
     tA, tB, tC = max_over_ranks(tA), max_over_ranks(tB), max_over_ranks(tC)
     wall = max_over_ranks(wall)
     K = args.steps
@@ -262,8 +268,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (site_fill_kernel), this rank ----
     fill_total_ms = sum(fill_ms)
-    n_fill = n_fill_steps * len(blocks)
-    alg_bytes_per_launch = 24.0 * my_elems / len(blocks)       # 16 B data + 8 B index per element
+    n_fill = len(fill_ms)
+    alg_bytes_per_launch = 24.0 * my_elems / len(syms)         # 16 B data + 8 B index per element
     avg_fill_ms = fill_total_ms / n_fill
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_per_launch / (avg_fill_ms * 1e-3) / 1e9
@@ -271,20 +277,23 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_fill_ms,
-                "timed": f"{n_fill_steps} extra passes after the timed steps, each block's fill alone on the stream "
-                         "(a launch = the two concurrent site_fill_kernel launches of one symmetry block); in the timed "
-                         "steps the blocks are pipelined over three stream pairs (bs2e_blocks_run)",
-                "share_of_stage_C": (fill_total_ms / n_fill_steps) / max(tC / K, 1e-9),
-                # the same bytes over the whole timed stage C (count pass, scans and launch gaps included)
+                "timed": "CUDA events around the fill of every block inside the timed steps (a launch = the two "
+                         "concurrent site_fill_kernel launches of one symmetry block; the stream is idle when they start)",
+                "share_of_stage_C": (fill_total_ms / K) / max(tC / K, 1e-9),
+                # the same bytes over the whole timed stage C (plans, count passes, scans, allocation included)
                 "achieved_over_timed_stage_C": 24.0 * my_elems * K / (tC * 1e-3) / 1e9,
                 "frac_over_timed_stage_C": 24.0 * my_elems * K / (tC * 1e-3) / 1e9 / peak,
+                "per_block_frac": [24.0 * q[2] / (q[0].elapsed_time(q[1]) * 1e-3) / 1e9 / peak for q in rec[-1][4]],
                 "rk_build": {"achieved": 8.0 * n_rk * K / (tB * 1e-3) / 1e9, "unit": "GB/s",
                              "frac": 8.0 * n_rk * K / (tB * 1e-3) / 1e9 / peak, "bound": "hbm"}}
+
+    fp64 = fp64_peak(torch) if rank == 0 and not args.no_fp64_peak else None
 
     # ---- e2e: through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, bs2e, ctx, setup, syms, ranges, blocks, S, H_vec, world, barrier,
+        sizes = [(q[5], q[3], q[4]) for q in rec[-1][4]]        # (rows, nnz_H, nnz_S) of this rank's share of every block
+        e2e = run_e2e(args, bs2e, ctx, setup, syms, ranges, sizes, S, H_vec, world, barrier,
                       max_over_ranks, total_elems, n_rk)
 
     cpu_base = None
@@ -296,26 +305,56 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": wall * 1e3 / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: " + describe(args.workload, setup, syms),
+            "config": {"workload": WORKLOADS[args.workload],
                        "elements_per_step": total_elems, "rk_integrals_per_step": n_rk,
+                       "stage_C": "per symmetry block: device-built plan + count pass + scan (host reads the totals), "
+                                  "CSR arrays from the memory pool, fill, release; one block at a time",
                        "l2": "256 MiB buffer written between timed iterations; R^k and CSR output exceed L2",
                        "parallelism": "R^k replicated per GPU, rows of every symmetry block dealt by first radial index (radial sites stay whole), no collective" if world > 1 else "single GPU"},
-            "stage_ms_per_step": {"A_cells": tA / K, "B_rk": tB / K, "C_blocks": tC / K},
+            "stage_ms_per_step": {"A_cells": tA / K, "B_rk": tB / K, "C_blocks": tC / K,
+                                  "C_fill_only": fill_total_ms / K},
             "rk_integrals_per_s": rk_per_s,
+            "whole_step_elements_per_s": total_elems * K / ((tA + tB + tC) * 1e-3),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_base,
+            "fp64_peak": fp64, "cpu_baseline": cpu_base,
         }
         print(json.dumps(out))
-    for b in blocks:
-        b.free()
+    for c in cfgs:
+        c.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def fp64_peak(torch, seconds=2.0):
+    """cuBLAS DGEMM 8192^3 on this box (BASELINE.md section 2 asks for the FP64 denominator): best single
+    call and back-to-back sustained rate"""
+    n = 8192
+    a = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    b = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(3):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    reps = max(3, int(seconds / (2.0 * n ** 3 / (best * 1e12))))
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record(); torch.cuda.synchronize()
+    return {"what": "cuBLAS DGEMM 8192^3 (torch.matmul float64)", "burst_tflops": best,
+            "sustained_tflops": 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12, "sustained_reps": reps,
+            "dmma_issue_peak_tflops": 148 * 0.25 * 512 * 1.965e9 / 1e12,
+            "note": "mma.sync.m8n8k4.f64 issues at 0.25 per cycle per SM (scripts/microbench/dmma_probe.cu)"}
+
+
 def describe(name, setup, syms):
     p = setup.p
-    return (f"k={p['k']} n_b={setup.n_b} k_GL={p['k_GL']} max_k={p['max_k']} max_l_1p={p['max_l_1p']} "
+    return (f"{name}: k={p['k']} n_b={setup.n_b} k_GL={p['k_GL']} max_k={p['max_k']} max_l_1p={p['max_l_1p']} "
             f"max_L={p['max_L']} n_sym={len(syms)} sum_n_config={sum(s.n_config for s in syms)}")
 
 
@@ -346,19 +385,19 @@ class PinnedArrays:
         self.ptrs = []
 
 
-def run_e2e(args, bs2e, ctx, setup, syms, ranges, blocks, S, H_vec, world, barrier,
+def run_e2e(args, bs2e, ctx, setup, syms, ranges, sizes, S, H_vec, world, barrier,
             max_over_ranks, total_elems, n_rk):
-    """Same step through the reference-facing calls with host buffers."""
+    """Same step through the reference-facing calls with host buffers.  One set of destination arrays sized
+    for the largest block is reused for every block (the consumer -- block_diag_CS%store -- takes a block
+    before the next one is built; the CSR of cfg4 is 159 GB, more than the host can pin)."""
     full = setup.p["full"]
-    nr = max(b.nrows for b in blocks)
-    mH = max(b.nnz_H for b in blocks)
-    mS = max(b.nnz_S for b in blocks)
-    pin = PinnedArrays(bs2e, nr, mH, mS)
-    h2d = d2h = 0
+    nr = max(q[0] for q in sizes)
+    mH = max(q[1] for q in sizes)
+    mS = max(q[2] for q in sizes)
     steps = max(1, min(args.steps, args.e2e_steps))
+    counted = {"h2d": 0, "d2h": 0}
 
-    def step(count_bytes):
-        nonlocal h2d, d2h
+    def step(arrs, count_bytes):
         t0 = time.perf_counter()
         ctx.slater_cells()
         ctx.rk_build()
@@ -366,136 +405,172 @@ def run_e2e(args, bs2e, ctx, setup, syms, ranges, blocks, S, H_vec, world, barri
         t1 = time.perf_counter()
         ctx.set_one_particle(H_vec, S)                      # H2D: one-particle matrices
         if count_bytes:
-            h2d += sum(h.nbytes for h in H_vec) + S.nbytes
-        for s, r, b in zip(syms, ranges, blocks):
-            n = sum(hi - lo + 1 for lo, hi in r)
-            out = tuple(a[:m] for a, m in zip(pin.arrs, (n + 1, max(b.nnz_H, 1), 2 * max(b.nnz_H, 1),
-                                                         n + 1, max(b.nnz_S, 1), 2 * max(b.nnz_S, 1))))
+            counted["h2d"] += sum(h.nbytes for h in H_vec) + S.nbytes
+        for s, r, (n, nH, nS) in zip(syms, ranges, sizes):
+            out = tuple(a[:m] for a, m in zip(arrs, (n + 1, max(nH, 1), 2 * max(nH, 1),
+                                                     n + 1, max(nS, 1), 2 * max(nS, 1))))
             if world == 1:
-                nnz = ctx.block_count(s, full)              # H2D configs + count pass
-                ctx.block_fill(s, full, nnz, out=out)       # fill + D2H into pinned host arrays
+                nnz = ctx.block_count(s, full)              # H2D configs + device plan + count pass
+                ctx.block_fill(s, full, nnz, out=out)       # fill + D2H into the caller's arrays
             else:
                 blk = ctx.block_plan(s, full, ranges=r)
                 blk.assemble()
                 blk.download(out=out)
                 blk.free()
             if count_bytes:
-                h2d += s.conf_n.nbytes + s.conf_l.nbytes
-                d2h += 2 * 8 * (n + 1) + 24 * (b.nnz_H + b.nnz_S)
+                counted["h2d"] += s.conf_n.nbytes + s.conf_l.nbytes
+                counted["d2h"] += 2 * 8 * (n + 1) + 24 * (nH + nS)
         ctx.sync()
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1
 
-    step(False)                                             # warm-up (page-locks, caches)
+    pin = PinnedArrays(bs2e, nr, mH, mS)
+    step(pin.arrs, False)                                   # warm-up (page-locks, caches)
     barrier()
     tAB = tC = 0.0
     for _ in range(steps):
-        a, c = step(True)
+        a, c = step(pin.arrs, True)
         tAB += a
         tC += c
     barrier()
     tC = max_over_ranks(tC)
     tAB = max_over_ranks(tAB)
     pin.free()
-    return {"value": total_elems * steps / tC, "unit": UNIT, "steps": steps,
-            "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
-            "ms_per_step_stage_C": tC * 1e3 / steps,
-            "rk_integrals_per_s": n_rk * steps / tAB,
-            "api": "bs2e_set_one_particle + bs2e_block_count + bs2e_block_fill (pinned host arrays)"
-                   if world == 1 else "bs2e_block_plan_ranges + assemble + download (pinned host arrays)"}
+    out = {"value": total_elems * steps / tC, "unit": UNIT, "steps": steps,
+           "h2d_bytes_per_step": counted["h2d"] // steps, "d2h_bytes_per_step": counted["d2h"] // steps,
+           "ms_per_step_stage_C": tC * 1e3 / steps,
+           "d2h_gb_per_s": counted["d2h"] / steps / (tC / steps) / 1e9,
+           "rk_integrals_per_s": n_rk * steps / tAB,
+           "destination": "pinned host arrays (bs2e_host_alloc), sized for the largest block and reused",
+           "api": "bs2e_set_one_particle + bs2e_block_count + bs2e_block_fill"
+                  if world == 1 else "bs2e_block_plan_ranges + assemble + download"}
+    if not args.no_pageable:
+        # the Fortran caller's arrays (H_sp%init, sparse_array_tools.f90:557-569) are ordinary pageable
+        # memory: the library stages such downloads through its pinned ring (csrc/download.cu)
+        pag = (np.zeros(nr + 1, np.int64), np.zeros(max(mH, 1), np.int64), np.zeros(2 * max(mH, 1)),
+               np.zeros(nr + 1, np.int64), np.zeros(max(mS, 1), np.int64), np.zeros(2 * max(mS, 1)))
+        for a in pag:
+            a.fill(0)                                       # init_CS zero-initialises: the pages exist
+        barrier()
+        _, c = step(pag, False)
+        barrier()
+        c = max_over_ranks(c)
+        out["pageable"] = {"value": total_elems / c, "unit": UNIT, "steps": 1, "ms_per_step_stage_C": c * 1e3,
+                           "destination": "pageable numpy arrays, as the reference caller allocates them"}
+        del pag
+    return out
 
 
 # ---------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------
-def cpu_baseline(workload, budget_s=20.0, verbose=False):
-    """Times the oracle (a C port of the reference path, kind="port") on a
-    bounded sample of the workload.  Threads as in the reference: stage A over
-    k, stage B serial, stage C over symmetry blocks."""
-    from concurrent.futures import ThreadPoolExecutor
-    import bs2e
-    from oracle import bs2e_oracle as O
+class CpuArm:
+    """The oracle (a C port of the reference path, kind="port") on the host cores: -O3 -march=native build,
+    thread count set explicitly (a multi-rank launcher exports OMP_NUM_THREADS=1).  The tensors stage C reads are
+    prepared once (untimed, tabulated evaluation on all cores); stage A is timed reference-faithfully on a sample
+    of its outermost index, stage B in full (serial like the reference), stage C on row samples."""
 
-    p = O.basis_params(**bs2e.CONFIGS[workload])
-    threads = int(O.lib().orc_max_threads())
-    run = O.OracleRun(**p)
-    K1 = p["max_k"] + 1
-    P = run.bs.num_pairs()
-    # untimed preparation: the tensors stage C reads (tabulated evaluation, all cores)
-    run.slater(tabulate=1, par_mode=1)
-    t0 = time.perf_counter()
-    run.rk_map()                                             # stage B, serial like the reference
-    tB = time.perf_counter() - t0
-    # stage A, reference-faithful evaluation on a sample of the outermost index
-    nnz6 = run.s6.nnz
-    est_full = nnz6 * K1 / 40e3 / min(threads, K1)           # ~40k values/s/thread
-    jp_step = max(1, int(np.ceil(est_full / (0.4 * budget_s))))
-    t0 = time.perf_counter()
-    _, done = O.time_Slater_diag_sample(run.bs, p["max_k"], p["k_GL"], jp_step)
-    tA_s = time.perf_counter() - t0
-    tA = tA_s * (nnz6 * K1) / max(done, 1)
-    rk_per_s = P * P * K1 / (tA + tB)
-    # stage C on evenly spaced row chunks of every symmetry block
-    run.one_particle()
-    syms = run.basis()
-    frac = None
-    per_row_s = 5.5e-4 * (sum(s.n_config for s in syms) / len(syms)) / 1e5   # rough: scan cost grows with n
-    tot_rows = sum(s.n_config for s in syms)
-    est = per_row_s * tot_rows / min(threads, len(syms))
-    frac = min(1.0, (0.5 * budget_s) / max(est, 1e-9))
-    chunk = 16
+    def __init__(self, workload, budget_s=20.0):
+        import bs2e
+        from oracle import bs2e_oracle as O
+        self.O, self.workload = O, workload
+        O.use_native_build()
+        self.threads = int(os.environ.get("BS2E_CPU_THREADS", os.cpu_count() or 1))
+        O.lib().orc_set_threads(self.threads)
+        p = self.p = O.basis_params(**bs2e.CONFIGS[workload])
+        run = self.run = O.OracleRun(**p)
+        K1 = p["max_k"] + 1
+        P = run.bs.num_pairs()
+        run.slater(tabulate=1, par_mode=1)                      # untimed preparation
+        t0 = time.perf_counter()
+        run.rk_map()                                             # stage B, serial like the reference
+        self.tB = time.perf_counter() - t0
+        nnz6 = run.s6.nnz
+        est_full = nnz6 * K1 / 40e3 / min(self.threads, K1)      # ~40k values/s/thread
+        self.jp_step = max(1, int(np.ceil(est_full / (0.25 * budget_s))))
+        t0 = time.perf_counter()
+        _, done = O.time_Slater_diag_sample(run.bs, p["max_k"], p["k_GL"], self.jp_step)
+        self.tA_s = time.perf_counter() - t0
+        self.tA = self.tA_s * (nnz6 * K1) / max(done, 1)
+        self.rk_per_s = P * P * K1 / (self.tA + self.tB)
+        run.one_particle()
+        self.syms = run.basis()
+        # calibration of the row cost (count_nnz + construct_block_tensor scan the whole configuration list per row)
+        big = max(self.syms, key=lambda q: q.n_config)
+        t0 = time.perf_counter()
+        self._rows(big, [(big.n_config // 2, big.n_config // 2 + 3)])
+        self.row_s_per_config = (time.perf_counter() - t0) / 4 / big.n_config
 
-    def sample_rows(n):
-        nch = max(1, int(round(frac * n / chunk)))
-        starts = np.linspace(1, max(1, n - chunk + 1), nch).astype(int)
-        return [(int(a), int(min(n, a + chunk - 1))) for a in starts]
-
-    def work(s):
-        el = 0
-        for lo, hi in sample_rows(s.n_config):
-            cap = O.count_nnz(run.bs.k, s, p["max_k"], p["full"], rows=(lo, hi))   # count_nnz scan
-            _, _, em = run.block(s, rows=(lo, hi), nnz=cap)                          # construct_block_tensor
+    def _rows(self, s, chunks):
+        O, p, el = self.O, self.p, 0
+        for lo, hi in chunks:
+            cap = O.count_nnz(self.run.bs.k, s, p["max_k"], p["full"], rows=(lo, hi))   # count_nnz scan
+            _, _, em = self.run.block(s, rows=(lo, hi), nnz=cap)                          # construct_block_tensor
             el += em[0] + em[1]
         return el
 
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=min(threads, len(syms))) as ex:
-        elems = sum(ex.map(work, syms))
-    tC = time.perf_counter() - t0
-    value = elems / tC
-    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-            "rk_integrals_per_s": rk_per_s,
-            "sample": (f"{workload}: stage C on {frac * 100:.2f}% of the rows of every symmetry block "
-                       f"(evenly spaced {chunk}-row chunks, count_nnz + construct_block_tensor, "
-                       f"{min(threads, len(syms))} threads over blocks, {tC:.1f} s); stage A on every "
-                       f"{jp_step}-th outer index ({tA_s:.1f} s, extrapolated to {tA:.0f} s), stage B full ({tB:.1f} s). "
-                       "The port memoises the 3j/6j factors and indexes R^k directly, so it is faster than the Fortran."),
-            "omp_num_threads": os.environ.get("OMP_NUM_THREADS", "unset"), "cpu_count": os.cpu_count()}
+    def stage_C_sample(self, budget_s):
+        from concurrent.futures import ThreadPoolExecutor
+        syms, chunk = self.syms, 8
+        est = sum(self.row_s_per_config * s.n_config * s.n_config for s in syms) / self.threads
+        frac = min(1.0, budget_s / max(est, 1e-9))
+        tasks = []
+        for s in syms:
+            n = s.n_config
+            nch = max(1, int(round(frac * n / chunk)))
+            starts = np.linspace(1, max(1, n - chunk + 1), nch).astype(int)
+            tasks += [(s, [(int(a), int(min(n, a + chunk - 1)))]) for a in starts]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=self.threads) as ex:
+            elems = sum(ex.map(lambda t: self._rows(*t), tasks))
+        dt = time.perf_counter() - t0
+        if frac < 1.0:                                           # keep the next sample on its budget
+            self.row_s_per_config *= min(4.0, max(0.25, dt / budget_s))
+        return elems, dt, frac, chunk
+
+    def result(self, elems, dt, frac, chunk):
+        return {"value": elems / dt, "unit": UNIT, "cores": self.threads, "kind": "port",
+                "rk_integrals_per_s": self.rk_per_s,
+                "sample": (f"{self.workload}: stage C on {frac * 100:.3f}% of the rows of every symmetry block "
+                           f"(evenly spaced {chunk}-row chunks, count_nnz + construct_block_tensor, "
+                           f"chunks dealt to {self.threads} threads, {dt:.1f} s); stage A on every "
+                           f"{self.jp_step}-th outer index ({self.tA_s:.1f} s, extrapolated to {self.tA:.0f} s), "
+                           f"stage B full ({self.tB:.1f} s). The port memoises the 3j/6j factors and indexes R^k "
+                           "directly, so it is faster than the Fortran; built -O3 -march=native on this box."),
+                "omp_threads_set": self.threads, "cpu_count": os.cpu_count()}
+
+
+def cpu_baseline(workload, budget_s=20.0):
+    arm = CpuArm(workload, budget_s)
+    return arm.result(*arm.stage_C_sample(0.5 * budget_s))
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    per_step = max(5.0, args.cpu_budget)
-    vals, rks, last = [], [], None
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline(args.workload, budget_s=per_step / 2)
+    arm = CpuArm(args.workload, args.cpu_budget)            # preparation once, not per step
+    per_step = max(0.5, min(0.5 * args.cpu_budget, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        arm.stage_C_sample(per_step)
+    vals, last = [], None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        last = cpu_baseline(args.workload, budget_s=per_step)
-        vals.append(last["value"]); rks.append(last["rk_integrals_per_s"])
+        last = arm.stage_C_sample(per_step)
+        vals.append(last[0] / last[1])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    last["value"] = v
+    cb = arm.result(*last)
+    cb["value"] = v
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": wall * 1e3 / args.steps,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": args.workload},
-           "rk_integrals_per_s": float(np.mean(rks)), "cpu_baseline": last,
+           "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]},
+           "rk_integrals_per_s": arm.rk_per_s, "cpu_baseline": cb,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0,
-           "note": "reference cannot be built here (no Fortran compiler); the C oracle port is timed instead"}
+           "note": "reference cannot be built here (no Fortran compiler); the C oracle port is timed instead; "
+                   "a step = one bounded row sample of stage C (the value), stage A/B timed once"}
     print(json.dumps(out))
 
 
@@ -510,6 +585,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-destination pass of the e2e leg")
+    ap.add_argument("--no-fp64-peak", action="store_true", help="skip the cuBLAS DGEMM measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

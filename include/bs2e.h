@@ -153,6 +153,8 @@ int bs2e_block_download(bs2e_block *blk, int64_t *H_ptr, int64_t *H_idx, double 
 /* 64-bit checksums of the device-resident fragment (indices and raw data
  * bits), for runs whose output is too large to bring to the host.           */
 int bs2e_block_checksum(bs2e_block *blk, uint64_t *sum_H, uint64_t *sum_S);
+/* Releases the fragment and the plan; the device memory goes back to the pool in stream order
+ * (after the work already queued on the context's stream), the call does not wait for the device. */
 int bs2e_block_free(bs2e_block *blk);
 
 /* Pinned host memory for callers that want full-speed transfers; the pages are

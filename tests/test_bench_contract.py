@@ -18,7 +18,7 @@ def _run(*args, env=None):
 
 
 def test_reference_arm_json_line():
-    r = _run("--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0", "--cpu-budget", "5")
+    r = _run("--impl", "reference", "--workload", "cfg1", "--steps", "2", "--warmup", "1", "--cpu-budget", "5")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -28,9 +28,10 @@ def test_reference_arm_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "cfg1" in cb["sample"] and cb["value"] == d["value"]
+    assert d["steps"] == 2 and d["warmup"] == 1 and cb["omp_threads_set"] == cb["cores"]
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert key in d
-    assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["config"]["workload"] == "cfg1"
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["config"]["workload"].startswith("cfg1: k=8 n_b=96")
 
 
 def test_reference_arm_other_ranks_exit_quietly():
