@@ -27,6 +27,7 @@
 #include "plan.h"
 #include "site_core.h"
 #include "dev_async.h"
+#include "site_mma.h"
 
 namespace bs2e {
 
@@ -909,14 +910,15 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
             throw Error("block_assemble: site tables exceed shared memory (max_l_1p above the planned bound)");
         // the launch without exchange windows goes to the side stream so that it fills
         // the SMs the other launch leaves idle in its last wave
-        const bool fork = b->nsites_x > 0 && b->nsites_x < b->nsites;
+        const bool fork = b->nsites_x > 0 && b->nsites_x < b->nsites && !getenv("BS2E_NOFORK");   // BS2E_NOFORK: A/B measurements
         if (fork) {
             BS2E_CUDA(cudaEventRecord(bs.fork, bs.main));
             BS2E_CUDA(cudaStreamWaitEvent(bs.side, bs.fork, 0));
         }
         cudaStream_t stD = fork ? bs.side : bs.main;
         const int nx = b->nsites_x, nd = b->nsites - b->nsites_x;
-        switch (kmax) {
+        if (b->use_mma) launch_site_mma(b, bs.main, stD);
+        else switch (kmax) {
         case 7: launch_site_fill<7, true>(b, layX, bs.main, 0, nx); launch_site_fill<7, false>(b, layD, stD, nx, nd); break;
         case 13: launch_site_fill<13, true>(b, layX, bs.main, 0, nx); launch_site_fill<13, false>(b, layD, stD, nx, nd); break;
         case 21: launch_site_fill<21, true>(b, layX, bs.main, 0, nx); launch_site_fill<21, false>(b, layD, stD, nx, nd); break;

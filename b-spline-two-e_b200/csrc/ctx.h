@@ -199,6 +199,7 @@ struct bs2e_block {
     int site_cap = 0;
     int nsites = 0, nsites_x = 0;
     bool use_site = false;               // site kernels (else: row-wise fallback with per-row tables)
+    bool use_mma = false;                // tensor-core site kernel (site_mma.cu); else the FMA site kernel of block.cu
     // CSR fragment (device)
     long long *d_cntH = nullptr, *d_cntS = nullptr;  // [nrows+1] counts
     long long *d_Hptr = nullptr, *d_Sptr = nullptr;  // [nrows+1] 1-based

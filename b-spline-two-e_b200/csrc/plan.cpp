@@ -77,14 +77,21 @@ AngTables build_ang_tables(const std::vector<BlockDesc>& blocks, int L, int K1)
             }
             t.flags[o] = (unsigned char)f;
             t.krange[o] = kr;
-            // the same factors packed by multipole parity for the site kernel
+            // the same factors packed by multipole parity for the site kernels.  A window whose pattern flag
+            // is off contributes nothing (hamiltonian.f90:174,183: no factor above 5e-15; with exact 3j/6j
+            // arithmetic such a window has no non-zero factor at all): its half stays zero, so the site
+            // kernels add both windows' sums without looking at the flags.
             if (nkp > 0) {
                 const int pd = (la + lc) & 1, px = (la + ld) & 1;
                 for (int k = 0; k < K1; ++k) {
+                    if (!(f & kDirAny) && bi != bj) continue;
                     if (t.angD[o * K1 + k] != 0.0) {
                         if ((k ^ pd) & 1) throw std::logic_error("block_plan: direct factor off parity");
                         t.angP[o * 2 * nkp + (k - pd) / 2] = t.angD[o * K1 + k];
                     }
+                }
+                for (int k = 0; k < K1; ++k) {
+                    if (!(f & kExAny)) continue;
                     if (t.angX[o * K1 + k] != 0.0) {
                         if ((k ^ px) & 1) throw std::logic_error("block_plan: exchange factor off parity");
                         t.angP[o * 2 * nkp + nkp + (k - px) / 2] = t.angX[o * K1 + k];
@@ -111,6 +118,18 @@ AngTables build_ang_tables(const std::vector<BlockDesc>& blocks, int L, int K1)
         for (auto& th : pool) th.join();
         for (auto& e : errs)
             if (!e.empty()) throw std::logic_error(e);
+    }
+    for (int bi = 0; bi < nblk; ++bi) {
+        int c = 0;
+        for (int bj = 0; bj < nblk; ++bj) c += bj == bi || t.flags[(size_t)bi * nblk + bj] != 0;
+        t.maxc = std::max(t.maxc, c);
+    }
+    {   // records a site can hold per multipole parity (wigner_tools.f90:131: parity of l_a + l_c)
+        int cnt[2] = {0, 0};
+        for (int bi = 0; bi < nblk; ++bi)
+            for (int bj = 0; bj < nblk; ++bj)
+                if (bj != bi && t.flags[(size_t)bi * nblk + bj] != 0) ++cnt[(blocks[bi].l1 + blocks[bj].l1) & 1];
+        t.maxrec = std::max(cnt[0], cnt[1]);
     }
     return t;
 }

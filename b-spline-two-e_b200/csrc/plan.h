@@ -12,6 +12,8 @@ namespace bs2e {
 // with the thresholds of hamiltonian.f90:174 (pattern) and mat_els.f90:568 (sum) folded in
 struct AngTables {
     int nblk = 0, K1 = 0, nkp = 0;
+    int maxc = 0;                      // most column groups any row group couples to (its own included)
+    int maxrec = 0;                    // most off-diagonal (row group, column group) pairs of one multipole parity
     std::vector<unsigned char> flags;  // [nblk][nblk]
     std::vector<KRange> krange;        // [nblk][nblk]
     std::vector<double> angD, angX;    // [nblk][nblk][K1]

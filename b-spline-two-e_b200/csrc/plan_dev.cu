@@ -22,6 +22,7 @@
 
 #include "ctx.h"
 #include "site_core.h"
+#include "site_mma.h"
 
 namespace bs2e {
 
@@ -322,6 +323,15 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     const int site_cap = hg.nb * std::max(1, max_nd);
     b->site_cap = site_cap;
     b->use_site = site_kernel_usable(c, nblk, b->lmax);
+    {   // Two site kernels fill the same CSR arrays: the tensor-core kernel (site_mma.cu) and the FMA kernel
+        // (block.cu).  Measured on B200 (scripts/fill_ab.py, profiles/r02_fill_ab.txt) the tensor-core kernel is
+        // ahead for 8..13 multipoles per parity list (cfg2, cfg3: -10 % time), the FMA kernel by 3-4 % for 21 and
+        // more (cfg4, cfg5) and on the small sites of cfg1.  BS2E_FILL=mma / fma forces one of them.
+        const char* mode = getenv("BS2E_FILL");
+        const bool want = mode ? strcmp(mode, "mma") == 0 : site_kmax_for(hg.K1) == 13;
+        b->use_mma = b->use_site && want && !(mode && strcmp(mode, "fma") == 0) &&
+                     site_mma_usable(c, nblk, b->ang->host.maxc, b->ang->host.maxrec, b->lmax);
+    }
     size_t scan_tmp = 0, sort_tmp = 0;
     BS2E_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, scan_tmp, (long long*)nullptr, (long long*)nullptr, cub::Sum(), 1LL,
                                              (long long)nrows + 1, st));   // same index type as block_count_scan

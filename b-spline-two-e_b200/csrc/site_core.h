@@ -359,6 +359,109 @@ BS2E_HD void site_diag_terms(const Geom& g, const Plan& pl, const SiteOneBody& s
     Sdat[2 * pos + 1] = sv.im;
 }
 
+// ---- tensor-core site kernel (site_mma.cu): bit masks over the candidate list ---------------
+// The candidates of a site are cut into SEGMENTS of 32; which candidates a (column group,
+// storage mode) pair stores is one 32-bit mask per segment plus the number of stored entries
+// before the segment, so that a thread finds "stored?" and the rank of its candidate with one
+// 8-byte load, an AND and a population count -- for any record, without per-mode arithmetic.
+constexpr int kSegCand = 32;
+struct alignas(8) MaskWord { unsigned mask, pre; };
+
+// one n_c slot of the candidate list: index of its first candidate and the n_d values it holds
+struct CandSlot { int base; Union2 u; };
+BS2E_HD CandSlot cand_slot(const Site& s, const int* cprefix, bool wantX, int q)
+{
+    CandSlot c;
+    if (wantX) {
+        c.base = cprefix[q];
+        c.u = site_nd_union(s, site_nc(s, q));
+    } else {
+        c.base = q * s.dw;
+        c.u = union2(s.dDlo, s.dDhi, 0, -1);
+    }
+    return c;
+}
+// candidate index of n_d inside the slot (n_d must belong to the slot's union)
+BS2E_HD int cand_index(const CandSlot& c, int nd)
+{
+    const int len0 = c.u.hi[0] - c.u.lo[0] + 1;
+    return c.base + ((c.u.n == 2 && nd > c.u.hi[0]) ? len0 + nd - c.u.lo[1] : nd - c.u.lo[0]);
+}
+// candidates t0..t1 (inclusive) as (segment, bits) pieces: orfn(segment, bits)
+template <class F>
+BS2E_HD void mask_range(int t0, int t1, F&& orfn)
+{
+    for (int seg = t0 / kSegCand; seg <= t1 / kSegCand; ++seg) {
+        const int a = imax(t0, seg * kSegCand) - seg * kSegCand, b = imin(t1, seg * kSegCand + kSegCand - 1) - seg * kSegCand;
+        const unsigned bits = (b - a == 31) ? 0xffffffffu : (((1u << (b - a + 1)) - 1u) << a);
+        orfn(seg, bits);
+    }
+}
+// the direct / exchange intervals of a clipped slot entry as candidate ranges: fd(t0,t1), fx(t0,t1)
+template <class FD, class FX>
+BS2E_HD void entry_cand_ranges(const CandSlot& c, const SiteEntry& e, FD&& fd, FX&& fx)
+{
+    if ((int)e.dhi >= (int)e.dlo) fd(cand_index(c, e.dlo), cand_index(c, e.dhi));
+    if ((int)e.xhi >= (int)e.xlo) fx(cand_index(c, e.xlo), cand_index(c, e.xhi));
+}
+BS2E_HD bool mask_has(const MaskWord& w, int bit) { return (w.mask >> bit) & 1u; }
+BS2E_HD int mask_rank(const MaskWord& w, int bit) { return (int)w.pre + popc32(w.mask & ((1u << bit) - 1u)); }
+
+// record of the tensor-core kernel: one (row, column group) pair of the site
+struct alignas(16) MmaRec {
+    long long hpos;       // 0-based position of the pair's first H entry
+    int cf;               // index of the pair's packed factors, bi*nblk + bj (-1: padding)
+    unsigned short tbl;   // row of the mask table
+    unsigned char bj;     // column group (row of the jbase table)
+    unsigned char ri;     // row of the group (diagonal pairs)
+};
+// rows of the mask table: (column group, mode) first, then the H and S masks of the diagonal pair of
+// each row of the group, then one all-zero row for padding records
+BS2E_HD int mask_modes(bool wantX) { return wantX ? 3 : 1; }
+BS2E_HD int mask_rows(int nblk, int G, bool wantX) { return nblk * mask_modes(wantX) + 2 * G + 1; }
+BS2E_HD int mask_row_pair(int bj, int mode, bool wantX) { return wantX ? bj * 3 + mode : bj; }
+BS2E_HD int mask_row_diagH(int nblk, int ri, bool wantX) { return nblk * mask_modes(wantX) + ri; }
+BS2E_HD int mask_row_diagS(int nblk, int G, int ri, bool wantX) { return nblk * mask_modes(wantX) + G + ri; }
+BS2E_HD int mask_row_zero(int nblk, int G, bool wantX) { return nblk * mask_modes(wantX) + 2 * G; }
+
+// one-body and overlap part of an entry of the diagonal pair (H_1p_neq, S_mat_neq: mat_els.f90:664-678,
+// 697-715), band rows from the site's shared-memory copy; same statements as one_body_terms (core.h)
+BS2E_HD void site_onebody_at(const Geom& g, int L, const SiteOneBody& so, int na, int nb, int la, int lb,
+                             int nc, int nd, bool samex, Cplx* hout, Cplx* sout)
+{
+    Cplx h = Cplx{0.0, 0.0}, sv = Cplx{0.0, 0.0};
+    {
+        const Cplx Sbd = site_S(g, so, 1, nb, nd), Sac = site_S(g, so, 0, na, nc);
+        h = cadd(h, cmul(site_H(g, so, la, 0, na, nc), Sbd));
+        h = cadd(h, cmul(site_H(g, so, lb, 1, nb, nd), Sac));
+        sv = cadd(sv, cmul(Sac, Sbd));
+    }
+    if (samex) {
+        const double sgn = ((L + la + lb) & 1) ? -1.0 : 1.0;
+        const Cplx Sbc = site_S(g, so, 1, nb, nc), Sad = site_S(g, so, 0, na, nd);
+        Cplx hx = cadd(cmul(site_H(g, so, la, 0, na, nd), Sbc), cmul(site_H(g, so, lb, 1, nb, nc), Sad));
+        h = cadd(h, Cplx{hx.re * sgn, hx.im * sgn});
+        Cplx sx2 = cmul(Cplx{sgn * Sad.re, sgn * Sad.im}, Sbc);
+        sv = cadd(sv, sx2);
+    }
+    *hout = h;
+    *sout = sv;
+}
+BS2E_HD void site_onebody(const Geom& g, const Plan& pl, const SiteOneBody& so, const Site& s, int la, int lb,
+                          int nc, int nd, bool samex, Cplx* hout, Cplx* sout)
+{
+    site_onebody_at(g, pl.L, so, s.na, s.nb, la, lb, nc, nd, samex, hout, sout);
+}
+
+// shared-memory stride (doubles) of a record's factor row: the B fragments of mma.m8n8k4 read
+// [record = lane/4][k = lane%4] as 8-byte words, conflict-free when stride mod 16 is 4 or 12
+BS2E_HD constexpr int mma_cf_stride(int cfs)
+{
+    int s = cfs;
+    while (s % 16 != 4 && s % 16 != 12) s += 2;
+    return s;
+}
+
 // storage mode that the pair effectively stores: a D+X pair whose exchange
 // (direct) windows are all empty for this site and column block is a pure D (X) pair
 BS2E_HD int effective_mode(int mode, int totD, int totX)

@@ -1,0 +1,8 @@
+L=b-spline-two-e_b200/lib
+run() { echo "== $1"; env $3 BS2E_LIB=$PWD/$L/$2 BS2E_ONLY_BLOCKS=6 python scripts/sharded_run.py cfg4 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['stage_C_ms'], d['elements_per_s'], d['checksum_xor_rank0'])"; }
+run mma libbs2e_gpu.so X=1
+run mma_nofork libbs2e_gpu.so BS2E_NOFORK=1
+run fma libbs2e_gpu.so BS2E_FILL=fma
+run fma_nofork libbs2e_gpu.so "BS2E_FILL=fma BS2E_NOFORK=1"
+run mma libbs2e_gpu.so X=1
+run fma libbs2e_gpu.so BS2E_FILL=fma

@@ -422,12 +422,301 @@ static void site_fill_emulate(HcCtx* c, const HostPlan& hp_,
     if (rows_seen != pl.nrows) throw std::logic_error("site list does not cover the rows");
 }
 
+
+// emulates site_mma_kernel<KMAX,WX> (csrc/site_mma.cu) phase by phase: one "CTA" of nthreads threads per
+// radial site, warps = nthreads/32; atomics, ballots and warp scans become serial loops; the 8x8x4 tensor
+// instruction becomes its measured arithmetic (ascending-k FMA chain per output element); the staging of the
+// factor rows is a plain copy.  Everything lane-level comes from site_core.h.
+template <int KMAX>
+static void site_mma_emulate(HcCtx* c, const HostPlan& hp_, int group_rows, int nthreads, int chunk_rec,
+                             const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
+                             int64_t* S_idx, double* S_dat)
+{
+    constexpr int NKH = (KMAX + 1) / 2, NKP = ((NKH + 1) & ~1), KS = (NKH + 3) / 4, CT = kSegCand / 8;
+    const Geom& g = c->hg.g;
+    const Plan pl = hp_.view();
+    if (pl.nkp != NKP) throw std::logic_error("packed factor stride mismatch");
+    const OneBody ob{c->Hb.data(), c->Sb.data()};
+    const double* R = c->R.data();
+    const int K1 = g.K1, nblk = pl.nblk;
+    const int NT = nthreads, NW = std::max(1, NT / 32);
+    const size_t plane = (size_t)g.P * g.ldP;
+    const int maxc = hp_.ang.maxc;
+    const int per_row = std::max(1, std::min(maxc, nblk));
+    const int G = group_rows > 0 ? std::min(group_rows, nblk) : std::min(nblk, 255);
+    const int capP = ((G * per_row + 7) & ~7) + ((G + 7) & ~7) + 8;
+    const int CH = std::max(8, chunk_rec & ~7);
+    long long* Hi = reinterpret_cast<long long*>(H_idx);
+    long long* Si = reinterpret_cast<long long*>(S_idx);
+    const int nsites = (int)hp_.site_key.size();
+    long long rows_seen = 0;
+    struct RowC { long long hbase, sbase; int bi, la, lb; };
+    for (int sidx = 0; sidx < nsites; ++sidx) {
+        const unsigned key = (unsigned)(hp_.site_key[sidx] & 0xffffffffull);
+        const bool WX = site_wants_X(g, pl.max_nd, (int)(key >> 16));
+        if (WX != (sidx < hp_.nsites_x)) throw std::logic_error("site filed in the wrong launch class");
+        const Site s = make_site(g, (int)(key >> 16), (int)(key & 0xffffu), WX);
+        const int nnc = s.nnc;
+        const int ncmax = WX ? site_max_nc(g) : 2 * g.w + 1;
+        const int nsegS = ((WX ? site_max_slots(g) : (2 * g.w + 1) * (2 * g.w + 1)) + kSegCand - 1) / kSegCand;
+        const int CFS = WX ? 2 * NKP : NKP, STR = mma_cf_stride(CFS);
+        if (nnc > ncmax) throw std::logic_error("site exceeds smem bounds");
+        // phase 0
+        std::vector<int> srow_bi, srow_local;
+        for (int bi = 0; bi < nblk; ++bi) {
+            const int row = config_index(g, pl, bi, s.na, s.nb);
+            const int local = row > 0 ? row_local_of(pl.rr, row) : -1;
+            if (local >= 0) { srow_bi.push_back(bi); srow_local.push_back(local); }
+        }
+        const int nr = (int)srow_bi.size();
+        if (nr != 1023 - (int)((hp_.site_key[sidx] >> 32) & 1023)) throw std::logic_error("site key row count");
+        std::vector<int> cprefix(ncmax + 1, -12345);
+        if (WX) {
+            int run = 0;
+            for (int q = 0; q < nnc; ++q) { cprefix[q] = run; run += site_cand_DX_count(s, q); }
+            cprefix[nnc] = run;
+        }
+        const int nl = c->lmax_1p + 1;
+        std::vector<double> ob_s(site_1p_doubles(g, nl));
+        for (int idx = 0; idx < site_1p_doubles(g, nl) / 2; ++idx) {
+            const Cplx v = site_1p_source(g, ob, s, nl, idx);
+            ob_s[2 * idx] = v.re;
+            ob_s[2 * idx + 1] = v.im;
+        }
+        const SiteOneBody so{ob_s.data(), ob_s.data() + (size_t)nl * 2 * (2 * g.w + 1) * 2};
+        const int pi = (pl.blk[0].l1 + pl.blk[0].l2) & 1;
+        const int nc_all = site_num_cand(s, cprefix.data(), WX);
+        const int nseg = (nc_all + kSegCand - 1) / kSegCand;
+        if (nseg > nsegS || nc_all > site_max_slots(g)) throw std::logic_error("candidate list exceeds its bound");
+        // phase 1
+        std::vector<SiteEntry> T((size_t)nblk * ncmax);
+        std::vector<int> jb((size_t)nblk * ncmax, -999999);
+        std::vector<unsigned> mD((size_t)nblk * nsegS, 0u), mX((size_t)nblk * nsegS, 0u);
+        for (int idx = 0; idx < nblk * nnc; ++idx) {
+            const int bj = idx / nnc, q = idx - bj * nnc;
+            const SiteEntry e = site_entry(g, pl, s, bj, q);
+            T[bj * ncmax + q] = e;
+            jb[bj * ncmax + q] = e.jbase;
+            const CandSlot cs = cand_slot(s, cprefix.data(), WX, q);
+            entry_cand_ranges(
+                cs, e,
+                [&](int t0, int t1) { mask_range(t0, t1, [&](int seg, unsigned bits) { mD[bj * nsegS + seg] |= bits; }); },
+                [&](int t0, int t1) { mask_range(t0, t1, [&](int seg, unsigned bits) { mX[bj * nsegS + seg] |= bits; }); });
+        }
+        // phase 2
+        const int nrows_tab = mask_rows(nblk, G, WX);
+        std::vector<MaskWord> mtab((size_t)nrows_tab * nsegS, MaskWord{0xdeadbeefu, 0xdeadu});
+        std::vector<unsigned short> tot(nrows_tab, 0xdead);
+        for (int task = 0; task < nblk * mask_modes(WX) + 1; ++task) {
+            if (task == nblk * mask_modes(WX)) {
+                const int row = mask_row_zero(nblk, G, WX);
+                for (int seg = 0; seg < nseg; ++seg) mtab[row * nsegS + seg] = MaskWord{0u, 0u};
+                tot[row] = 0;
+                continue;
+            }
+            const int bj = WX ? task / 3 : task, mode = WX ? task - bj * 3 : kModeD;
+            unsigned run = 0;
+            for (int seg = 0; seg < nseg; ++seg) {
+                const unsigned d = mD[bj * nsegS + seg], x = mX[bj * nsegS + seg];
+                const unsigned m = mode == kModeD ? d : (mode == kModeX ? x : (d | x));
+                mtab[task * nsegS + seg] = MaskWord{m, run};
+                run += popc32(m);
+            }
+            tot[task] = (unsigned short)run;
+        }
+        for (int g0 = 0; g0 < nr; g0 += G) {
+            const int gr = std::min(G, nr - g0);
+            // phase 3a
+            std::vector<RowC> rcache(G);
+            for (int ri = 0; ri < gr; ++ri) {
+                const int bi = srow_bi[g0 + ri];
+                const long long wrow = srow_local[g0 + ri];
+                rcache[ri] = RowC{H_ptr[wrow] - 1, S_ptr[wrow] - 1, bi, pl.blk[bi].l1, pl.blk[bi].l2};
+                ++rows_seen;
+            }
+            std::vector<unsigned> mgH((size_t)G * nsegS, 0u), mgS((size_t)G * nsegS, 0u);
+            for (int idx = 0; idx < gr * nnc; ++idx) {
+                const int ri = idx / nnc, q = idx - ri * nnc;
+                const RowC rc = rcache[ri];
+                SiteEntry e = T[rc.bi * ncmax + q];
+                if (!pl.full) e = entry_cut(e, s, site_nc(s, q));
+                const bool samex = rc.la == rc.lb;
+                const CandSlot cs = cand_slot(s, cprefix.data(), WX, q);
+                entry_cand_ranges(
+                    cs, e,
+                    [&](int t0, int t1) {
+                        mask_range(t0, t1, [&](int seg, unsigned bits) { mgH[ri * nsegS + seg] |= bits; mgS[ri * nsegS + seg] |= bits; });
+                    },
+                    [&](int t0, int t1) {
+                        mask_range(t0, t1, [&](int seg, unsigned bits) {
+                            mgH[ri * nsegS + seg] |= bits;
+                            if (samex) mgS[ri * nsegS + seg] |= bits;
+                        });
+                    });
+            }
+            for (int task = 0; task < 2 * gr; ++task) {
+                const int ri = task >> 1, isS = task & 1;
+                const unsigned* src = (isS ? mgS.data() : mgH.data()) + ri * nsegS;
+                const int row = isS ? mask_row_diagS(nblk, G, ri, WX) : mask_row_diagH(nblk, ri, WX);
+                unsigned run = 0;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    mtab[row * nsegS + seg] = MaskWord{src[seg], run};
+                    run += popc32(src[seg]);
+                }
+                tot[row] = (unsigned short)run;
+            }
+            // phase 3b
+            std::vector<MmaRec> recs((size_t)2 * capP, MmaRec{-777, -5, 0xffff, 0xff, 0xff});
+            int cnts[3] = {0, 0, 0};
+            for (int ri = 0; ri < gr; ++ri) {
+                const RowC rc = rcache[ri];
+                int run = 0, srun = 0;
+                for (int bj = 0; bj < nblk; ++bj) {
+                    int cnt = 0, row = 0;
+                    if (pl.full || bj >= rc.bi) {
+                        if (bj == rc.bi) {
+                            row = mask_row_diagH(nblk, ri, WX);
+                            cnt = tot[row];
+                            srun += tot[mask_row_diagS(nblk, G, ri, WX)];
+                        } else {
+                            const unsigned f = pl.flags[(size_t)rc.bi * nblk + bj];
+                            int mode = (f & kDirAny) ? ((f & kExAny) ? kModeDX : kModeD) : ((f & kExAny) ? kModeX : -1);
+                            if (!WX && mode == kModeDX) mode = kModeD;
+                            if (mode >= 0 && (WX || mode == kModeD)) {
+                                row = mask_row_pair(bj, mode, WX);
+                                cnt = tot[row];
+                            }
+                        }
+                    }
+                    if (cnt > 0) {
+                        const bool diag = bj == rc.bi;
+                        const int par = diag ? 2 : ((rc.la + pl.blk[bj].l1) & 1);
+                        const MmaRec rec{rc.hbase + run, rc.bi * nblk + bj, (unsigned short)row, (unsigned char)bj, (unsigned char)ri};
+                        const int at = cnts[par]++;
+                        if (par != 2 && at >= capP - ((G + 7) & ~7) - 8) throw std::logic_error("record list overflow");
+                        recs[par == 0 ? at : (par == 1 ? capP + at : capP - 1 - at)] = rec;
+                    }
+                    run += cnt;
+                }
+                // the mask-table counts must agree with the count pass (site_count_kernel / row_count)
+                const long long wrow = srow_local[g0 + ri];
+                if (run != H_ptr[wrow + 1] - H_ptr[wrow] || srun != S_ptr[wrow + 1] - S_ptr[wrow])
+                    throw std::logic_error("site fill: row of group " + std::to_string(rc.bi) + " counted differently");
+            }
+            // phase 3c
+            const int n0 = cnts[0], n1 = cnts[1], ndg = cnts[2];
+            const int n0p = (n0 + 7) & ~7, dg0 = n0p, n0all = n0p + ((ndg + 7) & ~7), n1p = (n1 + 7) & ~7;
+            if (n0all > capP || n1p > capP || dg0 + ndg > capP - ndg) throw std::logic_error("record list overflow");
+            {
+                const MmaRec padrec{0, -1, (unsigned short)mask_row_zero(nblk, G, WX), 0, 0};
+                std::vector<MmaRec> mine(ndg);
+                for (int t = 0; t < ndg; ++t) mine[t] = recs[capP - 1 - t];
+                for (int t = 0; t < ndg; ++t) recs[dg0 + t] = mine[t];
+                for (int i = n0; i < n0p; ++i) recs[i] = padrec;
+                for (int i = dg0 + ndg; i < n0all; ++i) recs[i] = padrec;
+                for (int i = n1; i < n1p; ++i) recs[capP + i] = padrec;
+            }
+            // phase 4
+            const int nch0 = (n0all + CH - 1) / CH, nch1 = (n1p + CH - 1) / CH, nchd = nch0 + nch1;
+            const int npass = nchd > 0 ? (nseg + NW - 1) / NW : 0;
+            std::vector<double> cbuf((size_t)CH * STR);
+            for (int pass = 0; pass < npass; ++pass)
+                for (int warp = 0; warp < NW; ++warp) {
+                    const int seg = pass * NW + warp;
+                    if (seg >= nseg) continue;
+                    const int nin = std::min(kSegCand, nc_all - seg * kSegCand);
+                    for (int par = 0; par < 2; ++par) {
+                        const int nchp = par ? nch1 : nch0;
+                        // A fragments as a dense table [ct][candidate of the tile][multipole slot]
+                        double Ad[CT][8][4 * KS], Ax[CT][8][4 * KS];
+                        int qn[CT][8];
+                        for (int ct = 0; ct < CT; ++ct)
+                            for (int m = 0; m < 8; ++m) {
+                                const int t = seg * kSegCand + ct * 8 + m;
+                                const bool ok = t < nc_all;
+                                const OwnCand cd = site_own_cand(g, s, cprefix.data(), WX, ok ? t : 0);
+                                qn[ct][m] = cd.q | (cd.nd << 8);
+                                for (int i = 0; i < 4 * KS; ++i) {
+                                    const int k = 2 * i + par, kx = 2 * i + (par ^ pi);
+                                    Ad[ct][m][i] = (ok && cd.inD && k < K1) ? R[(size_t)k * plane + (size_t)cd.rowD * g.ldP + cd.colD] : 0.0;
+                                    Ax[ct][m][i] = (WX && ok && cd.inX && kx < K1) ? R[(size_t)kx * plane + (size_t)cd.rowX * g.ldP + cd.colX] : 0.0;
+                                }
+                            }
+                        for (int cc = 0; cc < nchp; ++cc) {
+                            const int first = cc * CH;
+                            const int count = std::min(CH, (par ? n1p : n0all) - first);
+                            const MmaRec* rl = recs.data() + (par ? capP : 0) + first;
+                            std::fill(cbuf.begin(), cbuf.end(), std::nan(""));
+                            int real = 0;
+                            for (int i = 0; i < count; ++i) {
+                                if (rl[i].cf < 0) continue;
+                                ++real;
+                                const double* src = pl.angP + (size_t)rl[i].cf * (2 * NKP);
+                                std::copy(src, src + CFS, cbuf.begin() + (size_t)i * STR);
+                            }
+                            auto overlap = [](int a0, int a1, int b0, int b1) { return imax(0, imin(a1, b1) - imax(a0, b0)); };
+                            const int real2 = par ? overlap(first, first + count, 0, n1)
+                                                  : overlap(first, first + count, 0, n0) + overlap(first, first + count, dg0, dg0 + ndg);
+                            if (real != real2 || real == 0) throw std::logic_error("staged byte count of a chunk");
+                            for (int rt = 0; rt < count; rt += 8) {
+                                const bool diag = !par && first + rt >= dg0;
+                                for (int n = 0; n < 8; ++n) {          // record of the tile
+                                    const MmaRec rr = rl[rt + n];
+                                    const MaskWord wh = mtab[rr.tbl * nsegS + seg];
+                                    const double* cf = cbuf.data() + (size_t)(rt + n) * STR;
+                                    for (int ct = 0; ct < CT; ++ct) {
+                                        if (ct * 8 >= nin) break;
+                                        for (int m = 0; m < 8; ++m) {  // candidate of the tile
+                                            const int bit = ct * 8 + m;
+                                            if (!mask_has(wh, bit)) continue;
+                                            if (rr.cf < 0) throw std::logic_error("padding record stores");
+                                            double c0 = 0.0;
+                                            for (int i = 0; i < 4 * KS; ++i) c0 += cf[i] * Ad[ct][m][i];   // on the device: one FMA chain, like the FMA kernels
+                                            if (WX) {
+                                                double x0 = 0.0;
+                                                for (int i = 0; i < 4 * KS; ++i) x0 += cf[NKP + i] * Ax[ct][m][i];
+                                                c0 += x0;
+                                            }
+                                            const int q = qn[ct][m] & 0xff, nd = qn[ct][m] >> 8;
+                                            const int jcol = jb[rr.bj * ncmax + q] + nd;
+                                            double re = c0, im = 0.0;
+                                            if (diag) {
+                                                const RowC rc = rcache[rr.ri];
+                                                if (rc.bi != rr.bj) throw std::logic_error("diagonal pair on a foreign block");
+                                                const MaskWord ws = mtab[(rr.tbl + G) * nsegS + seg];
+                                                if (mask_has(ws, bit)) {
+                                                    Cplx h, sv;
+                                                    site_onebody(g, pl, so, s, rc.la, rc.lb, site_nc(s, q), nd, rc.la == rc.lb, &h, &sv);
+                                                    re += h.re;
+                                                    im += h.im;
+                                                    const long long spos = rc.sbase + mask_rank(ws, bit);
+                                                    Si[spos] = jcol;
+                                                    S_dat[2 * spos] = sv.re;
+                                                    S_dat[2 * spos + 1] = sv.im;
+                                                }
+                                            }
+                                            const long long pos = rr.hpos + mask_rank(wh, bit);
+                                            Hi[pos] = jcol;
+                                            H_dat[2 * pos] = re;
+                                            H_dat[2 * pos + 1] = im;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+        }
+    }
+    if (rows_seen != pl.nrows) throw std::logic_error("site list does not cover the rows");
+}
+
 extern "C" {
 
 int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
                  const int64_t* conf_l, int64_t full, int64_t n_ranges, const int64_t* range_lo,
                  const int64_t* range_hi, const int64_t* H_ptr, const int64_t* S_ptr, int64_t* H_idx, double* H_dat,
-                 int64_t* S_idx, double* S_dat, int64_t group_rows, int64_t nthreads)
+                 int64_t* S_idx, double* S_dat, int64_t group_rows, int64_t nthreads, int64_t mma, int64_t chunk_rec)
 {
     try {
         const Geom& g = c->hg.g;
@@ -436,8 +725,12 @@ int hc_site_fill(HcCtx* c, int64_t L, int64_t n_config, const int64_t* conf_n,
         if (hp_.site_key.empty()) throw std::logic_error("no site list");
 #define HC_SITE(KM)                                                                                  \
     case KM:                                                                                         \
-        site_fill_emulate<KM>(c, hp_, (int)group_rows, (int)nthreads, H_ptr, S_ptr,  \
-                              H_idx, H_dat, S_idx, S_dat);                                           \
+        if (mma)                                                                                     \
+            site_mma_emulate<KM>(c, hp_, (int)group_rows, (int)nthreads, (int)chunk_rec, H_ptr, S_ptr, \
+                                 H_idx, H_dat, S_idx, S_dat);                                        \
+        else                                                                                         \
+            site_fill_emulate<KM>(c, hp_, (int)group_rows, (int)nthreads, H_ptr, S_ptr,              \
+                                  H_idx, H_dat, S_idx, S_dat);                                       \
         break;
         switch (site_kmax_for(g.K1)) {
             HC_SITE(7) HC_SITE(13) HC_SITE(21) HC_SITE(31)

@@ -37,7 +37,7 @@ def lib():
         L.hc_block_count.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, _pi, _pi, _pi, _pi]
         L.hc_block_fill.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, _pi, _pi, _pi, _pi,
                                     _pi, _pd, _pi, _pd]
-        L.hc_site_fill.argtypes = L.hc_block_fill.argtypes + [i64, i64]
+        L.hc_site_fill.argtypes = L.hc_block_fill.argtypes + [i64, i64, i64, i64]
         L.hc_set_radial_dipole.argtypes = [C.c_void_p, i64, _pd, C.c_void_p]
         L.hc_dip_block.restype = i64
         L.hc_dip_block.argtypes = [C.c_void_p, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64,
@@ -93,8 +93,9 @@ class HostCheck:
         if lib().hc_set_one_particle(self.h, len(H_vec) - 1, Hv, Sf):
             raise RuntimeError(lib().hc_last_error().decode())
 
-    def block(self, L, conf_n, conf_l, full, rows=None, kernel="site", group_rows=0, nthreads=256,
-              ranges=None):
+    def block(self, L, conf_n, conf_l, full, rows=None, kernel="mma", group_rows=0, nthreads=256,
+              ranges=None, chunk_rec=80):
+        """kernel: "mma" (site_mma.cu, the product default), "site" (FMA site kernel of block.cu), "row" (fallback)"""
         n = len(conf_n)
         cn = np.ascontiguousarray(conf_n.reshape(-1), np.int64)
         cl = np.ascontiguousarray(conf_l.reshape(-1), np.int64)
@@ -113,7 +114,8 @@ class HostCheck:
         Hd = np.full(2 * max(nH, 1), np.nan)
         Sd = np.full(2 * max(nS, 1), np.nan)
         args = (self.h, L, n, cn, cl, int(full), len(lo), lo, hi, Hp, Sp, Hi, Hd, Si, Sd)
-        rc = lib().hc_site_fill(*args, group_rows, nthreads) if kernel == "site" else lib().hc_block_fill(*args)
+        rc = (lib().hc_site_fill(*args, group_rows, nthreads, int(kernel == "mma"), chunk_rec) if kernel in ("site", "mma")
+              else lib().hc_block_fill(*args))
         if rc:
             raise RuntimeError(lib().hc_last_error().decode())
         return (Hp, Hi[:nH], Hd.view(np.complex128)[:nH]), (Sp, Si[:nS], Sd.view(np.complex128)[:nS])

@@ -59,7 +59,7 @@ def test_stage_B_Rk(case):
         assert np.all(R[:, :, hc.P:] == 0.0)
 
 
-@pytest.mark.parametrize("kernel", ["row", "site"])
+@pytest.mark.parametrize("kernel", ["row", "site", "mma"])
 @pytest.mark.parametrize("full", [False, True])
 def test_stage_C_blocks(case, full, kernel):
     run, hc = case
@@ -84,9 +84,10 @@ def test_site_and_row_kernels_bit_identical(case):
     for s in run.syms:
         for full in (False, True):
             a = hc.block(s.l, s.conf_n, s.conf_l, full, kernel="row")
-            b = hc.block(s.l, s.conf_n, s.conf_l, full, kernel="site")
-            for (p1, i1, d1), (p2, i2, d2) in zip(a, b):
-                assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
+            for kernel in ("site", "mma"):
+                b = hc.block(s.l, s.conf_n, s.conf_l, full, kernel=kernel)
+                for (p1, i1, d1), (p2, i2, d2) in zip(a, b):
+                    assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2), kernel
 
 
 def test_site_kernel_row_groups(case):
@@ -101,6 +102,11 @@ def test_site_kernel_row_groups(case):
         b = hc.block(s.l, s.conf_n, s.conf_l, True, kernel="site", group_rows=group_rows, nthreads=nthreads)
         for (p1, i1, d1), (p2, i2, d2) in zip(a, b):
             assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # tensor-core kernel: row groups, few warps (several segment passes), small staging chunks (many chunks)
+    for group_rows, nthreads, chunk in ((0, 256, 80), (1, 256, 8), (2, 64, 16), (3, 32, 8)):
+        b = hc.block(s.l, s.conf_n, s.conf_l, True, kernel="mma", group_rows=group_rows, nthreads=nthreads, chunk_rec=chunk)
+        for (p1, i1, d1), (p2, i2, d2) in zip(a, b):
+            assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(d1, d2), (group_rows, nthreads)
 
 
 def test_row_range_fragments_concatenate(case):
