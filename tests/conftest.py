@@ -13,6 +13,34 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_terminal_summary(terminalreporter):
+    """strict per-entry error of every CSR comparison of the run (parity_utils.PARITY_STATS)"""
+    import json
+    from parity_utils import PARITY_STATS, REL_TOL
+    if not PARITY_STATS:
+        return
+    n = sum(q["entries"] for q in PARITY_STATS)
+    over = sum(q["strict_over_1e-12"] for q in PARITY_STATS)
+    worst = max(PARITY_STATS, key=lambda q: q["strict_max"])
+    tr = terminalreporter
+    tr.write_line(f"parity: {len(PARITY_STATS)} CSR comparisons, {n} entries; scaled max "
+                  f"{max(q['scaled_max'] for q in PARITY_STATS):.2e}; strict per-entry max {worst['strict_max']:.2e} "
+                  f"({worst['what']}); entries over {REL_TOL:.0e} strict: {over} ({over / max(n, 1):.2e} of all)")
+    path = os.environ.get("BS2E_PARITY_REPORT")
+    if path:
+        agg = {}
+        for q in PARITY_STATS:
+            key = q["what"].split(" ")[0] if q["what"] else "?"
+            a = agg.setdefault(key, {"comparisons": 0, "entries": 0, "scaled_max": 0.0, "strict_max": 0.0, "strict_over_1e-12": 0})
+            a["comparisons"] += 1
+            a["entries"] += q["entries"]
+            a["scaled_max"] = max(a["scaled_max"], q["scaled_max"])
+            a["strict_max"] = max(a["strict_max"], q["strict_max"])
+            a["strict_over_1e-12"] += q["strict_over_1e-12"]
+        with open(path, "w") as f:
+            json.dump({"total_entries": n, "strict_over_1e-12": over, "worst": worst, "by_label": agg}, f, indent=1)
+
+
 # Small deterministic basis_input namelists (the namelist is the seed; the
 # reference has no random inputs).  Chosen to hit the edge cases of the path:
 # radial truncation of the second electron (r_2_max), the large-r angular

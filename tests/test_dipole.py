@@ -202,3 +202,45 @@ def test_gpu_driver_writes_dipole_files(tmp_path):
             assert G.nnz == D.nnz
             if D.nnz:
                 assert_csr_equal(G, D, scale_tol=5e-12, what=f"D_{q}.dat block ({i},{j})")
+
+
+def test_reference_hint_He_1s2_to_1s2p_dipole():
+    """The one number the reference's own tests hold for this path (tests/test_mat_els.f90:483, a print
+    statement that divides by it): |<1s^2 (0,0,e)| z |1s2p (1,0,o)>| = 0.42082 for helium on the grid of
+    that test (k=8, m=3, Z=2, h_max=1.5, r_max=15).  Restated on the oracle: lowest generalised eigenvectors
+    of the L=0 and L=1 blocks, contracted with the q=0 dipole block in the length gauge.  l_max = 2 and a
+    15 bohr box carry the 2^1P state to about 1 %, so this is an anchor, not a 1e-12 check."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    run = O.OracleRun(k=8, m=3, Z=2, h_max=1.5, r_max=15.0, k_GL=14, max_k=4, max_L=1, max_l_1p=2, max_l2=2,
+                      CAP_eta=0j, CAP_r_0=45.0, full=False, z_pol=True)
+    run.slater(); run.rk_map(); run.one_particle()
+    syms = run.basis()
+    gs_sym = next(s for s in syms if (s.l, s.pi) == (0, 0))
+    ex_sym = next(s for s in syms if (s.l, s.pi) == (1, 1))
+    vec, en = {}, {}
+    for name, s, sigma in (("gs", gs_sym, -3.0), ("ex", ex_sym, -2.2)):
+        H, S, _ = run.block(s)
+        n = s.n_config
+        up = lambda M: sp.csr_matrix((M.data.real, M.indices - 1, M.index_ptr - 1), shape=(n, n))
+        full = lambda U: U + U.T - sp.diags(U.diagonal())
+        Hf, Sf = full(up(H)), full(up(S))
+        ev, v = sla.eigsh(Hf.tocsc(), k=1, M=Sf.tocsc(), sigma=sigma, which="LM")
+        v = v[:, 0] / np.sqrt(v[:, 0] @ (Sf @ v[:, 0]))
+        vec[name], en[name] = v, float(ev[0])
+    assert abs(en["gs"] + 2.90276684) < 1e-6            # SURVEY.md section 8c
+    assert abs(en["ex"] + 2.1238) < 5e-3                # He 2^1P: -2.12384 (box and l_max limited)
+    rd = O.setup_radial_dip(run.bs, 14, "l")
+    D = O.construct_dip_block_tensor(run.bs, rd, run.S, gs_sym, ex_sym, 0)
+    Dm = sp.csr_matrix((D.data, D.indices - 1, D.index_ptr - 1), shape=(gs_sym.n_config, ex_sym.n_config))
+    res = abs(vec["gs"] @ (Dm @ vec["ex"]))
+    assert abs(res - 0.42082) < 2e-3, res               # 0.42156 on this grid
+    # the oscillator strength the reference prints next (lines 484-488): length form 2 dE |<z>|^2, velocity form
+    # 2 |<d/dz>|^2 / dE; He 1^1S -> 2^1P: 0.2762.  The two gauges go through different radial integrals
+    # (r_mat vs dr_mat, r_inv_mat) and different angular branches of dip_red_1p, and agree to 2e-3.
+    f_len = 2.0 * (en["ex"] - en["gs"]) * res ** 2
+    rv = O.setup_radial_dip(run.bs, 14, "v")
+    Dv = O.construct_dip_block_tensor(run.bs, rv, run.S, gs_sym, ex_sym, 0)
+    Dvm = sp.csr_matrix((Dv.data, Dv.indices - 1, Dv.index_ptr - 1), shape=(gs_sym.n_config, ex_sym.n_config))
+    f_vel = 2.0 / (en["ex"] - en["gs"]) * abs(vec["gs"] @ (Dvm @ vec["ex"])) ** 2
+    assert abs(f_len - 0.2762) < 2e-3 and abs(f_vel - 0.2762) < 2e-3 and abs(f_len - f_vel) < 2e-3, (f_len, f_vel)

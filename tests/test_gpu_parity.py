@@ -242,12 +242,10 @@ def test_cfg1_full_true_upper_triangle_matches(cfg1):
 
 
 # ---------------------------------------------------------------------------
-# BASELINE config 4 (n_b=307, max_k=20, L<=8) at full size.  The oracle's stage A/B
-# take minutes at this size, so stage C is checked against the oracle fed with the
-# R^k tensor the GPU built (stage A/B themselves are checked in full at cfg1 and on
-# the small cases, here only through the symmetries of the tensor); the output of
-# a block (up to 3e9 elements, 77 GB) stays on the device and is compared through
-# row-range fragments and checksums.
+# BASELINE config 4 (n_b=307, max_k=20, L<=8) at full size: the smallest and the largest
+# block with their counts, checksums and row-range fragments (the output of a block, up to
+# 28 GB, stays on the device).  Stage C is fed here with the R^k tensor the GPU built; stage
+# A/B at this size are compared with the oracle in test_cfg4_stage_AB_full_against_oracle.
 # ---------------------------------------------------------------------------
 def test_cfg4_scale_blocks_sampled_rows_and_properties():
     p = bs2e.CONFIGS["cfg4"]
@@ -411,3 +409,169 @@ def test_small_factor_chunks_are_bit_identical(case, monkeypatch):
         b = ctx.block_plan(s, False); b.assemble(); H, S = b.download(); b.free()
         assert np.array_equal(H.indices, H0.indices) and np.array_equal(H.data, H0.data)
         assert np.array_equal(S.indices, S0.indices) and np.array_equal(S.data, S0.data)
+
+
+# ---------------------------------------------------------------------------
+# both site kernels (tensor-core site_mma.cu and the FMA kernel of block.cu) on every small case:
+# each against the oracle, and bit for bit against each other -- the tensor instruction accumulates
+# the multipoles in ascending order, i.e. it runs the FMA chain of the other kernel
+# ---------------------------------------------------------------------------
+def test_stage_C_both_site_kernels(case, monkeypatch):
+    run, ctx = case
+    run.p["full"] = False
+    for s in run.syms:
+        if s.n_config == 0:
+            continue
+        H, S, _ = run.block(s)
+        out = {}
+        for fill in ("mma", "fma"):
+            monkeypatch.setenv("BS2E_FILL", fill)
+            b = ctx.block_plan(s, False); b.assemble(); out[fill] = b.download(); b.free()
+            assert_csr_equal(out[fill][0], H, what=f"H[{fill}] L={s.l} pi={s.pi}")
+            assert_csr_equal(out[fill][1], S, what=f"S[{fill}] L={s.l} pi={s.pi}")
+        for a, b in zip(out["mma"], out["fma"]):
+            assert np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+
+
+def _sampled_rows_vs_oracle(run, ctx, s, label, nrows=16, where=(0.0, 0.37, 1.0), ranges_of=None):
+    """row ranges of a block assembled on the device against the oracle's construct_block_tensor"""
+    n = s.n_config
+    for f in where:
+        lo = max(1, min(n - nrows + 1, int(f * n)))
+        hi = lo + nrows - 1
+        frag = ctx.block_plan(s, run.p["full"], rows=(lo, hi))
+        frag.assemble()
+        H, S = frag.download()
+        cap = (frag.nnz_H, frag.nnz_S)
+        frag.free()
+        Ho, So, em = run.block(s, rows=(lo, hi), nnz=cap)
+        assert em == cap, (label, lo, hi)
+        ref = O.CSR(None, cap[0], Ho.index_ptr[lo - 1:hi + 1], Ho.indices, Ho.data)
+        assert_csr_equal(H, ref, what=f"{label} H rows {lo}-{hi} L={s.l}")
+        ref = O.CSR(None, cap[1], So.index_ptr[lo - 1:hi + 1], So.indices, So.data)
+        assert_csr_equal(S, ref, what=f"{label} S rows {lo}-{hi} L={s.l}")
+
+
+def _full_tensor_vs_oracle(run, ctx, label):
+    K1 = run.p["max_k"] + 1
+    worst = 0.0
+    for k in range(K1):
+        Rg = ctx.rk_plane(k)
+        ref = run.R[:, :, k]
+        assert Rg.min() >= 0.0
+        worst = max(worst, float(np.max(np.abs(Rg - ref) / np.maximum(ref, np.finfo(float).tiny))))
+    assert worst <= REL_TOL, f"{label}: R^k max relative error {worst:.2e}"
+    return worst
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 2 whole: every block of the GPU path against the oracle
+# ---------------------------------------------------------------------------
+def test_cfg2_whole():
+    from concurrent.futures import ThreadPoolExecutor
+    p = bs2e.CONFIGS["cfg2"]
+    run = O.OracleRun(**p)
+    run.slater(tabulate=1, par_mode=1); run.rk_map(); run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    assert (ctx.n_b, ctx.P) == (105, 1323)
+    _full_tensor_vs_oracle(run, ctx, "cfg2")
+    with ThreadPoolExecutor(max_workers=len(run.syms)) as ex:      # the oracle scans n_config^2 pairs per block
+        refs = list(ex.map(lambda s: run.block(s), run.syms))
+    for s, (H, S, em) in zip(run.syms, refs):
+        assert ctx.block_count(s, False) == em
+        Hg, Sg = ctx.block_fill(s, False, em)
+        assert_csr_equal(Hg, H, what=f"cfg2 H L={s.l}")
+        assert_csr_equal(Sg, S, what=f"cfg2 S L={s.l}")
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 3: stage A/B in full against the oracle (its tabulated evaluation on all cores), sampled
+# rows of every block against the oracle fed with ITS OWN R^k
+# ---------------------------------------------------------------------------
+def test_cfg3_stage_AB_full_and_sampled_rows_of_every_block():
+    p = bs2e.CONFIGS["cfg3"]
+    run = O.OracleRun(**p)
+    run.slater(tabulate=1, par_mode=1); run.rk_map(); run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    assert (ctx.n_b, ctx.P, ctx.nnz_4d, ctx.nnz_6d) == (206, 3034, 12834, 819906)
+    _full_tensor_vs_oracle(run, ctx, "cfg3")
+    for s in run.syms:
+        whole = ctx.block_plan(s, False)
+        cH, cS = whole.row_counts()
+        assert cH.sum() == whole.nnz_H and cS.sum() == whole.nnz_S and cS.min() >= 1
+        whole.free()
+        _sampled_rows_vs_oracle(run, ctx, s, "cfg3")
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 4 (the bench workload): stage A/B in full against the oracle, then sampled rows against
+# the oracle's own tensor
+# ---------------------------------------------------------------------------
+def test_cfg4_stage_AB_full_against_oracle():
+    p = bs2e.CONFIGS["cfg4"]
+    run = O.OracleRun(**p)
+    run.slater(tabulate=1, par_mode=1); run.rk_map(); run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    assert (ctx.n_b, ctx.P) == (307, 4549)
+    _full_tensor_vs_oracle(run, ctx, "cfg4")
+    for s in (run.syms[0], run.syms[4], run.syms[8]):
+        _sampled_rows_vs_oracle(run, ctx, s, "cfg4", nrows=8, where=(0.0, 0.5, 1.0))
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 5: the share of one rank of eight of one block (the unit of the 8-GPU run), sampled rows
+# of the share against the oracle.  The oracle's stage A/B would take minutes at this size (n_b = 606,
+# max_k = 30): its stage C is fed with the tensor the GPU built, which is checked through its symmetries.
+# ---------------------------------------------------------------------------
+def test_cfg5_one_share_of_eight_sampled_rows():
+    from bs2e.sharding import exchange_cost, site_partition
+    p = bs2e.CONFIGS["cfg5"]
+    run = O.OracleRun(**p)
+    run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    K1 = p["max_k"] + 1
+    assert (ctx.n_b, ctx.P) == (606, 9034)
+    rng = np.random.default_rng(3)
+    a = rng.integers(1, ctx.n_b + 1, 3000); b = rng.integers(1, ctx.n_b + 1, 3000)
+    c = np.clip(a + rng.integers(-7, 8, 3000), 1, ctx.n_b); d = np.clip(b + rng.integers(-7, 8, 3000), 1, ctx.n_b)
+    v0 = ctx.rk_get(np.stack([a, b, c, d], 1))
+    assert v0.min() >= 0.0
+    assert_rel(ctx.rk_get(np.stack([b, a, d, c], 1)), v0, tol=1e-12, what="cfg5 R^k(ba;dc)")
+    assert_rel(ctx.rk_get(np.stack([c, b, a, d], 1)), v0, tol=1e-12, what="cfg5 R^k(cb;ad)")
+    R = np.empty((ctx.P, ctx.P, K1))
+    for k in range(K1):
+        R[:, :, k] = ctx.rk_plane(k)
+    run.R = R
+    s = run.syms[0]                                       # (0,0,even): 0.42 M configurations
+    whole = ctx.block_plan(s, False)
+    cH, cS = whole.row_counts()
+    whole.free()
+    shares = site_partition(s.conf_n, cH + cS, 8, p["k"], exchange_cost(p["max_k"]))
+    for rank in (0, 5):                                   # a share with exchange windows and one without
+        ranges = shares[rank]
+        blk = ctx.block_plan(s, False, ranges=ranges)
+        assert blk.nnz_H == sum(int(cH[lo - 1:hi].sum()) for lo, hi in ranges)
+        blk.assemble()
+        H, S = blk.download()
+        blk.free()
+        # rows of the share: local row r of range q is configuration lo_q + (r - off_q)
+        off = 0
+        for lo, hi in ranges[:2]:
+            m = min(6, hi - lo + 1)
+            cap = (int(cH[lo - 1:lo - 1 + m].sum()), int(cS[lo - 1:lo - 1 + m].sum()))
+            Ho, So, em = run.block(s, rows=(lo, lo + m - 1), nnz=cap)
+            assert em == cap
+            for M, Mo, what in ((H, Ho, "H"), (S, So, "S")):
+                a0, a1 = int(M.index_ptr[off] - 1), int(M.index_ptr[off + m] - 1)
+                frag = O.CSR(None, a1 - a0, M.index_ptr[off:off + m + 1] - a0, M.indices[a0:a1], M.data[a0:a1])
+                ref = O.CSR(None, a1 - a0, Mo.index_ptr[lo - 1:lo + m], Mo.indices, Mo.data)
+                assert_csr_equal(frag, ref, what=f"cfg5 {what} share {rank} rows {lo}-{lo + m - 1}")
+            off += hi - lo + 1
+    ctx.close()
