@@ -81,6 +81,20 @@ __device__ __forceinline__ void st_value_if(unsigned on, const char* base, unsig
         "@p st.global.cs.v2.f64 [a], {%3, %4};\n}\n" ::"r"(on), "r"(off), "l"(base), "d"(re), "d"(0.0));
 }
 
+// one elected lane of the (converged) warp
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+// shared -> global bulk copy (TMA engine, linear form) as part of the thread's current bulk group
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+
 struct alignas(16) RowC {   // per row of the group
     long long hbase, sbase; // 0-based position of the first H / S entry of the row
     int bi, la, lb, pad;
@@ -91,7 +105,7 @@ struct alignas(16) RowC {   // per row of the group
 #ifndef BS2E_MMA_MINB
 #define BS2E_MMA_MINB 2
 #endif
-template <int KMAX, bool WX>
+template <int KMAX, bool WX, bool BULK>
 __global__ void __launch_bounds__(kMmaThreads, BS2E_MMA_MINB)
 site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl, const __grid_constant__ OneBody ob,
                 const unsigned long long* __restrict__ site_key, const __grid_constant__ MmaSmem lay, int site_off,
@@ -264,6 +278,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
     // their latency hides behind phase 3
     if (nr > 0) fetch_A(0, 0);
 
+    unsigned tctr = 0;                        // staged tiles so far (row buffer = tctr & 1)
     unsigned mphase = 0;                      // phase parity of the two staging barriers (bit b)
     bool pending0 = false, pending1 = false;  // a copy into buffer b is in flight
 
@@ -449,13 +464,14 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
             }
             const int bsel = resident ? l : (gi & 1);
             wait_buf(bsel);
-            if (seg >= nseg) continue;
-            const int nin = imin(kSegCand, nc_all - seg * kSegCand);   // candidates of this warp's segment
+            const bool has = seg < nseg;
+            if (!BULK && !has) continue;   // (with CTA-level row staging every warp takes part in its barriers)
+            const int nin = has ? imin(kSegCand, nc_all - seg * kSegCand) : 0;   // candidates of this warp's segment
             const int count = imin(CH, (par ? n1p_f() : n0all_f()) - first);
             const int dgt = par ? count : imax(0, n0p_f() - first);   // tiles from here on hold diagonal records
             const double* cfr = BS2E_SM(double, off_cfs) + (size_t)bsel * CH * STR + (size_t)l4 * STR + l3;
             const MmaRec* rl = BS2E_SM(MmaRec, off_recs) + (par ? lay.cap : 0) + first + 2 * l3;
-            const MaskWord* mseg = BS2E_SM(MaskWord, off_mtab) + seg;
+            const MaskWord* mseg = BS2E_SM(MaskWord, off_mtab) + (has ? seg : 0);
 #pragma unroll 1
             for (int rt = 0; rt < count; rt += 8, cfr += 8 * STR, rl += 8) {
                 // the two records this thread stores for: 2*(lane%4) and the next
@@ -470,51 +486,89 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                 }
                 if constexpr (!WX) bx[0] = 0.0;
                 if (rt < dgt) {
-                    if (__all_sync(0xffffffffu, (wa.mask | wb.mask) == 0u)) continue;   // nothing stored in this segment
+                    const bool any = has && !__all_sync(0xffffffffu, (wa.mask | wb.mask) == 0u);   // something stored in this segment
+                    if (!BULK && !any) continue;
                     const unsigned ma = wa.mask >> l4, mb = wb.mask >> l4;   // bit 8 ct: this thread's candidate of tile ct
-                    // The C fragment holds 8 candidates x 4 rows per instruction: stored directly that is four
-                    // 128-byte runs per store, which the L1 -> L2 path handles at a third of its rate
-                    // (scripts/microbench/store_probe.cu).  The values are therefore transposed through the warp's
-                    // staging tile (row r of the tile at r*512 bytes, entry `off` of the segment at 16*off) and leave
-                    // row by row, one 512-byte run per store; the column indices are produced in the same row-wise
-                    // role (lane = candidate of the segment) without staging.
-                    const unsigned va = smem_u32(stile) + (2 * l3) * 512, vb = va + 512;
-                    __syncwarp();   // the rows of the previous tile have been read
-                    // products of CTH tiles together: CTH (2 CTH with exchange windows) independent chains
+                    // Stores.  The C fragment holds 8 candidates x 4 rows per instruction: stored directly that is four
+                    // 128-byte runs per store, which the L1 -> L2 path takes at a third of its rate; row-wise stores
+                    // (one 512-byte run per instruction) reach 0.64 of the HBM write rate, bulk copies of whole rows
+                    // from shared memory 0.9 and more (scripts/microbench/store_probe.cu).  Hence
+                    //   default: the values are transposed through the warp's staging tile and stored row-wise;
+                    //   BULK (BS2E_MMA_STORE=bulk, sites without exchange windows): the values of the 8 rows of a tile
+                    //     are collected by all warps in a CTA-level buffer (row r at r*rowb, entry at 16*rank) and leave
+                    //     as ONE bulk copy per row (cp.async.bulk shared -> global, issued by warp r), double buffered,
+                    //     one barrier per tile.  Measured 7 % slower than the default at cfg4: the barrier per tile and
+                    //     the issue slots of the copies cost more than the store path gains;
+                    //   column indices: row-wise (lane = candidate of the segment), no staging.
+                    unsigned va, vb, offa0, offb0;
+                    if constexpr (!BULK) {
+                        va = smem_u32(stile) + (2 * l3) * 512;
+                        vb = va + 512;
+                        offa0 = offb0 = 0;
+                        __syncwarp();   // the rows of the previous tile have been read
+                    } else {
+                        const unsigned vbuf = smem_u32(smraw) + lay.off_stage + (tctr & 1) * 8 * lay.rowb;
+                        va = vbuf + (2 * l3) * lay.rowb;
+                        vb = va + lay.rowb;
+                        const int seg0 = pass * NW;   // first segment of the pass: rows are staged from its first entry on
+                        offa0 = wa.pre - BS2E_SM(MaskWord, off_mtab)[ra.tbl * nsegS + seg0].pre;
+                        offb0 = wb.pre - BS2E_SM(MaskWord, off_mtab)[rb.tbl * nsegS + seg0].pre;
+                    }
+                    if (any) {
+                        // products of CTH tiles together: CTH (2 CTH with exchange windows) independent chains
 #pragma unroll
-                    for (int h = 0; h < CT; h += CTH) {
-                        if (h * 8 < nin) {
-                            double c0[CTH], c1[CTH];
+                        for (int h = 0; h < CT; h += CTH) {
+                            if (h * 8 < nin) {
+                                double c0[CTH], c1[CTH];
 #pragma unroll
-                            for (int u = 0; u < CTH; ++u) c0[u] = c1[u] = 0.0;
-#pragma unroll
-                            for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                                for (int u = 0; u < CTH; ++u) dmma884(c0[u], c1[u], Ad[h + u][ks], bd[ks], c0[u], c1[u]);
-                            if constexpr (WX) {
-                                double x0[CTH], x1[CTH];
-#pragma unroll
-                                for (int u = 0; u < CTH; ++u) x0[u] = x1[u] = 0.0;
+                                for (int u = 0; u < CTH; ++u) c0[u] = c1[u] = 0.0;
 #pragma unroll
                                 for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-                                    for (int u = 0; u < CTH; ++u) dmma884(x0[u], x1[u], Ax[h + u][ks], bx[ks], x0[u], x1[u]);
+                                    for (int u = 0; u < CTH; ++u) dmma884(c0[u], c1[u], Ad[h + u][ks], bd[ks], c0[u], c1[u]);
+                                if constexpr (WX) {
+                                    double x0[CTH], x1[CTH];
 #pragma unroll
-                                for (int u = 0; u < CTH; ++u) { c0[u] += x0[u]; c1[u] += x1[u]; }
-                            }
+                                    for (int u = 0; u < CTH; ++u) x0[u] = x1[u] = 0.0;
 #pragma unroll
-                            for (int u = 0; u < CTH; ++u) {
-                                const int ct = h + u;
-                                const unsigned below = (1u << (ct * 8 + l4)) - 1u;
-                                sts_value_if((ma >> (8 * ct)) & 1u, va, __popc(wa.mask & below), c0[u]);
-                                sts_value_if((mb >> (8 * ct)) & 1u, vb, __popc(wb.mask & below), c1[u]);
+                                    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                                        for (int u = 0; u < CTH; ++u) dmma884(x0[u], x1[u], Ax[h + u][ks], bx[ks], x0[u], x1[u]);
+#pragma unroll
+                                    for (int u = 0; u < CTH; ++u) { c0[u] += x0[u]; c1[u] += x1[u]; }
+                                }
+#pragma unroll
+                                for (int u = 0; u < CTH; ++u) {
+                                    const int ct = h + u;
+                                    const unsigned below = (1u << (ct * 8 + l4)) - 1u;
+                                    sts_value_if((ma >> (8 * ct)) & 1u, va, offa0 + __popc(wa.mask & below), c0[u]);
+                                    sts_value_if((mb >> (8 * ct)) & 1u, vb, offb0 + __popc(wb.mask & below), c1[u]);
+                                }
                             }
                         }
                     }
-                    __syncwarp();
-                    // row-wise: lane = entry of the row (values), lane = candidate of the segment (indices)
-                    {
-                        const MmaRec* rt8 = rl - 2 * l3;   // first record of the tile
+                    const MmaRec* rt8 = rl - 2 * l3;   // first record of the tile
+                    if constexpr (!BULK) {
+                        __syncwarp();
+                    } else {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staged values, for the copy engine
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // this warp's copy of the tile before the last
+                        __syncthreads();
+                        {   // warp r hands row r of the tile to the bulk-copy engine
+                            const MmaRec rr = rt8[warp];
+                            const MaskWord* mrow = BS2E_SM(MaskWord, off_mtab) + rr.tbl * nsegS;
+                            const int seg0 = pass * NW;
+                            const unsigned pre0 = mrow[seg0].pre;
+                            const unsigned pre1 = seg0 + NW < nseg ? mrow[seg0 + NW].pre : BS2E_SM(unsigned short, off_tot)[rr.tbl];
+                            if (pre1 > pre0 && elect_one())
+                                bulk_s2g(Hdat + rr.hpos + pre0, smem_u32(smraw) + lay.off_stage + ((tctr & 1) * 8 + warp) * lay.rowb,
+                                         (pre1 - pre0) * 16u);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++tctr;
+                    }
+                    // row-wise: lane = entry of the row (values, with exchange windows), lane = candidate of the segment (indices)
+                    if (any) {
                         const unsigned lt = (1u << lane) - 1u;
                         const char* jbl = reinterpret_cast<const char*>(BS2E_SM(int, off_jb)) + (ql & 0xfff);
                         const int ndl = ql >> 12;
@@ -523,25 +577,26 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                         for (int r0 = 0; r0 < 8; r0 += 4) {
                             MmaRec rr[4];
                             MaskWord wr[4];
-                            double2 v[4];
+                            double2 v[BULK ? 1 : 4];
                             int jc[4];
 #pragma unroll
                             for (int r = 0; r < 4; ++r) rr[r] = rt8[r0 + r];
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
                                 wr[r] = mseg[rr[r].tbl * nsegS];
-                                v[r] = srow[(r0 + r) * 32];
+                                if constexpr (!BULK) v[r] = srow[(r0 + r) * 32];
                                 jc[r] = *reinterpret_cast<const int*>(jbl + rr[r].bj * ncmax * 4) + ndl;
                             }
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
                                 const long long start = rr[r].hpos + wr[r].pre;
-                                st_value2_if(lane < __popc(wr[r].mask) ? 1u : 0u, reinterpret_cast<const char*>(Hdat + start), lane, v[r]);
+                                if constexpr (!BULK)
+                                    st_value2_if(lane < __popc(wr[r].mask) ? 1u : 0u, reinterpret_cast<const char*>(Hdat + start), lane, v[r]);
                                 st_index_if((wr[r].mask >> lane) & 1u, reinterpret_cast<const char*>(Hidx + start), __popc(wr[r].mask & lt), jc[r]);
                             }
                         }
                     }
-                } else {
+                } else if (has) {
                     // diagonal pairs (column group == row group): one-body terms and the S entry
                     const RowC* rcache = BS2E_SM(RowC, off_rcache);
                     const RowC rca = rcache[ra.ri], rcb = rcache[rb.ri];
@@ -593,6 +648,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                 }
             }
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the output copies are complete
         // a staging copy that was issued must land before the buffers are reused or the CTA exits
         wait_buf(0);
         wait_buf(1);
@@ -608,7 +664,7 @@ namespace {
 size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
 }
 
-MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, int lmax)
+MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, int lmax, bool bulk)
 {
     const Geom& g = c->hg;
     MmaSmem lay{};
@@ -650,7 +706,9 @@ MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, i
     put(lay.off_mbar, 16);
     put(lay.off_misc, 32);
     b = (b + 127) & ~(size_t)127;
-    put(lay.off_stage, (size_t)(kMmaThreads / 32) * kMmaStageBytes);
+    // staging of the values: with exchange windows one tile per warp; without, two CTA-level buffers of 8 whole rows
+    lay.rowb = (int)((std::min<size_t>((size_t)(kMmaThreads / 32) * kSegCand, (size_t)lay.nseg * kSegCand) * 16 + 127) & ~(size_t)127);
+    put(lay.off_stage, !bulk ? (size_t)(kMmaThreads / 32) * kMmaStageBytes : (size_t)2 * 8 * lay.rowb);
     lay.bytes = b;
     return lay;
 }
@@ -661,16 +719,16 @@ bool site_mma_usable(const bs2e_ctx* c, int nblk, int maxc, int maxrec, int lmax
     if (site_kmax_for(g.K1) <= 0) return false;
     if (nblk > 255 || 2 * (2 * g.w + 1) > 255) return false;   // column group and n_c slot are bytes
     if (site_max_slots(g) > 65535) return false;
-    return mma_layout(c, nblk, maxc, maxrec, true, lmax).bytes <= kMmaSmemLimit &&
-           mma_layout(c, nblk, maxc, maxrec, false, lmax).bytes <= kMmaSmemLimit;
+    return mma_layout(c, nblk, maxc, maxrec, true, lmax, false).bytes <= kMmaSmemLimit &&
+           mma_layout(c, nblk, maxc, maxrec, false, lmax, true).bytes <= kMmaSmemLimit;
 }
 
-template <int KMAX, bool WX>
+template <int KMAX, bool WX, bool BULK = false>
 static void launch_one(bs2e_block* b, const MmaSmem& lay, cudaStream_t st, int first, int count)
 {
     if (count <= 0) return;
     bs2e_ctx* c = b->ctx;
-    auto kern = site_mma_kernel<KMAX, WX>;
+    auto kern = site_mma_kernel<KMAX, WX, BULK>;
     BS2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     kern<<<(unsigned)count, kMmaThreads, lay.bytes, st>>>(
         c->dg, b->dplan, c->one_body(), b->d_site_key, lay, first, c->d_R, b->d_Hptr, b->d_Sptr, b->d_Hidx,
@@ -683,16 +741,30 @@ void launch_site_mma(bs2e_block* b, cudaStream_t stX, cudaStream_t stD)
     bs2e_ctx* c = b->ctx;
     const int nblk = b->dplan.nblk;
     const int kmax = site_kmax_for(c->hg.K1);
-    const MmaSmem layX = mma_layout(c, nblk, b->ang->host.maxc, b->ang->host.maxrec, true, b->lmax);
-    const MmaSmem layD = mma_layout(c, nblk, b->ang->host.maxc, b->ang->host.maxrec, false, b->lmax);
+    const char* store = getenv("BS2E_MMA_STORE");
+    const bool bulk = store && strcmp(store, "bulk") == 0;
+    const MmaSmem layX = mma_layout(c, nblk, b->ang->host.maxc, b->ang->host.maxrec, true, b->lmax, false);
+    const MmaSmem layD = mma_layout(c, nblk, b->ang->host.maxc, b->ang->host.maxrec, false, b->lmax, bulk);
     if (layX.bytes > kMmaSmemLimit || layD.bytes > kMmaSmemLimit)
         throw Error("block_assemble: site tables exceed shared memory");
     const int nx = b->nsites_x, nd = b->nsites - b->nsites_x;
     switch (kmax) {
-    case 7: launch_one<7, true>(b, layX, stX, 0, nx); launch_one<7, false>(b, layD, stD, nx, nd); break;
-    case 13: launch_one<13, true>(b, layX, stX, 0, nx); launch_one<13, false>(b, layD, stD, nx, nd); break;
-    case 21: launch_one<21, true>(b, layX, stX, 0, nx); launch_one<21, false>(b, layD, stD, nx, nd); break;
-    case 31: launch_one<31, true>(b, layX, stX, 0, nx); launch_one<31, false>(b, layD, stD, nx, nd); break;
+    case 7:
+        launch_one<7, true>(b, layX, stX, 0, nx);
+        if (bulk) launch_one<7, false, true>(b, layD, stD, nx, nd); else launch_one<7, false>(b, layD, stD, nx, nd);
+        break;
+    case 13:
+        launch_one<13, true>(b, layX, stX, 0, nx);
+        if (bulk) launch_one<13, false, true>(b, layD, stD, nx, nd); else launch_one<13, false>(b, layD, stD, nx, nd);
+        break;
+    case 21:
+        launch_one<21, true>(b, layX, stX, 0, nx);
+        if (bulk) launch_one<21, false, true>(b, layD, stD, nx, nd); else launch_one<21, false>(b, layD, stD, nx, nd);
+        break;
+    case 31:
+        launch_one<31, true>(b, layX, stX, 0, nx);
+        if (bulk) launch_one<31, false, true>(b, layD, stD, nx, nd); else launch_one<31, false>(b, layD, stD, nx, nd);
+        break;
     default: throw Error("block_assemble: no site kernel for this max_k");
     }
 }

@@ -20,13 +20,14 @@ struct MmaSmem {    // element counts of the dynamic shared memory carve-up
     int cap;        // records per parity list
     int chrec;      // records per staging buffer (multiple of 8)
     int nl;         // l_max + 1 of the one-particle matrices
+    int rowb;       // bytes per row of the CTA-level value staging (sites without exchange windows)
     // byte offsets of the pieces (kept in the constant bank by the kernel)
     int off_cfs, off_ob, off_recs, off_rcache, off_sblk, off_mtab, off_mraw, off_jb, off_ncq, off_cand, off_cprefix, off_stage,
         off_srow, off_tot, off_mbar, off_misc;
     size_t bytes;
 };
 
-MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, int lmax);
+MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, int lmax, bool bulk);
 bool site_mma_usable(const bs2e_ctx* c, int nblk, int maxc, int maxrec, int lmax);
 // the two launches of a block: sites with exchange windows on stX, the others on stD
 void launch_site_mma(bs2e_block* b, cudaStream_t stX, cudaStream_t stD);

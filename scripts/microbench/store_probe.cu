@@ -107,6 +107,10 @@ __global__ void k_mixed(char* out, long long* idx, size_t elems_per_warp, int id
                 if (idx_mode == 1) __stcs(iout + (t * 8 + row) * 32 + col, (long long)col);
                 if (idx_mode == 2) *reinterpret_cast<long long*>(tile + 4096 + row * 320 + 8 + col * 8) = col;
             }
+        if (idx_mode == 3) {   // indices row-wise: one 256-byte run per store instruction
+#pragma unroll
+            for (int row = 0; row < 8; ++row) __stcs(iout + (t * 8 + row) * 32 + lane, (long long)lane);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane < 8) {
@@ -162,12 +166,13 @@ int main()
                 report(name, (double)(n_per / rowlen) * rowlen * ctas * (wi ? 24 : 16));
             }
         }
-        for (int mode = 0; mode < 3; ++mode) {
+        for (int mode = 0; mode < 4; ++mode) {
             const size_t epw = (total / 16 / (ctas * 8)) & ~(size_t)255;
             cudaEventRecord(e0);
             k_mixed<<<ctas, 256, 8 * 6656>>>(buf, idx, epw, mode);
-            const char* nm[3] = {"staged values -> bulk (512 B rows), no indices", "staged values -> bulk + indices by STG.64",
-                                 "staged values and indices -> bulk (+2 STG per row)"};
+            const char* nm[4] = {"staged values -> bulk (512 B rows), no indices", "staged values -> bulk + indices by STG.64",
+                                 "staged values and indices -> bulk (+2 STG per row)",
+                                 "staged values -> bulk + indices row-wise (256 B runs)"};
             report(nm[mode], (double)((epw - 2) / 256) * 256 * ctas * 8 * (mode ? 24 : 16));
         }
         for (int chunk : {512, 3600}) {

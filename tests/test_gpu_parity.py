@@ -424,13 +424,15 @@ def test_stage_C_both_site_kernels(case, monkeypatch):
             continue
         H, S, _ = run.block(s)
         out = {}
-        for fill in ("mma", "fma"):
-            monkeypatch.setenv("BS2E_FILL", fill)
+        for fill in ("mma", "mma-bulk", "fma"):   # mma-bulk: rows leave through cp.async.bulk shared -> global
+            monkeypatch.setenv("BS2E_FILL", fill.split("-")[0])
+            monkeypatch.setenv("BS2E_MMA_STORE", "bulk" if fill.endswith("bulk") else "stg")
             b = ctx.block_plan(s, False); b.assemble(); out[fill] = b.download(); b.free()
             assert_csr_equal(out[fill][0], H, what=f"H[{fill}] L={s.l} pi={s.pi}")
             assert_csr_equal(out[fill][1], S, what=f"S[{fill}] L={s.l} pi={s.pi}")
-        for a, b in zip(out["mma"], out["fma"]):
-            assert np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+        for other in ("mma-bulk", "fma"):
+            for a, b in zip(out["mma"], out[other]):
+                assert np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data), other
 
 
 def _sampled_rows_vs_oracle(run, ctx, s, label, nrows=16, where=(0.0, 0.37, 1.0), ranges_of=None):
