@@ -1064,8 +1064,10 @@ void block_free(bs2e_block* b)
         if (b->d_Hdat) cudaFreeAsync(b->d_Hdat, st);
         if (b->d_Sdat) cudaFreeAsync(b->d_Sdat, st);
     }
-    b->arena1.release();
-    b->arena0.release();
+    if (b->ctx) {   // the plan tables go back to the context's pool, reusable once the queued work has read them
+        arena_give(b->ctx, b->arena1, b->ctx->stream);
+        arena_give(b->ctx, b->arena0, b->ctx->stream);
+    }
     delete b;
 }
 

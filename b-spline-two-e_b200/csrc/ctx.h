@@ -64,35 +64,29 @@ T* dev_upload(const std::vector<T>& v, cudaStream_t st)
     return p;
 }
 
-// One stream-ordered allocation carved into aligned pieces (the plan tables of a block).
-struct DevArena {
+// Plan tables of a block: one buffer carved into aligned pieces.  The buffers come from a small per-context
+// pool (arena_take / arena_give, plan_dev.cu) instead of the stream-ordered allocator: a plan is built on the
+// context's PLAN stream while the fill of the previous block still runs on the main stream, and a buffer
+// released behind that fill (event on the main stream) must not tie the two streams together.
+struct ArenaBuf {
     char* base = nullptr;
-    size_t size = 0, used = 0;
-    cudaStream_t st = nullptr;
-    void reserve(size_t bytes, cudaStream_t s)
-    {
-        release();
-        st = s;
-        size = bytes + 256;
-        BS2E_CUDA(cudaMallocAsync(&base, size, st));
-        used = 0;
-    }
+    size_t size = 0;
+    cudaEvent_t free_after = nullptr;   // recorded on the stream of the last reader when the buffer is given back
+    bool busy = false;
+};
+struct DevArena {
+    ArenaBuf* buf = nullptr;
+    size_t used = 0;
     template <class T>
     T* take(size_t n)
     {
         const size_t at = (used + 255) & ~(size_t)255;
         const size_t bytes = sizeof(T) * (n ? n : 1);
-        if (at + bytes > size) throw Error("internal: plan arena overflow");
+        if (!buf || at + bytes > buf->size) throw Error("internal: plan arena overflow");
         used = at + bytes;
-        return reinterpret_cast<T*>(base + at);
+        return reinterpret_cast<T*>(buf->base + at);
     }
     static size_t need(size_t bytes) { return ((bytes ? bytes : 1) + 255) & ~(size_t)255; }
-    void release()
-    {
-        if (base) cudaFreeAsync(base, st);
-        base = nullptr;
-        size = used = 0;
-    }
 };
 
 // angular tables of one (L, list of (l1,l2) groups, max_k): computed once per context with
@@ -138,6 +132,9 @@ struct bs2e_ctx {
     // plan state shared by the calls on this context (serialised by plan_mu)
     std::mutex plan_mu;
     std::map<std::vector<int>, std::shared_ptr<bs2e::AngDev>> ang_cache;
+    cudaStream_t plan_stream = nullptr;   // plans are built here, concurrently with fills on `stream`
+    std::mutex arena_mu;
+    std::vector<bs2e::ArenaBuf*> arenas;  // pool of plan buffers (arena_take / arena_give)
     int* h_pin = nullptr;        // pinned staging for the small read-backs of a plan
     size_t h_pin_bytes = 0;
     // copy stream + pinned bounce buffers for downloads into pageable memory (download.cu)
@@ -228,6 +225,8 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
 bs2e_configs* configs_upload(bs2e_ctx* c, long long n_config, const int64_t* conf_n, const int64_t* conf_l);
 void configs_free(bs2e_configs* cfg);
 void ctx_release_plan_state(bs2e_ctx* c);
+void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes);          // a free pool buffer of at least `bytes`
+void arena_give(bs2e_ctx* c, DevArena& a, cudaStream_t last_use);  // back to the pool, reusable after the work queued on last_use
 // per-row tables (row_n1 / row_n2 / row_blk) of a configuration list, built on the device
 void build_row_tables(cudaStream_t st, long long n_config, const long long* d_conf_n, int nblk,
                       const int* d_blk_start, unsigned short* row_n1, unsigned short* row_n2,

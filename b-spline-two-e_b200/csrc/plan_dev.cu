@@ -207,9 +207,60 @@ void configs_free(bs2e_configs* cfg)
     delete cfg;
 }
 
+void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes)
+{
+    bytes += 256;
+    ArenaBuf* pick = nullptr;
+    {
+        // a buffer whose last reader has finished; a new one while the pool is small (waiting for a buffer that was
+        // released behind a running fill would serialise the plan with that fill); else any free one
+        std::lock_guard<std::mutex> lk(c->arena_mu);
+        const int passes = c->arenas.size() < 16 ? 1 : 2;
+        for (int pass = 0; pass < passes && !pick; ++pass)
+            for (ArenaBuf* q : c->arenas) {
+                if (q->busy || q->size < bytes) continue;
+                if (pass == 0 && cudaEventQuery(q->free_after) != cudaSuccess) { cudaGetLastError(); continue; }
+                pick = q;
+                break;
+            }
+        if (pick) pick->busy = true;
+    }
+    if (pick) {
+        BS2E_CUDA(cudaEventSynchronize(pick->free_after));
+    } else {
+        std::unique_ptr<ArenaBuf> q(new ArenaBuf());
+        q->size = bytes + bytes / 4;
+        BS2E_CUDA(cudaMalloc(&q->base, q->size));
+        BS2E_CUDA(cudaEventCreateWithFlags(&q->free_after, cudaEventDisableTiming));
+        q->busy = true;
+        pick = q.release();
+        std::lock_guard<std::mutex> lk(c->arena_mu);
+        c->arenas.push_back(pick);
+    }
+    a.buf = pick;
+    a.used = 0;
+}
+
+void arena_give(bs2e_ctx* c, DevArena& a, cudaStream_t last_use)
+{
+    if (!a.buf) return;
+    cudaEventRecord(a.buf->free_after, last_use);
+    std::lock_guard<std::mutex> lk(c->arena_mu);
+    a.buf->busy = false;
+    a.buf = nullptr;
+    a.used = 0;
+}
+
 void ctx_release_plan_state(bs2e_ctx* c)
 {
     c->ang_cache.clear();
+    for (ArenaBuf* q : c->arenas) {
+        cudaFree(q->base);
+        if (q->free_after) cudaEventDestroy(q->free_after);
+        delete q;
+    }
+    c->arenas.clear();
+    if (c->plan_stream) { cudaStreamSynchronize(c->plan_stream); cudaStreamDestroy(c->plan_stream); c->plan_stream = nullptr; }
     if (c->h_pin) cudaFreeHost(c->h_pin);
     c->h_pin = nullptr;
     c->h_pin_bytes = 0;
@@ -254,7 +305,12 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         throw Error(e.what());
     }
     b->nrows = nrows;
-    cudaStream_t st = c->stream;
+    if (!c->plan_stream) {   // highest priority: the small plan kernels must not queue behind the CTAs of a running fill
+        int lo = 0, hi = 0;
+        BS2E_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BS2E_CUDA(cudaStreamCreateWithPriority(&c->plan_stream, cudaStreamNonBlocking, hi));
+    }
+    cudaStream_t st = c->plan_stream;   // not the main stream: the plan overlaps the fill of the previous block
     const int nr = (int)rlo.size();
 
     // ---- arena 0: configuration list (unless resident), boundary list, counters, row ranges ----
@@ -262,7 +318,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         size_t bytes = DevArena::need(sizeof(int4) * kBoundCap) + DevArena::need(sizeof(int) * kCounters) +
                        DevArena::need(sizeof(int) * 3 * nr) + 1024;
         if (!cfg) bytes += 2 * DevArena::need(sizeof(long long) * 2 * n_config);
-        b->arena0.reserve(bytes, st);
+        arena_take(c, b->arena0, bytes);
     }
     if (cfg) {
         b->d_conf_n = cfg->d_n;
@@ -344,7 +400,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
                        4 * DevArena::need(sizeof(long long) * ((size_t)nrows + 1)) + DevArena::need(scan_tmp) +
                        DevArena::need(sort_tmp) + 1024;
         if (!b->use_site) bytes += 3 * DevArena::need(sizeof(unsigned short) * n_config);
-        b->arena1.reserve(bytes, st);
+        arena_take(c, b->arena1, bytes);
     }
     BlockDesc* d_blk = b->arena1.take<BlockDesc>(nblk);
     b->d_blk_start = b->arena1.take<int>(nblk + 1);
@@ -409,7 +465,10 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         pl.row_blk = rblk;
     }
     // count pass + scan, then one read-back: error bits, number of sites, totals
-    block_count_scan(b, false);
+    {
+        const BlockStreams ps{st, st, nullptr, nullptr};
+        block_count_scan(b, false, &ps);
+    }
     long long* h_tot = reinterpret_cast<long long*>(c->h_pin + 16);
     BS2E_CUDA(cudaMemcpyAsync(h_cnt, b->d_counters, sizeof(int) * kCounters, cudaMemcpyDeviceToHost, st));
     BS2E_CUDA(cudaMemcpyAsync(h_tot, b->d_Hptr + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
