@@ -14,6 +14,8 @@
 #include "geom_host.h"
 #include "plan.h"
 
+struct bs2e_ctx;
+
 namespace bs2e {
 
 struct Error : std::runtime_error {
@@ -102,6 +104,18 @@ struct AngDev {
     }
 };
 
+// group structure of a configuration list on the device (plan_dev.cu: build_structure)
+struct GroupStructure {
+    bs2e_ctx* ctx = nullptr;
+    int nblk = 0, max_nd = 0, lmax = 0;
+    std::vector<BlockDesc> blocks;   // (l1, l2) of every group (host copy: key of the angular tables)
+    char* d_mem = nullptr;           // one allocation behind the three tables
+    BlockDesc* d_blk = nullptr;      // [nblk] with the n(1) ranges filled in
+    int* d_blk_start = nullptr;      // [nblk+1] first configuration (0-based) of each group
+    NcRow* d_ncrow = nullptr;        // [nblk][nb+1]
+    ~GroupStructure();
+};
+
 }  // namespace bs2e
 
 struct bs2e_ctx;
@@ -110,6 +124,7 @@ struct bs2e_configs {
     bs2e_ctx* ctx = nullptr;
     long long n = 0;
     long long *d_n = nullptr, *d_l = nullptr;  // (2, n) each, as given by the caller
+    mutable std::shared_ptr<bs2e::GroupStructure> gs;   // built by the first plan of the list
 };
 
 struct bs2e_ctx {
@@ -188,6 +203,7 @@ struct bs2e_block {
     // device-side plan storage: two stream-ordered arenas (before / after the structure read-back)
     bs2e::DevArena arena0, arena1;
     std::shared_ptr<bs2e::AngDev> ang;   // shared through the context's cache
+    std::shared_ptr<bs2e::GroupStructure> gs;   // group tables (shared with the resident configuration list, if any)
     const long long *d_conf_n = nullptr, *d_conf_l = nullptr;   // configuration list on the device (owned by arena0 or by a bs2e_configs)
     int* d_blk_start = nullptr;          // [nblk+1] first configuration (0-based) of each (l1,l2) group
     // radial sites of the planned rows, sorted (plan.h: site_sort_key); counters[0] = nsites, [1] = nsites_x

@@ -251,6 +251,8 @@ void arena_give(bs2e_ctx* c, DevArena& a, cudaStream_t last_use)
     a.used = 0;
 }
 
+GroupStructure::~GroupStructure() { cudaFree(d_mem); }
+
 void ctx_release_plan_state(bs2e_ctx* c)
 {
     c->ang_cache.clear();
@@ -267,6 +269,91 @@ void ctx_release_plan_state(bs2e_ctx* c)
 }
 
 bool site_kernel_usable(const bs2e_ctx* c, int nblk, int lmax);   // block.cu
+
+// The (l1,l2) group structure of a configuration list: group boundaries, per group and n(1) the range of n(2)
+// and the first configuration index.  It depends on the list only, so a list kept resident on the device
+// (bs2e_configs) carries it from its first plan on; a plan then costs the radial-site enumeration, the count
+// pass and ONE host synchronisation.
+std::shared_ptr<GroupStructure> build_structure(bs2e_ctx* c, long long n_config, const long long* d_conf_n,
+                                                const long long* d_conf_l, cudaStream_t st)
+{
+    const Geom& hg = c->hg;
+    auto gs = std::make_shared<GroupStructure>();
+    gs->ctx = c;
+    const int stride = hg.nb + 1;
+    // counters + boundary list first (their size does not depend on the number of groups)
+    DevArena tmp;
+    arena_take(c, tmp, DevArena::need(sizeof(int4) * kBoundCap) + DevArena::need(sizeof(int) * kCounters) + 1024);
+    struct Give { bs2e_ctx* c; DevArena& a; cudaStream_t st; ~Give() { arena_give(c, a, st); } } give{c, tmp, st};
+    int4* d_bounds = tmp.take<int4>(kBoundCap);
+    int* d_counters = tmp.take<int>(kCounters);
+    ensure_pin(c, 64 + sizeof(int4) * kBoundCap + sizeof(BlockDesc) * kBoundCap + sizeof(int) * (kBoundCap + 1) + 256);
+    BS2E_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * kCounters, st));
+    conf_scan_kernel<<<(unsigned)((n_config + 255) / 256), 256, 0, st>>>(n_config, d_conf_n, d_conf_l, hg.nb, d_counters,
+                                                                        d_bounds);
+    BS2E_LAUNCHED();
+    int* h_cnt = c->h_pin;
+    int4* h_bounds = reinterpret_cast<int4*>(c->h_pin + 16);
+    BS2E_CUDA(cudaMemcpyAsync(h_cnt, d_counters, sizeof(int) * kCounters, cudaMemcpyDeviceToHost, st));
+    BS2E_CUDA(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(int4) * kBoundCap, cudaMemcpyDeviceToHost, st));
+    BS2E_CUDA(cudaStreamSynchronize(st));
+    {
+        const int err = h_cnt[kCntErr];
+        if (err & kErrRangeN) throw Error("block_plan: configuration n outside 1..n_b");
+        if (err & kErrOrderL) throw Error("block_plan: configurations must have l(1) >= l(2) >= 0 (count_configs order)");
+        if ((err & kErrBounds) || h_cnt[kCntBounds] > kMaxBlocks) throw Error("block_plan: too many (l1,l2) blocks");
+    }
+    const int nblk = h_cnt[kCntBounds];
+    gs->nblk = nblk;
+    gs->max_nd = h_cnt[kCntMaxNd];
+    gs->lmax = h_cnt[kCntLmax];
+    std::vector<int4> bounds(h_bounds, h_bounds + nblk);
+    std::sort(bounds.begin(), bounds.end(), [](const int4& a, const int4& q) { return a.x < q.x; });
+    gs->blocks.resize(nblk);
+    std::vector<int> blk_start(nblk + 1);
+    {
+        std::set<std::pair<int, int>> seen;
+        for (int q = 0; q < nblk; ++q) {
+            gs->blocks[q] = BlockDesc{bounds[q].y, bounds[q].z, 0, 0};
+            blk_start[q] = bounds[q].x;
+            if (!seen.insert({bounds[q].y, bounds[q].z}).second)
+                throw Error("block_plan: configurations of one (l1,l2) pair are not contiguous");
+            if (((bounds[q].y + bounds[q].z) & 1) != ((bounds[0].y + bounds[0].z) & 1))
+                throw Error("block_plan: configurations of both parities in one symmetry block");
+        }
+        blk_start[nblk] = (int)n_config;
+    }
+    {
+        const size_t b0 = DevArena::need(sizeof(BlockDesc) * nblk), b1 = DevArena::need(sizeof(int) * (nblk + 1));
+        BS2E_CUDA(cudaMalloc(&gs->d_mem, b0 + b1 + DevArena::need(sizeof(NcRow) * (size_t)nblk * stride)));
+        gs->d_blk = reinterpret_cast<BlockDesc*>(gs->d_mem);
+        gs->d_blk_start = reinterpret_cast<int*>(gs->d_mem + b0);
+        gs->d_ncrow = reinterpret_cast<NcRow*>(gs->d_mem + b0 + b1);
+    }
+    {   // small host -> device tables through the pinned staging buffer
+        char* hp = reinterpret_cast<char*>(c->h_pin);
+        std::memcpy(hp, gs->blocks.data(), sizeof(BlockDesc) * nblk);
+        BS2E_CUDA(cudaMemcpyAsync(gs->d_blk, hp, sizeof(BlockDesc) * nblk, cudaMemcpyHostToDevice, st));
+        char* hp2 = hp + ((sizeof(BlockDesc) * nblk + 15) & ~(size_t)15);
+        std::memcpy(hp2, blk_start.data(), sizeof(int) * (nblk + 1));
+        BS2E_CUDA(cudaMemcpyAsync(gs->d_blk_start, hp2, sizeof(int) * (nblk + 1), cudaMemcpyHostToDevice, st));
+    }
+    const size_t ncells = (size_t)nblk * stride;
+    ncrow_init_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(ncells, gs->d_ncrow);
+    BS2E_LAUNCHED();
+    BS2E_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * kCounters, st));
+    ncrow_build_kernel<<<(unsigned)((n_config + 255) / 256), 256, 0, st>>>(n_config, d_conf_n, nblk, gs->d_blk_start, stride,
+                                                                          gs->d_ncrow, gs->d_blk, d_counters);
+    BS2E_LAUNCHED();
+    BS2E_CUDA(cudaMemcpyAsync(h_cnt, d_counters, sizeof(int) * kCounters, cudaMemcpyDeviceToHost, st));
+    BS2E_CUDA(cudaStreamSynchronize(st));
+    {
+        const int err = h_cnt[kCntErr];
+        if (err & kErrN1) throw Error("block_plan: n(1) not ascending inside an (l1,l2) block");
+        if (err & kErrN2) throw Error("block_plan: n(2) not consecutive inside an n(1) row");
+    }
+    return gs;
+}
 
 bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* conf_n, const int64_t* conf_l,
                        const bs2e_configs* cfg, int full, long long n_ranges, const int64_t* range_lo,
@@ -313,69 +400,30 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     cudaStream_t st = c->plan_stream;   // not the main stream: the plan overlaps the fill of the previous block
     const int nr = (int)rlo.size();
 
-    // ---- arena 0: configuration list (unless resident), boundary list, counters, row ranges ----
-    {
-        size_t bytes = DevArena::need(sizeof(int4) * kBoundCap) + DevArena::need(sizeof(int) * kCounters) +
-                       DevArena::need(sizeof(int) * 3 * nr) + 1024;
-        if (!cfg) bytes += 2 * DevArena::need(sizeof(long long) * 2 * n_config);
-        arena_take(c, b->arena0, bytes);
-    }
+    // ---- the configuration list on the device and its group structure ----
     if (cfg) {
         b->d_conf_n = cfg->d_n;
         b->d_conf_l = cfg->d_l;
+        if (!cfg->gs) cfg->gs = build_structure(c, n_config, cfg->d_n, cfg->d_l, st);
+        b->gs = cfg->gs;
     } else {
         if (!conf_n || !conf_l) throw Error("block_plan: null configuration arrays");
+        arena_take(c, b->arena0, 2 * DevArena::need(sizeof(long long) * 2 * n_config) + 1024);
         long long* dn = b->arena0.take<long long>(2 * (size_t)n_config);
         long long* dl = b->arena0.take<long long>(2 * (size_t)n_config);
         BS2E_CUDA(cudaMemcpyAsync(dn, conf_n, sizeof(long long) * 2 * n_config, cudaMemcpyHostToDevice, st));
         BS2E_CUDA(cudaMemcpyAsync(dl, conf_l, sizeof(long long) * 2 * n_config, cudaMemcpyHostToDevice, st));
         b->d_conf_n = dn;
         b->d_conf_l = dl;
+        b->gs = build_structure(c, n_config, dn, dl, st);
     }
-    int4* d_bounds = b->arena0.take<int4>(kBoundCap);
-    b->d_counters = b->arena0.take<int>(kCounters);
-    int* d_ranges = b->arena0.take<int>(3 * (size_t)nr);
-    // pinned staging: counters + boundary list coming back, the small tables going out (bounded by kMaxBlocks groups)
-    ensure_pin(c, 64 + sizeof(int4) * kBoundCap + sizeof(BlockDesc) * kBoundCap + sizeof(int) * (kBoundCap + 1) +
-                      sizeof(int) * 3 * (size_t)nr + 256);
-    BS2E_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * kCounters, st));
-    conf_scan_kernel<<<(unsigned)((n_config + 255) / 256), 256, 0, st>>>(n_config, b->d_conf_n, b->d_conf_l, hg.nb,
-                                                                        b->d_counters, d_bounds);
-    BS2E_LAUNCHED();
-    int* h_cnt = c->h_pin;
-    int4* h_bounds = reinterpret_cast<int4*>(c->h_pin + 16);
-    BS2E_CUDA(cudaMemcpyAsync(h_cnt, b->d_counters, sizeof(int) * kCounters, cudaMemcpyDeviceToHost, st));
-    BS2E_CUDA(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(int4) * kBoundCap, cudaMemcpyDeviceToHost, st));
-    BS2E_CUDA(cudaStreamSynchronize(st));
-    {
-        const int err = h_cnt[kCntErr];
-        if (err & kErrRangeN) throw Error("block_plan: configuration n outside 1..n_b");
-        if (err & kErrOrderL) throw Error("block_plan: configurations must have l(1) >= l(2) >= 0 (count_configs order)");
-        if ((err & kErrBounds) || h_cnt[kCntBounds] > kMaxBlocks) throw Error("block_plan: too many (l1,l2) blocks");
-    }
-    const int nblk = h_cnt[kCntBounds];
-    const int max_nd = h_cnt[kCntMaxNd];
-    b->lmax = h_cnt[kCntLmax];
-    std::vector<int4> bounds(h_bounds, h_bounds + nblk);
-    std::sort(bounds.begin(), bounds.end(), [](const int4& a, const int4& q) { return a.x < q.x; });
-    std::vector<BlockDesc> blocks(nblk);
-    std::vector<int> blk_start(nblk + 1);
-    {
-        std::set<std::pair<int, int>> seen;
-        for (int q = 0; q < nblk; ++q) {
-            blocks[q] = BlockDesc{bounds[q].y, bounds[q].z, 0, 0};
-            blk_start[q] = bounds[q].x;
-            if (!seen.insert({bounds[q].y, bounds[q].z}).second)
-                throw Error("block_plan: configurations of one (l1,l2) pair are not contiguous");
-            if (((bounds[q].y + bounds[q].z) & 1) != ((bounds[0].y + bounds[0].z) & 1))
-                throw Error("block_plan: configurations of both parities in one symmetry block");
-        }
-        blk_start[nblk] = (int)n_config;
-    }
-    b->ang = ang_tables(c, blocks, L, st);
+    const GroupStructure& gs = *b->gs;
+    const int nblk = gs.nblk, max_nd = gs.max_nd;
+    b->lmax = gs.lmax;
+    b->d_blk_start = gs.d_blk_start;
+    b->ang = ang_tables(c, gs.blocks, L, st);
 
-    // ---- arena 1: group tables, site keys, count / pointer arrays, scan and sort scratch ----
-    const int stride = hg.nb + 1;
+    // ---- arena 1: site keys, counters, row ranges, count / pointer arrays, scan and sort scratch ----
     const int site_cap = hg.nb * std::max(1, max_nd);
     b->site_cap = site_cap;
     b->use_site = site_kernel_usable(c, nblk, b->lmax);
@@ -394,17 +442,15 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     BS2E_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const unsigned long long*)nullptr,
                                              (unsigned long long*)nullptr, site_cap, 0, 43, st));
     {
-        size_t bytes = DevArena::need(sizeof(BlockDesc) * nblk) + DevArena::need(sizeof(int) * (nblk + 1)) +
-                       DevArena::need(sizeof(NcRow) * (size_t)nblk * stride) +
+        size_t bytes = DevArena::need(sizeof(int) * kCounters) + DevArena::need(sizeof(int) * 3 * nr) +
                        2 * DevArena::need(sizeof(unsigned long long) * site_cap) +
                        4 * DevArena::need(sizeof(long long) * ((size_t)nrows + 1)) + DevArena::need(scan_tmp) +
                        DevArena::need(sort_tmp) + 1024;
         if (!b->use_site) bytes += 3 * DevArena::need(sizeof(unsigned short) * n_config);
         arena_take(c, b->arena1, bytes);
     }
-    BlockDesc* d_blk = b->arena1.take<BlockDesc>(nblk);
-    b->d_blk_start = b->arena1.take<int>(nblk + 1);
-    NcRow* d_ncrow = b->arena1.take<NcRow>((size_t)nblk * stride);
+    b->d_counters = b->arena1.take<int>(kCounters);
+    int* d_ranges = b->arena1.take<int>(3 * (size_t)nr);
     unsigned long long* d_keys_raw = b->arena1.take<unsigned long long>(site_cap);
     b->d_site_key = b->arena1.take<unsigned long long>(site_cap);
     b->d_cntH = b->arena1.take<long long>((size_t)nrows + 1);
@@ -414,25 +460,20 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     b->d_scan_tmp = b->arena1.take<char>(scan_tmp);
     b->scan_tmp_bytes = scan_tmp;
     void* d_sort_tmp = b->arena1.take<char>(sort_tmp);
-    // small host -> device tables through the pinned staging buffer
-    {
-        char* hp = reinterpret_cast<char*>(c->h_pin);
-        size_t at = 0;
-        auto put = [&](void* dst, const void* src, size_t bytes) {
-            std::memcpy(hp + at, src, bytes);
-            BS2E_CUDA(cudaMemcpyAsync(dst, hp + at, bytes, cudaMemcpyHostToDevice, st));
-            at += (bytes + 15) & ~(size_t)15;
-        };
-        put(d_blk, blocks.data(), sizeof(BlockDesc) * nblk);
-        put(b->d_blk_start, blk_start.data(), sizeof(int) * (nblk + 1));
-        put(d_ranges, rlo.data(), sizeof(int) * nr);
-        put(d_ranges + nr, rhi.data(), sizeof(int) * nr);
-        put(d_ranges + 2 * nr, roff.data(), sizeof(int) * nr);
+    ensure_pin(c, 64 + sizeof(int) * 3 * (size_t)nr + 256 + sizeof(int4) * kBoundCap + sizeof(BlockDesc) * kBoundCap +
+                      sizeof(int) * (kBoundCap + 1));
+    {   // the row ranges through the pinned staging buffer (behind the 64 bytes of the read-backs)
+        int* hp = c->h_pin + 16;
+        std::memcpy(hp, rlo.data(), sizeof(int) * nr);
+        std::memcpy(hp + nr, rhi.data(), sizeof(int) * nr);
+        std::memcpy(hp + 2 * nr, roff.data(), sizeof(int) * nr);
+        BS2E_CUDA(cudaMemcpyAsync(d_ranges, hp, sizeof(int) * 3 * nr, cudaMemcpyHostToDevice, st));
     }
+    BS2E_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * kCounters, st));
     pl.nblk = nblk;
     pl.max_nd = max_nd;
-    pl.blk = d_blk;
-    pl.ncrow = d_ncrow;
+    pl.blk = gs.d_blk;
+    pl.ncrow = gs.d_ncrow;
     pl.flags = b->ang->flags;
     pl.krange = b->ang->krange;
     pl.angD = b->ang->angD;
@@ -441,14 +482,6 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     pl.nkp = b->ang->host.nkp;
     pl.nrows = nrows;
     pl.rr = RowRanges{nr, d_ranges, d_ranges + nr, d_ranges + 2 * nr, rlo[0], rhi[0]};
-    {
-        const size_t ncells = (size_t)nblk * stride;
-        ncrow_init_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(ncells, d_ncrow);
-        BS2E_LAUNCHED();
-        ncrow_build_kernel<<<(unsigned)((n_config + 255) / 256), 256, 0, st>>>(n_config, b->d_conf_n, nblk, b->d_blk_start,
-                                                                              stride, d_ncrow, d_blk, b->d_counters);
-        BS2E_LAUNCHED();
-    }
     if (b->use_site) {
         BS2E_CUDA(cudaMemsetAsync(d_keys_raw, 0xff, sizeof(unsigned long long) * site_cap, st));
         site_enum_kernel<<<(unsigned)((site_cap + 127) / 128), 128, 0, st>>>(c->dg, pl, site_cap, d_keys_raw, b->d_counters);
@@ -459,26 +492,22 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         unsigned short* rn1 = b->arena1.take<unsigned short>(n_config);
         unsigned short* rn2 = b->arena1.take<unsigned short>(n_config);
         unsigned short* rblk = b->arena1.take<unsigned short>(n_config);
-        build_row_tables(st, n_config, b->d_conf_n, nblk, b->d_blk_start, rn1, rn2, rblk);
+        build_row_tables(st, n_config, b->d_conf_n, nblk, gs.d_blk_start, rn1, rn2, rblk);
         pl.row_n1 = rn1;
         pl.row_n2 = rn2;
         pl.row_blk = rblk;
     }
-    // count pass + scan, then one read-back: error bits, number of sites, totals
+    // count pass + scan, then one read-back: number of sites, totals
     {
         const BlockStreams ps{st, st, nullptr, nullptr};
         block_count_scan(b, false, &ps);
     }
-    long long* h_tot = reinterpret_cast<long long*>(c->h_pin + 16);
+    int* h_cnt = c->h_pin;
+    long long* h_tot = reinterpret_cast<long long*>(c->h_pin + 8);
     BS2E_CUDA(cudaMemcpyAsync(h_cnt, b->d_counters, sizeof(int) * kCounters, cudaMemcpyDeviceToHost, st));
     BS2E_CUDA(cudaMemcpyAsync(h_tot, b->d_Hptr + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
     BS2E_CUDA(cudaMemcpyAsync(h_tot + 1, b->d_Sptr + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
     BS2E_CUDA(cudaStreamSynchronize(st));
-    {
-        const int err = h_cnt[kCntErr];
-        if (err & kErrN1) throw Error("block_plan: n(1) not ascending inside an (l1,l2) block");
-        if (err & kErrN2) throw Error("block_plan: n(2) not consecutive inside an n(1) row");
-    }
     b->nsites = h_cnt[kCntSites];
     b->nsites_x = h_cnt[kCntSitesX];
     if (b->nsites > site_cap) throw Error("internal: site list overflow");

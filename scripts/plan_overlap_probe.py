@@ -6,6 +6,7 @@ import torch, bs2e
 from bs2e.sharding import exchange_cost, site_partition
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 nshare = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 setup = bs2e.BasisSetup(device=0, **bs2e.CONFIGS[wl])
 S, H_vec, syms = setup.host_inputs()
 ctx = setup.open()
@@ -18,7 +19,7 @@ for s, c in zip(syms, cfgs):
         ranges.append([(1, s.n_config)])
     else:
         tmp = ctx.block_plan(s, False, cfg=c); cH, cS = tmp.row_counts(); tmp.free()
-        ranges.append(site_partition(s.conf_n, cH + cS, nshare, setup.k, exchange_cost(setup.p['max_k']))[0])
+        ranges.append(site_partition(s.conf_n, cH + cS, nshare, setup.k, exchange_cost(setup.p['max_k']))[which])
 ctx.sync()
 for rep in range(4):
     t = []
