@@ -47,6 +47,10 @@ ABI = {
     "bs2e_rk_get": (C.c_int, [vp, i64, _pi, _pd]),
     "bs2e_rk_plane": (C.c_int, [vp, i64, _pd]),
     "bs2e_set_one_particle": (C.c_int, [vp, i64, _pd, _pd]),
+    "bs2e_one_particle_device": (C.c_int, [vp, i64, i64, i64, f64, f64, f64]),
+    "bs2e_get_one_particle": (C.c_int, [vp, vp, vp]),
+    "bs2e_radial_dipole_device": (C.c_int, [vp, i64]),
+    "bs2e_get_radial_dipole": (C.c_int, [vp, vp, vp]),
     "bs2e_block_count": (C.c_int, [vp, i64, i64, _pi, _pi, i64, C.POINTER(i64), C.POINTER(i64)]),
     "bs2e_block_fill": (C.c_int, [vp, i64, i64, _pi, _pi, i64, vp, vp, vp, vp, vp, vp]),
     "bs2e_block_plan": (C.c_int, [vp, i64, i64, _pi, _pi, i64, i64, i64, C.POINTER(vp)]),
@@ -404,6 +408,34 @@ class Context:
         Sf = np.ascontiguousarray(np.asfortranarray(S).ravel(order="F").view(np.float64))
         _chk(lib().bs2e_set_one_particle(self.h, len(H_vec) - 1, Hv, Sf))
 
+    def one_particle_device(self, Z, max_l_1p, CAP_order, CAP_r_0, CAP_eta):
+        """setup_S + setup_H_one_particle on the device (mat_els.f90:47-118); replaces set_one_particle"""
+        eta = complex(CAP_eta)
+        _chk(lib().bs2e_one_particle_device(self.h, Z, max_l_1p, CAP_order, CAP_r_0, eta.real, eta.imag))
+        self._lmax_1p = max_l_1p
+
+    def get_one_particle(self):
+        """(H_vec, S) as the Fortran (n, n') matrices"""
+        nb, nl = self.n_b, self._lmax_1p + 1
+        H = np.zeros(2 * nb * nb * nl)
+        S = np.zeros(2 * nb * nb)
+        _chk(lib().bs2e_get_one_particle(self.h, _ptr(H), _ptr(S)))
+        Hc = H.view(np.complex128).reshape(nl, nb * nb)
+        return [Hc[l].reshape(nb, nb, order="F") for l in range(nl)], S.view(np.complex128).reshape(nb, nb, order="F")
+
+    def radial_dipole_device(self, gauge):
+        """setup_radial_dip on the device (mat_els.f90:120-170); replaces set_radial_dipole"""
+        _chk(lib().bs2e_radial_dipole_device(self.h, ord(gauge)))
+        self._gauge = gauge
+
+    def get_radial_dipole(self):
+        nb = self.n_b
+        A = np.zeros(2 * nb * nb)
+        B = np.zeros(2 * nb * nb) if self._gauge == "v" else None
+        _chk(lib().bs2e_get_radial_dipole(self.h, _ptr(A), _ptr(B)))
+        f = lambda M: M.view(np.complex128).reshape(nb, nb, order="F")
+        return f(A), (f(B) if B is not None else None)
+
     @staticmethod
     def _conf(sym):
         return (np.ascontiguousarray(sym.conf_n, np.int64).reshape(-1),
@@ -558,13 +590,19 @@ class BasisSetup:
             self.ctx = Context(self.k, self.grid, self.p["max_k"], self.p["k_GL"], device=self.device)
         return self.ctx
 
-    def run(self):
-        """setup_Slater_integrals; compute_R_k_map; construct_block_tensor per symmetry."""
+    def run(self, device_one_particle=False):
+        """setup_Slater_integrals; compute_R_k_map; construct_block_tensor per symmetry.
+        device_one_particle: H_vec and S are computed on the device (bs2e_one_particle_device) instead of
+        being handed over by the caller."""
         S, H_vec, syms = self.host_inputs()
         ctx = self.open()
         ctx.slater_cells()
         ctx.rk_build()
-        ctx.set_one_particle(H_vec, S)
+        if device_one_particle:
+            p = self.p
+            ctx.one_particle_device(p["Z"], p["max_l_1p"], p["CAP_order"], p["CAP_r_0"], p["CAP_eta"])
+        else:
+            ctx.set_one_particle(H_vec, S)
         H_diag, S_diag = [], []
         for s in syms:
             H, Sm = ctx.construct_block_tensor(s, self.p["full"])

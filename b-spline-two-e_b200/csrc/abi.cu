@@ -296,6 +296,43 @@ int bs2e_set_one_particle(bs2e_ctx* c, int64_t max_l_1p, const double* H_vec, co
     });
 }
 
+int bs2e_one_particle_device(bs2e_ctx* c, int64_t Z, int64_t max_l_1p, int64_t CAP_order, double CAP_r_0,
+                             double CAP_eta_re, double CAP_eta_im)
+{
+    return guarded("bs2e_one_particle_device", [&] {
+        if (!c) throw Error("null context");
+        use_device(c);
+        one_particle_device(c, (int)Z, (int)max_l_1p, (int)CAP_order, CAP_r_0, CAP_eta_re, CAP_eta_im);
+    });
+}
+
+int bs2e_get_one_particle(bs2e_ctx* c, double* H_vec, double* S)
+{
+    return guarded("bs2e_get_one_particle", [&] {
+        if (!c) throw Error("null context");
+        use_device(c);
+        fetch_one_particle(c, H_vec, S);
+    });
+}
+
+int bs2e_radial_dipole_device(bs2e_ctx* c, int64_t gauge)
+{
+    return guarded("bs2e_radial_dipole_device", [&] {
+        if (!c) throw Error("null context");
+        use_device(c);
+        radial_dipole_device(c, (int)gauge);
+    });
+}
+
+int bs2e_get_radial_dipole(bs2e_ctx* c, double* A, double* B)
+{
+    return guarded("bs2e_get_radial_dipole", [&] {
+        if (!c) throw Error("null context");
+        use_device(c);
+        fetch_radial_dipole(c, A, B);
+    });
+}
+
 int bs2e_set_radial_dipole(bs2e_ctx* c, int64_t gauge, const double* A, const double* B)
 {
     return guarded("bs2e_set_radial_dipole", [&] {

@@ -247,6 +247,11 @@ void arena_give(bs2e_ctx* c, DevArena& a, cudaStream_t last_use);  // back to th
 void build_row_tables(cudaStream_t st, long long n_config, const long long* d_conf_n, int nblk,
                       const int* d_blk_start, unsigned short* row_n1, unsigned short* row_n2,
                       unsigned short* row_blk);
+// onebody.cu
+void one_particle_device(bs2e_ctx* c, int Z, int lmax, int cap_order, double cap_r0, double eta_re, double eta_im);
+void radial_dipole_device(bs2e_ctx* c, int gauge);
+void fetch_one_particle(bs2e_ctx* c, double* H_vec, double* S);
+void fetch_radial_dipole(bs2e_ctx* c, double* A, double* B);
 void download_to_host(bs2e_ctx* c, void* dst, const void* d_src, size_t bytes);   // pinned or pageable destination
 void download_flush(bs2e_ctx* c);
 void stager_destroy(bs2e_ctx* c);

@@ -83,6 +83,16 @@ int bs2e_rk_plane(bs2e_ctx *ctx, int64_t k, double *out);
 int bs2e_set_one_particle(bs2e_ctx *ctx, int64_t max_l_1p, const double *H_vec,
                           const double *S);
 
+/* The same matrices computed ON THE DEVICE: setup_S and setup_H_one_particle for
+ * l = 0..max_l_1p (src/mat_els/mat_els.f90:47-118,294-346; V = l(l+1)/(2r^2) - Z/r,
+ * src/mat_els/potentials.f90:35-43; CAP -i eta (r-r0)^order for r >= r0, src/tools/CAP_tools.f90:24-34)
+ * with the Gauss-Legendre rule of the context.  Replaces bs2e_set_one_particle; bs2e_get_one_particle
+ * copies the dense n_b x n_b column-major matrices back (H_vec concatenated over l; either may be NULL)
+ * so that the Fortran H_vec / S stay populated for the consumers that write them out.                 */
+int bs2e_one_particle_device(bs2e_ctx *ctx, int64_t Z, int64_t max_l_1p, int64_t CAP_order,
+                             double CAP_r_0, double CAP_eta_re, double CAP_eta_im);
+int bs2e_get_one_particle(bs2e_ctx *ctx, double *H_vec, double *S);
+
 /* ---- stage C: one symmetry block.
  * conf_n / conf_l are (2, n_config): term%configs(:)%n and %l
  * (src/tools/orbital_tools.f90:15-19) in the order count_configs generates
@@ -173,6 +183,10 @@ int bs2e_host_free(void *ptr);
  *   The overlap matrix is the one given to bs2e_set_one_particle.  index_ptr has
  *   n_config1+1 entries; indices / data have the nnz of the count call.              */
 int bs2e_set_radial_dipole(bs2e_ctx *ctx, int64_t gauge, const double *A, const double *B);
+/* setup_radial_dip on the device (mat_els.f90:120-170,348-390), in place of bs2e_set_radial_dipole;
+ * bs2e_get_radial_dipole copies A (and B in the velocity gauge) back as dense matrices.            */
+int bs2e_radial_dipole_device(bs2e_ctx *ctx, int64_t gauge);
+int bs2e_get_radial_dipole(bs2e_ctx *ctx, double *A, double *B);
 int bs2e_dip_block_count(bs2e_ctx *ctx, int64_t q, const int64_t *sym1, int64_t n_config1,
                          const int64_t *conf_n1, const int64_t *conf_l1, const int64_t *sym2,
                          int64_t n_config2, const int64_t *conf_n2, const int64_t *conf_l2,

@@ -15,6 +15,7 @@
 #include "../../b-spline-two-e_b200/csrc/slater_core.h"
 #include "../../b-spline-two-e_b200/csrc/site_core.h"
 #include "../../b-spline-two-e_b200/csrc/dip_plan.h"
+#include "../../b-spline-two-e_b200/csrc/onebody_core.h"
 
 using namespace bs2e;
 
@@ -812,3 +813,39 @@ int64_t hc_dip_block(HcCtx* c, int64_t q, const int64_t* sym1, int64_t n1, const
 }
 
 }  // extern "C"
+
+// ---- one-particle matrices and radial dipole integrals: emulates one_body_kernel (onebody.cu), one
+//      "thread" per band entry; output as dense complex n_b x n_b column-major matrices ----
+extern "C" int hc_one_body(HcCtx* c, int64_t Z, int64_t lmax, int64_t cap_order, double cap_r0, double eta_re,
+                           double eta_im, int64_t want_1p, int64_t gauge, double* H_vec, double* S, double* A, double* B)
+{
+    try {
+        const Geom& g = c->hg.g;
+        const size_t per = band_doubles(g);
+        std::vector<double> Sb(per, 0.0), Hb((size_t)(lmax + 1) * per, 0.0), Ab(per, 0.0), Bb(per, 0.0);
+        const OneBodyParams p{(int)Z, (int)lmax, (int)cap_order, cap_r0, eta_re, eta_im, (int)want_1p, (int)gauge};
+        const OneBodyOut o{Sb.data(), Hb.data(), Ab.data(), Bb.data()};
+        const int bw = 2 * g.w + 1;
+        for (int idx = 0; idx < g.nb * bw; ++idx) one_body_entry(g, p, o, idx / bw + 1, idx % bw);
+        auto dense = [&](const double* band, double* out) {
+            if (!out) return;
+            for (size_t q = 0; q < (size_t)g.nb * g.nb * 2; ++q) out[q] = 0.0;
+            for (int n = 1; n <= g.nb; ++n)
+                for (int d = 0; d < bw; ++d) {
+                    const int np = n + d - g.w;
+                    if (np < 1 || np > g.nb) continue;
+                    const size_t at = 2 * ((size_t)(n - 1) + (size_t)g.nb * (np - 1));
+                    out[at] = band[((size_t)n * bw + d) * 2];
+                    out[at + 1] = band[((size_t)n * bw + d) * 2 + 1];
+                }
+        };
+        dense(Sb.data(), S);
+        if (H_vec) for (int l = 0; l <= lmax; ++l) dense(Hb.data() + l * per, H_vec + (size_t)l * g.nb * g.nb * 2);
+        dense(Ab.data(), A);
+        dense(Bb.data(), B);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}

@@ -38,6 +38,7 @@ def lib():
         L.hc_block_fill.argtypes = [C.c_void_p, i64, i64, _pi, _pi, i64, i64, _pi, _pi, _pi, _pi,
                                     _pi, _pd, _pi, _pd]
         L.hc_site_fill.argtypes = L.hc_block_fill.argtypes + [i64, i64, i64, i64]
+        L.hc_one_body.argtypes = [C.c_void_p, i64, i64, i64, C.c_double, C.c_double, C.c_double, i64, i64] + [C.c_void_p] * 4
         L.hc_set_radial_dipole.argtypes = [C.c_void_p, i64, _pd, C.c_void_p]
         L.hc_dip_block.restype = i64
         L.hc_dip_block.argtypes = [C.c_void_p, i64, _pi, i64, _pi, _pi, _pi, i64, _pi, _pi, i64,
@@ -119,6 +120,20 @@ class HostCheck:
         if rc:
             raise RuntimeError(lib().hc_last_error().decode())
         return (Hp, Hi[:nH], Hd.view(np.complex128)[:nH]), (Sp, Si[:nS], Sd.view(np.complex128)[:nS])
+
+    # ---- one-particle matrices / radial dipole integrals (onebody_core.h) ----
+    def one_body(self, Z, lmax, CAP_order, CAP_r_0, CAP_eta, gauge=None):
+        nb = self.nb
+        H = np.zeros(2 * nb * nb * (lmax + 1)); S = np.zeros(2 * nb * nb)
+        A = np.zeros(2 * nb * nb); B = np.zeros(2 * nb * nb)
+        eta = complex(CAP_eta)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if lib().hc_one_body(self.h, Z, lmax, CAP_order, CAP_r_0, eta.real, eta.imag, 1, ord(gauge) if gauge else 0,
+                             p(H), p(S), p(A), p(B)):
+            raise RuntimeError(lib().hc_last_error().decode())
+        f = lambda M: M.view(np.complex128).reshape(nb, nb, order="F")
+        Hc = H.view(np.complex128).reshape(lmax + 1, nb * nb)
+        return [Hc[l].reshape(nb, nb, order="F") for l in range(lmax + 1)], f(S), f(A), f(B)
 
     # ---- dipole blocks ----
     def set_radial_dipole(self, gauge, A, B=None):

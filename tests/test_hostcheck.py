@@ -138,3 +138,32 @@ def test_plan_rejects_foreign_orderings(case):
     if np.any(cl2[:, 0] < cl2[:, 1]):
         with pytest.raises(RuntimeError):
             hc.block(s.l, s.conf_n, cl2, False)
+
+
+def _mat_close(got, ref, what, tol=1e-12):
+    """one-particle matrices: sums of terms of mixed sign (kinetic against potential), compared against the
+    largest entry of the row"""
+    scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), np.abs(ref))
+    err = np.abs(got - ref) / np.maximum(scale, np.finfo(float).tiny)
+    assert err.max() <= tol, f"{what}: {err.max():.2e}"
+    assert np.array_equal(got != 0, ref != 0) or np.abs(got[(got != 0) != (ref != 0)]).max() < 1e-300, f"{what}: band pattern"
+
+
+@pytest.mark.parametrize("name", ["trunc_k5", "wide_k6", "order10"])
+def test_one_particle_matrices_and_radial_dipole(name):
+    """setup_S / setup_H_one_particle / setup_radial_dip element by element
+    (csrc/onebody_core.h) against the oracle's restatement of mat_els.f90:47-170"""
+    p = O.basis_params(**SMALL_CASES[name])
+    run = O.OracleRun(**p)
+    S, H_vec = run.one_particle()
+    glx, glw = O.gauss_legendre(p["k_GL"])
+    hc = HostCheck(p["k"], run.grid, p["max_k"], glx, glw)
+    for gauge in ("l", "v"):
+        Hg, Sg, A, B = hc.one_body(p["Z"], p["max_l_1p"], p["CAP_order"], p["CAP_r_0"], p["CAP_eta"], gauge)
+        _mat_close(Sg, S, "S")
+        for l in range(p["max_l_1p"] + 1):
+            _mat_close(Hg[l], H_vec[l], f"H_{l}")
+        rd = O.setup_radial_dip(run.bs, p["k_GL"], gauge)
+        _mat_close(A, rd.A, f"A[{gauge}]")
+        if gauge == "v":
+            _mat_close(B, rd.B, "r_inv_mat")
