@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -44,6 +45,7 @@ ABI = {
     "bs2e_get_r_k": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "bs2e_get_r_d_k": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "bs2e_rk_build": (C.c_int, [vp]),
+    "bs2e_rk_rows": (C.c_int, [vp, C.c_int64, C.c_int64]),
     "bs2e_rk_get": (C.c_int, [vp, i64, _pi, _pd]),
     "bs2e_rk_plane": (C.c_int, [vp, i64, _pd]),
     "bs2e_set_one_particle": (C.c_int, [vp, i64, _pd, _pd]),
@@ -264,6 +266,7 @@ class Block:
         a, b = i64(), i64()
         _chk(lib().bs2e_block_nnz(self.h, C.byref(a), C.byref(b)))
         self.nnz_H, self.nnz_S = int(a.value), int(b.value)
+        ctx._children.add(self)   # freed with the context at the latest (a handle must not outlive its context)
 
     @property
     def nrows(self):
@@ -311,8 +314,10 @@ class Block:
 class DeviceConfigs:
     """handle of a configuration list resident on the device"""
 
-    def __init__(self, handle, sym):
+    def __init__(self, handle, sym, ctx=None):
         self.h, self.sym = handle, sym
+        if ctx is not None:
+            ctx._children.add(self)
 
     def free(self):
         if self.h:
@@ -341,6 +346,7 @@ class Context:
             gl_x, gl_w = gauss_legendre(k_GL)
         self.k, self.max_k, self.k_GL = int(k_spline), int(max_k), int(k_GL)
         self.knots = knots
+        self._children = weakref.WeakSet()   # live Block / DeviceConfigs handles of this context
         h = vp()
         _chk(lib().bs2e_ctx_create(self.k, len(knots), knots, self.max_k, self.k_GL,
                                    np.ascontiguousarray(gl_x, np.float64),
@@ -352,6 +358,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for child in list(self._children):
+                child.free()
             lib().bs2e_ctx_destroy(self.h)
             self.h = None
 
@@ -389,6 +397,12 @@ class Context:
     # ---- stage B: compute_R_K_map (sparse_array_tools.f90:452) ----
     def rk_build(self):
         _chk(lib().bs2e_rk_build(self.h))
+
+    def rk_rows(self, a_lo, a_hi):
+        """Multi-GPU: the next slater_cells / rk_build produce only the rows of the R^k tensor whose first spline
+        index lies in [a_lo, a_hi] (what the radial sites of this GPU's share of the rows read, see
+        bs2e.sharding.rk_rows_needed); assembling rows that need others is an error."""
+        _chk(lib().bs2e_rk_rows(self.h, int(a_lo), int(a_hi)))
 
     def rk_get(self, keys):
         keys = np.ascontiguousarray(keys, np.int64).reshape(-1, 4)
@@ -497,7 +511,7 @@ class Context:
         cn, cl = self._conf(sym)
         h = vp()
         _chk(lib().bs2e_configs_upload(self.h, sym.n_config, cn, cl, C.byref(h)))
-        return DeviceConfigs(h, sym)
+        return DeviceConfigs(h, sym, self)
 
     def block_plan(self, sym, full, rows=None, ranges=None, cfg=None) -> Block:
         """rows=(lo,hi): one row range; ranges=[(lo,hi),...]: a union of ascending row ranges

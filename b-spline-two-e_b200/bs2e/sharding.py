@@ -78,6 +78,13 @@ def site_partition(conf_n, weights, parts, k_spline=None, x_cost=1.0):
     times more, see exchange_cost().  Returns a list of `parts` lists of (lo, hi),
     1-based inclusive; a part may be empty when there are fewer distinct n1 than parts.
     """
+    present, unit_w = site_units(conf_n, weights, k_spline, x_cost)
+    return ranges_of_bounds(conf_n, unit_bounds(present, unit_w, parts))
+
+
+def site_units(conf_n, weights, k_spline=None, x_cost=1.0):
+    """The units of the partition: the distinct first radial indices n1 of a block (ascending)
+    and the total weight of the rows of each (exchange-window rows weighted by x_cost)."""
     n1 = np.asarray(conf_n)[:, 0].astype(np.int64)
     w = np.asarray(weights, np.float64)
     if k_spline is not None and x_cost != 1.0:
@@ -86,11 +93,21 @@ def site_partition(conf_n, weights, parts, k_spline=None, x_cost=1.0):
     nmax = int(n1.max())
     per_n1 = np.bincount(n1, weights=w, minlength=nmax + 1)[1:]          # index n1-1
     present = np.flatnonzero(np.bincount(n1, minlength=nmax + 1)[1:] > 0) + 1
+    return present, per_n1[present - 1]
+
+
+def unit_bounds(present, unit_w, parts):
+    """Cut the ascending n1 values `present` into `parts` intervals (a, b) of nearly equal weight;
+    (1, 0) = empty part when there are fewer units than parts."""
     if len(present) >= parts:
-        cuts = balanced_ranges(per_n1[present - 1], parts)               # over the present n1 values
-        bounds = [(int(present[lo - 1]), int(present[hi - 1])) for lo, hi in cuts]
-    else:
-        bounds = [(int(v), int(v)) for v in present] + [(1, 0)] * (parts - len(present))
+        cuts = balanced_ranges(unit_w, parts)
+        return [(int(present[lo - 1]), int(present[hi - 1])) for lo, hi in cuts]
+    return [(int(v), int(v)) for v in present] + [(1, 0)] * (parts - len(present))
+
+
+def ranges_of_bounds(conf_n, bounds):
+    """Row ranges (1-based inclusive, ascending) of the rows whose n1 lies in each interval of `bounds`."""
+    n1 = np.asarray(conf_n)[:, 0].astype(np.int64)
     out = []
     for a, b in bounds:
         mine = (n1 >= a) & (n1 <= b)
@@ -98,6 +115,41 @@ def site_partition(conf_n, weights, parts, k_spline=None, x_cost=1.0):
         starts, ends = np.flatnonzero(edge == 1) + 1, np.flatnonzero(edge == -1)
         out.append([(int(s), int(e)) for s, e in zip(starts, ends)])
     return out
+
+
+def rk_rows_needed(conf_n, bounds_of_rank, k_spline):
+    """First spline indices [a_lo, a_hi] of the R^k rows a rank reads when it assembles the rows whose n1 lies in
+    bounds_of_rank = (lo, hi): the direct window reads rows (n1, .); radial sites that have exchange windows
+    (n1 - (k_spline-1) <= largest n2) also read rows (n2, .) (site_core.h: site_own_cand)."""
+    conf_n = np.asarray(conf_n)
+    lo, hi = bounds_of_rank
+    n1, n2 = conf_n[:, 0], conf_n[:, 1]
+    mine = (n1 >= lo) & (n1 <= hi)
+    if not mine.any():
+        return None
+    a_lo, a_hi = int(n1[mine].min()), int(n1[mine].max())
+    has_x = mine & (n1 - (int(k_spline) - 1) <= int(n2.max()))
+    if has_x.any():
+        a_lo, a_hi = min(a_lo, int(n2[has_x].min())), max(a_hi, int(n2[has_x].max()))
+    return a_lo, a_hi
+
+
+def refine_bounds(present, unit_w, bounds, times):
+    """One step of measured rebalancing.  `times[r]` is the device time part r took for the rows of
+    `bounds[r]`; the cost of a unit is taken as its weight scaled by time/weight of the part it was
+    in, and the n1 axis is cut again into intervals of equal cost.  Deterministic in its inputs, so
+    that every rank that holds the gathered times computes the same partition.  The model weights
+    (stored entries, exchange_cost) only have to be right up to a smooth factor along n1: two or three
+    steps remove what they miss (per-site fixed work, last-wave tails, the mix of the two site kernels)."""
+    present = np.asarray(present)
+    unit_w = np.asarray(unit_w, np.float64)
+    cost = unit_w.copy()
+    for (a, b), t in zip(bounds, times):
+        sel = (present >= a) & (present <= b)
+        tot = unit_w[sel].sum()
+        if tot > 0 and t > 0:
+            cost[sel] = unit_w[sel] * (float(t) / tot)
+    return unit_bounds(present, cost, len(bounds))
 
 
 def merge_fragments(n_config, parts):

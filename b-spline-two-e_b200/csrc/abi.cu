@@ -109,6 +109,8 @@ int bs2e_ctx_create(int64_t k_spline, int64_t n_knots, const double* knots, int6
             throw Error(e.what());
         }
         c->hg = c->host.g;
+        c->slice_lo = 1;
+        c->slice_hi = c->hg.nb;
         c->max_k = c->host.max_k;
         c->nnz_4d = c->host.nnz_4d;
         c->nnz_6d = c->host.nnz_6d;
@@ -157,7 +159,7 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         cudaFree(c->d_t); cudaFree(c->d_bp); cudaFree(c->d_glx); cudaFree(c->d_glw);
         cudaFree(c->d_rowoff); cudaFree(c->d_pair);
         cudaFree(c->d_mom_rk); cudaFree(c->d_mom_rmk); cudaFree(c->d_pre); cudaFree(c->d_sufx);
-        cudaFree(c->d_rd); cudaFree(c->d_R); cudaFree(c->d_Hb); cudaFree(c->d_Sb);
+        cudaFree(c->d_rd); cudaFree(c->d_rkrow); cudaFree(c->d_R); cudaFree(c->d_Hb); cudaFree(c->d_Sb);
         cudaFree(c->d_dipA); cudaFree(c->d_dipB);
         if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
         if (c->have_lanes) {
@@ -247,6 +249,16 @@ int bs2e_rk_build(bs2e_ctx* c)
         if (!c) throw Error("null context");
         use_device(c);
         run_rk_build(c);
+    });
+}
+
+int bs2e_rk_rows(bs2e_ctx* c, int64_t a_lo, int64_t a_hi)
+{
+    return guarded("bs2e_rk_rows", [&] {
+        if (!c) throw Error("null context");
+        if (a_lo < 1 || a_hi > c->hg.nb || a_lo > a_hi) throw Error("bs2e_rk_rows: need 1 <= a_lo <= a_hi <= n_b");
+        c->slice_lo = (int)a_lo;
+        c->slice_hi = (int)a_hi;
     });
 }
 

@@ -892,6 +892,8 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
     const BlockStreams bs = bsp ? *bsp : default_streams(c);
     if (b->n_config == 0 || b->nrows == 0) { b->assembled = true; return; }
     if (!c->have_R) throw Error("block_assemble: call bs2e_rk_build first");
+    if (b->a_need_lo < c->R_lo || b->a_need_hi > c->R_hi)
+        throw Error("block_assemble: the planned rows read R^k rows outside the slice that was built (bs2e_rk_rows)");
     if (!c->have_1p) throw Error("block_assemble: call bs2e_set_one_particle first");
     if (b->lmax > c->lmax_1p) throw Error("block_assemble: configuration l exceeds max_l_1p of H_vec");
     if (!b->d_Hidx) {

@@ -134,6 +134,9 @@ BS2E_HD double rk_diag(const Geom& g, const CellData& cd, int k, PairAC q1, Pair
 {
     const int ks = g.ks, ks2 = ks * ks;
     double d1 = 0.0, d2 = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4   // the loads of four cells in flight together (their addresses do not depend on the sums)
+#endif
     for (int v = vlo; v <= vhi; ++v) {
         const int l1 = (q1.a + 1 - v) * ks + (q1.c + 1 - v);
         const int l2 = (q2.a + 1 - v) * ks + (q2.c + 1 - v);
@@ -155,20 +158,31 @@ BS2E_HD double rk_element(const Geom& g, const CellData& cd, int k, int p1, int 
     return val;
 }
 
-// The stage-B kernel works on tiles of kRkRows p1 rows x 2*kRkThreads p2 columns of
-// the plane of multipole k.  Disjoint cell ranges collapse to one product of total
-// moments (97 % of the tensor: a streaming write, phase 1); the elements whose cell
-// ranges overlap are collected per tile and computed by all threads of the tile
-// together in phase 2, so that no warp runs the general formula with a few lanes.
-constexpr int kRkRows = 16;      // p1 rows per CTA
-constexpr int kRkThreads = 128;  // each thread owns two adjacent p2 columns
+// The stage-B kernel (rk.cu) writes the plane of multipole k in two roles that share one launch:
+//   streaming tiles  kRkRowsS p1 rows x 2*kRkThreads p2 columns: the entries whose pairs live on disjoint cell
+//                    ranges (97 % of the tensor) are one product of total moments -- a pure streaming write from
+//                    the packed per-pair records RkRow (two 16-byte loads per column, none per entry);
+//   band tiles       kRkRowsB p1 rows x kRkThreads p2 columns along the band |a - b| <= w, outside of which no two
+//                    cell ranges meet: one thread per column walks the rows of the tile and computes the entries
+//                    with overlapping ranges by the general formula (rk_element), its column's moments staying in L1.
+// The two roles write disjoint sets of entries, so they need no ordering.
+constexpr int kRkThreads = 256;
+constexpr int kRkRowsS = 32;   // p1 rows per streaming tile
+constexpr int kRkRowsB = 16;   // p1 rows per band tile
 
-struct RkRow { int lo, hi; double trk, trmk; };  // cell range and total moments of a pair
+// cell range and total moments of a band pair for one multipole (written by stage A: pair_prefix_item)
+struct alignas(16) RkRow { int lo, hi; double trk, trmk; double pad; };
+
+BS2E_HD RkRow rk_row_empty()
+{
+    RkRow r;
+    r.lo = 1; r.hi = 0; r.trk = 0.0; r.trmk = 0.0; r.pad = 0.0;
+    return r;
+}
 
 BS2E_HD RkRow rk_row_data(const Geom& g, const CellData& cd, int k, int p)
 {
-    RkRow r;
-    r.lo = 1; r.hi = 0; r.trk = 0.0; r.trmk = 0.0;
+    RkRow r = rk_row_empty();
     if (p < g.P) {
         const PairAC q = g.pair[p];
         r.lo = pair_lo_cell(g, q.a, q.c);
@@ -179,36 +193,31 @@ BS2E_HD RkRow rk_row_data(const Geom& g, const CellData& cd, int k, int p)
     return r;
 }
 
-// phase 1 of a tile, thread tx: rows[] holds rk_row_data of the tile's p1 rows.
-// general(code) is called for every element that needs the general formula,
-// code = row | local column << 4.
-template <class G>
-BS2E_HD void rk_stream_thread(const Geom& g, const CellData& cd, double* R, const RkRow* rows, int bx, int by,
-                              int k, int tx, G&& general)
+// the cell ranges of the two pairs meet: the entry needs the general formula
+BS2E_HD bool rk_ranges_meet(const RkRow& a, const RkRow& c) { return !(a.hi < c.lo) && !(c.hi < a.lo); }
+// disjoint ranges: electron 1 strictly inside electron 2's radius, or the other way round
+BS2E_HD double rk_disjoint_value(const RkRow& a, const RkRow& c) { return a.hi < c.lo ? a.trk * c.trmk : a.trmk * c.trk; }
+
+// columns [c0, c1) of the band of the p1 rows [r0, r1): every pair (b, .) with |a - b| <= w for an a of the rows
+BS2E_HD void rk_band_columns(const Geom& g, int r0, int r1, int* c0, int* c1)
 {
-    const int p2 = (bx * kRkThreads + tx) * 2;
-    if (p2 >= g.ldP) return;
-    const RkRow c0 = rk_row_data(g, cd, k, p2), c1 = rk_row_data(g, cd, k, p2 + 1);
+    const int a_min = g.pair[r0].a, a_max = g.pair[r1 - 1].a;
+    *c0 = g.rowoff[imax(1, a_min - g.w)];
+    *c1 = g.rowoff[imin(g.nb, a_max + g.w) + 1];
+}
+
+// streaming role, one thread: columns p2, p2+1 (p2 even) of the rows [r0, r0 + nrows); rows[] holds their records,
+// c0 / c1 those of the two columns (rk_row_empty() past the last pair: the padding columns are written as zeros).
+BS2E_HD void rk_stream_columns(const Geom& g, double* R, const RkRow* rows, int r0, int nrows, int k, int p2,
+                               const RkRow& c0, const RkRow& c1)
+{
     const bool ok0 = p2 < g.P, ok1 = p2 + 1 < g.P;
-    const int r0 = by * kRkRows;
     double* dst = R + ((size_t)k * g.P + r0) * g.ldP + p2;
-    for (int row = 0; row < kRkRows; ++row, dst += g.ldP) {
-        if (r0 + row >= g.P) break;
+    for (int row = 0; row < nrows; ++row, dst += g.ldP) {
         const RkRow a = rows[row];
-        double o0 = 0.0, o1 = 0.0;
-        bool g0 = false, g1 = false;
-        if (ok0) {
-            if (a.hi < c0.lo) o0 = a.trk * c0.trmk;        // electron 1 strictly inside
-            else if (c0.hi < a.lo) o0 = a.trmk * c0.trk;   // electron 2 strictly inside
-            else g0 = true;
-        }
-        if (ok1) {
-            if (a.hi < c1.lo) o1 = a.trk * c1.trmk;
-            else if (c1.hi < a.lo) o1 = a.trmk * c1.trk;
-            else g1 = true;
-        }
-        if (g0) general(row | ((tx * 2) << 4));
-        if (g1) general(row | ((tx * 2 + 1) << 4));
+        const bool g0 = ok0 && rk_ranges_meet(a, c0), g1 = ok1 && rk_ranges_meet(a, c1);
+        const double o0 = (ok0 && !g0) ? rk_disjoint_value(a, c0) : 0.0;
+        const double o1 = (ok1 && !g1) ? rk_disjoint_value(a, c1) : 0.0;
 #if defined(__CUDA_ARCH__)
         if (!g0 && !g1) *reinterpret_cast<double2*>(dst) = make_double2(o0, o1);
         else {
@@ -222,12 +231,46 @@ BS2E_HD void rk_stream_thread(const Geom& g, const CellData& cd, double* R, cons
     }
 }
 
-// phase 2 of a tile: one collected element
-BS2E_HD void rk_general_item(const Geom& g, const CellData& cd, double* R, int bx, int by, int k, int code)
+// rk_element with the per-pair vectors handed in by the caller (the band role of the stage-B kernel keeps them in
+// shared memory): pre1 / suf1 [ks+1] of pair p1, rk2 / rmk2 [ks] of pair p2, a / c the pairs' records.  Same
+// statements in the same order as rk_offdiag + rk_diag.
+BS2E_HD double rk_element_staged(const Geom& g, const CellData& cd, int k, PairAC q1, PairAC q2, const RkRow& a,
+                                 const RkRow& c, const double* pre1, const double* suf1, const double* rk2,
+                                 const double* rmk2)
 {
-    const int p1 = by * kRkRows + (code & 15);
-    const int p2 = bx * kRkThreads * 2 + (code >> 4);
-    R[((size_t)k * g.P + p1) * g.ldP + p2] = rk_element(g, cd, k, p1, p2);
+    const int ks = g.ks;
+    double val = 0.0;
+    for (int s = 0; s <= c.hi - c.lo; ++s) {
+        const int tt = c.lo + s - a.lo;
+        val += rmk2[s] * pre1[iclamp(tt, 0, ks)];
+        val += rk2[s] * suf1[iclamp(tt + 1, 0, ks)];
+    }
+    const int vlo = imax(a.lo, c.lo), vhi = imin(a.hi, c.hi);
+    if (vlo <= vhi) val += rk_diag(g, cd, k, q1, q2, vlo, vhi);
+    return val;
+}
+
+// band role with staged vectors, one thread: column p2 of the rows [r0, r0 + nrows); pre1s / suf1s hold the rows'
+// vectors ([row][ks+1]), rk2 / rmk2 the column's
+BS2E_HD void rk_band_column_staged(const Geom& g, const CellData& cd, double* R, const RkRow* rows, int r0, int nrows,
+                                   int k, int p2, const RkRow& c, const double* pre1s, const double* suf1s,
+                                   const double* rk2, const double* rmk2)
+{
+    const PairAC q2 = g.pair[p2];
+    for (int row = 0; row < nrows; ++row)
+        if (rk_ranges_meet(rows[row], c))
+            R[((size_t)k * g.P + r0 + row) * g.ldP + p2] =
+                rk_element_staged(g, cd, k, g.pair[r0 + row], q2, rows[row], c, pre1s + (size_t)row * (g.ks + 1),
+                                  suf1s + (size_t)row * (g.ks + 1), rk2, rmk2);
+}
+
+// band role, one thread: column p2 of the rows [r0, r0 + nrows)
+BS2E_HD void rk_band_column(const Geom& g, const CellData& cd, double* R, const RkRow* rows, int r0, int nrows, int k,
+                            int p2, const RkRow& c)
+{
+    for (int row = 0; row < nrows; ++row)
+        if (rk_ranges_meet(rows[row], c))
+            R[((size_t)k * g.P + r0 + row) * g.ldP + p2] = rk_element(g, cd, k, r0 + row, p2);
 }
 
 // ---------------------------------------------------------------------------

@@ -67,9 +67,10 @@ T* dev_upload(const std::vector<T>& v, cudaStream_t st)
 }
 
 // Plan tables of a block: one buffer carved into aligned pieces.  The buffers come from a small per-context
-// pool (arena_take / arena_give, plan_dev.cu) instead of the stream-ordered allocator: a plan is built on the
-// context's PLAN stream while the fill of the previous block still runs on the main stream, and a buffer
-// released behind that fill (event on the main stream) must not tie the two streams together.
+// pool (arena_take / arena_give, plan_dev.cu) that is recycled by hand rather than freed stream-ordered: a plan is
+// built on the context's PLAN stream while the fill of the previous block still runs on the main stream, and a
+// buffer released behind that fill (event on the main stream) must not tie the two streams together.  The pool's
+// buffers themselves are allocated (once, power-of-two size classes) from the device's stream-ordered memory pool.
 struct ArenaBuf {
     char* base = nullptr;
     size_t size = 0;
@@ -150,6 +151,7 @@ struct bs2e_ctx {
     cudaStream_t plan_stream = nullptr;   // plans are built here, concurrently with fills on `stream`
     std::mutex arena_mu;
     std::vector<bs2e::ArenaBuf*> arenas;  // pool of plan buffers (arena_take / arena_give)
+    cudaMemPool_t arena_pool = nullptr;   // the memory pool they are allocated from
     int* h_pin = nullptr;        // pinned staging for the small read-backs of a plan
     size_t h_pin_bytes = 0;
     // copy stream + pinned bounce buffers for downloads into pageable memory (download.cu)
@@ -173,11 +175,16 @@ struct bs2e_ctx {
     double *d_mom_rk = nullptr, *d_mom_rmk = nullptr;  // [K1][P][ks]
     double *d_pre = nullptr, *d_sufx = nullptr;        // [K1][P][ks+1]
     double* d_rd = nullptr;                            // [C][K1][ks^2][ks^2]
+    bs2e::RkRow* d_rkrow = nullptr;                    // [K1][P] packed pair records of stage B
     bool have_cells = false;
 
     // stage B product
     double* d_R = nullptr;  // [K1][P][ldP]
     bool have_R = false;
+    // row slice of stages A and B (bs2e_rk_rows): first spline index a of the band pairs (a, c) that are built;
+    // slice_* = what the next run builds, cells_* / R_* = what the last run of stage A / B built
+    int slice_lo = 1, slice_hi = 0;   // set to 1..n_b when the context is created
+    int cells_lo = 1, cells_hi = 0, R_lo = 1, R_hi = 0;
 
     // stage C inputs (band storage)
     int lmax_1p = -1;
@@ -211,6 +218,7 @@ struct bs2e_block {
     int* d_counters = nullptr;
     int site_cap = 0;
     int nsites = 0, nsites_x = 0;
+    int a_need_lo = 1, a_need_hi = 0;   // first spline indices of the R^k rows the planned sites read
     bool use_site = false;               // site kernels (else: row-wise fallback with per-row tables)
     bool use_mma = false;                // tensor-core site kernel (site_mma.cu); else the FMA site kernel of block.cu
     // CSR fragment (device)
@@ -241,7 +249,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
 bs2e_configs* configs_upload(bs2e_ctx* c, long long n_config, const int64_t* conf_n, const int64_t* conf_l);
 void configs_free(bs2e_configs* cfg);
 void ctx_release_plan_state(bs2e_ctx* c);
-void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes);          // a free pool buffer of at least `bytes`
+void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes, cudaStream_t first_use);   // a free pool buffer of at least `bytes`
 void arena_give(bs2e_ctx* c, DevArena& a, cudaStream_t last_use);  // back to the pool, reusable after the work queued on last_use
 // per-row tables (row_n1 / row_n2 / row_blk) of a configuration list, built on the device
 void build_row_tables(cudaStream_t st, long long n_config, const long long* d_conf_n, int nblk,

@@ -31,24 +31,80 @@ struct DipArena {   // device arrays of one call, released on every exit path
 };
 }  // namespace
 
+// One warp per row.  Per flagged column group the lanes first take one n_c slot each (clipped n_d intervals of
+// both windows, their union, its size), a warp scan turns the sizes into offsets, and then the lanes take
+// consecutive stored ENTRIES of the (row, column group) pair: every store instruction writes 32 consecutive
+// entries of the CSR row, whatever the width of the windows (<= 2w+1 columns per n_c; the first version walked
+// the n_c slots one after the other with one lane per n_d: 15 of 32 lanes at best and the whole interval
+// arithmetic repeated by every lane for every slot -- 42 warp instructions per stored entry, 0.08 of the HBM
+// rate, profiles/r01t_*).
 __global__ void __launch_bounds__(kDipWarps * 32)
-dip_fill_kernel(Geom g, Plan plC, DipTables dt, DipBand bd, const long long* __restrict__ ptr,
-                long long* __restrict__ idx, double2* __restrict__ dat)
+dip_fill_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan plC, const __grid_constant__ DipTables dt,
+                const __grid_constant__ DipBand bd, const long long* __restrict__ ptr, long long* __restrict__ idx,
+                double2* __restrict__ dat)
 {
     const long long wrow = (long long)blockIdx.x * kDipWarps + (threadIdx.x >> 5);
     if (wrow >= dt.nrows) return;
     const int lane = threadIdx.x & 31;
-    const RowInfo r = dip_row(dt, (int)wrow + 1);
+    constexpr unsigned kAll = 0xffffffffu;
+    RowInfo r = dip_row(dt, (int)wrow + 1);
+    const int bi = r.bi;
+    r.bi = -1;   // never the "own" group of the column list: no triangle cut (dip_for_each_chunk)
     long long pos = ptr[wrow] - 1;
-    dip_for_each_chunk(g, plC, dt, r, [&](int bj, int nc, const Segment& s, int base, int hi) {
-        const int nd = base + lane;
-        if (nd <= hi) {
-            const Cplx v = dip_value(g, dt, bd, r, bj, nc, nd);
-            idx[pos + lane] = (long long)s.jbase + nd;
-            dat[pos + lane] = make_double2(v.re, v.im);
+    for (int bj = 0; bj < plC.nblk; ++bj) {
+        if (!dt.flag[(size_t)bi * dt.nblkC + bj]) continue;
+        const Union2 win = nc_windows(g, plC, r, bj);
+        const int n0 = win.n > 0 ? win.hi[0] - win.lo[0] + 1 : 0;
+        const int nslots = n0 + (win.n > 1 ? win.hi[1] - win.lo[1] + 1 : 0);
+        const double* cf = dt.coef + ((size_t)bi * dt.nblkC + bj) * 8;
+        for (int s0 = 0; s0 < nslots; s0 += 32) {
+            // lane = n_c slot
+            const int sl = s0 + lane;
+            int nc = 0, cnt = 0, lo0 = 0, c0 = 0, lo1 = 0, jbase = 0;
+            if (sl < nslots) {
+                nc = sl < n0 ? win.lo[0] + sl : win.lo[1] + (sl - n0);
+                const Segment sg = segment(g, plC, r, bj, nc);
+                const Union2 u = union2(sg.dlo, sg.dhi, sg.xlo, sg.xhi);
+                if (u.n > 0) { lo0 = u.lo[0]; c0 = u.hi[0] - u.lo[0] + 1; }
+                cnt = c0;
+                if (u.n > 1) { lo1 = u.lo[1]; cnt += u.hi[1] - u.lo[1] + 1; }
+                jbase = sg.jbase;
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kAll, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(kAll, incl, 31);
+            const int excl = incl - cnt;
+            // lane = stored entry
+            for (int p0 = 0; p0 < total; p0 += 32) {
+                const int p = p0 + lane;
+                // slot of entry p: the last slot whose offset is <= p (offsets ascend; empty slots share the offset of
+                // their successor and lose against it)
+                int at = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int e = __shfl_sync(kAll, excl, (at + step) & 31);
+                    if (at + step < 32 && e <= p) at += step;
+                }
+                const int s_nc = __shfl_sync(kAll, nc, at), s_ex = __shfl_sync(kAll, excl, at);
+                const int s_lo0 = __shfl_sync(kAll, lo0, at), s_c0 = __shfl_sync(kAll, c0, at);
+                const int s_lo1 = __shfl_sync(kAll, lo1, at), s_jb = __shfl_sync(kAll, jbase, at);
+                if (p < total) {
+                    const int off = p - s_ex;
+                    const int nd = off < s_c0 ? s_lo0 + off : s_lo1 + (off - s_c0);
+                    RowInfo rv = r;
+                    rv.bi = bi;
+                    const Cplx v = dip_value_cf(g, cf, bd, rv, s_nc, nd);
+                    __stcs(idx + pos + p, (long long)s_jb + nd);
+                    __stcs(dat + pos + p, make_double2(v.re, v.im));
+                }
+            }
+            pos += total;
         }
-        pos += imin(32, hi - base + 1);
-    });
+    }
 }
 
 // count -> scan -> (optionally) fill + download.  index_ptr may be NULL (count only).

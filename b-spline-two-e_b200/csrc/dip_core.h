@@ -83,9 +83,14 @@ BS2E_HD long long dip_row_count(const Geom& g, const Plan& plC, const DipTables&
 }
 
 // value of the entry (row r, column (bj; nc, nd))
+BS2E_HD Cplx dip_value_cf(const Geom& g, const double* cf, const DipBand& bd, const RowInfo& r, int nc, int nd);
 BS2E_HD Cplx dip_value(const Geom& g, const DipTables& dt, const DipBand& bd, const RowInfo& r, int bj, int nc, int nd)
 {
-    const double* cf = dt.coef + ((size_t)r.bi * dt.nblkC + bj) * 8;
+    return dip_value_cf(g, dt.coef + ((size_t)r.bi * dt.nblkC + bj) * 8, bd, r, nc, nd);
+}
+// cf: the eight folded coefficients (alpha_t, beta_t) of the (row group, column group) pair
+BS2E_HD Cplx dip_value_cf(const Geom& g, const double* cf, const DipBand& bd, const RowInfo& r, int nc, int nd)
+{
     Cplx acc = Cplx{0.0, 0.0};
     // t: (n, n') of the one-particle dipole, (m, m') of the overlap
     const int n_[4] = {r.na, r.nb, r.na, r.nb}, np_[4] = {nc, nd, nd, nc};

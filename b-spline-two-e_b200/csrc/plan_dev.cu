@@ -32,7 +32,9 @@ constexpr int kErrRangeN = 1, kErrOrderL = 2, kErrN2 = 4, kErrN1 = 8, kErrBounds
 constexpr int kBoundCap = kMaxBlocks + 1;
 // counters of a plan (device ints): [0] nsites, [1] nsites_x, [2] group boundaries found,
 // [3] error bits, [4] largest n(2), [5] largest l(1)
-constexpr int kCntSites = 0, kCntSitesX = 1, kCntBounds = 2, kCntErr = 3, kCntMaxNd = 4, kCntLmax = 5, kCounters = 8;
+// [6] n_b + 1 - (smallest first index a of an R^k row the sites read), [7] the largest such a
+constexpr int kCntSites = 0, kCntSitesX = 1, kCntBounds = 2, kCntErr = 3, kCntMaxNd = 4, kCntLmax = 5, kCntALo = 6, kCntAHi = 7,
+              kCounters = 8;
 
 __global__ void conf_scan_kernel(long long n, const long long* __restrict__ cn, const long long* __restrict__ cl,
                                  int nb, int* __restrict__ counters, int4* __restrict__ bounds)
@@ -127,6 +129,10 @@ __global__ void site_enum_kernel(Geom g, Plan pl, int cap, unsigned long long* _
     const int q = atomicAdd(&counters[kCntSites], 1);
     if (wantX) atomicAdd(&counters[kCntSitesX], 1);
     if (q < cap) keys[q] = site_sort_key(wantX, cnt, na, nb);
+    // rows of R^k the site reads: pairs (n_a, .) for the direct window, (n_b, .) for the exchange window (site_own_cand)
+    const int alo = wantX ? imin(na, nb) : na, ahi = wantX ? imax(na, nb) : na;
+    atomicMax(&counters[kCntALo], g.nb + 1 - alo);
+    atomicMax(&counters[kCntAHi], ahi);
 }
 
 __global__ void row_tables_kernel(long long n, const long long* __restrict__ cn, int nblk,
@@ -207,21 +213,27 @@ void configs_free(bs2e_configs* cfg)
     delete cfg;
 }
 
-void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes)
+// Plan buffers come in power-of-two size classes from a stream-ordered memory pool of their own -- NOT from cudaMalloc: with
+// the CSR arrays of earlier blocks cached in the pool (release threshold = all), a cudaMalloc beside a running fill
+// was measured at 50-120 ms (the driver trims the pool), once per new buffer, well into the timed steps
+// (gpurun_out/r03a trace: block_plan 0.5 ms -> 118 ms).  `st` is the stream the buffer is used on first.
+void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes, cudaStream_t st)
 {
     bytes += 256;
+    size_t cls = 64 * 1024;
+    while (cls < bytes) cls <<= 1;
     ArenaBuf* pick = nullptr;
     {
-        // a buffer whose last reader has finished; a new one while the pool is small (waiting for a buffer that was
-        // released behind a running fill would serialise the plan with that fill); else any free one
+        // the smallest buffer of sufficient size whose last reader has finished; a new one while the pool is small
+        // (waiting for a buffer that was released behind a running fill would serialise the plan with that fill);
+        // else any free one
         std::lock_guard<std::mutex> lk(c->arena_mu);
-        const int passes = c->arenas.size() < 16 ? 1 : 2;
+        const int passes = c->arenas.size() < 24 ? 1 : 2;
         for (int pass = 0; pass < passes && !pick; ++pass)
             for (ArenaBuf* q : c->arenas) {
-                if (q->busy || q->size < bytes) continue;
+                if (q->busy || q->size < bytes || (pick && q->size >= pick->size)) continue;
                 if (pass == 0 && cudaEventQuery(q->free_after) != cudaSuccess) { cudaGetLastError(); continue; }
                 pick = q;
-                break;
             }
         if (pick) pick->busy = true;
     }
@@ -229,8 +241,18 @@ void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes)
         BS2E_CUDA(cudaEventSynchronize(pick->free_after));
     } else {
         std::unique_ptr<ArenaBuf> q(new ArenaBuf());
-        q->size = bytes + bytes / 4;
-        BS2E_CUDA(cudaMalloc(&q->base, q->size));
+        q->size = cls;
+        if (!c->arena_pool) {   // a pool of their own: plan buffers never split the free blocks of the CSR arrays
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = c->device;
+            BS2E_CUDA(cudaMemPoolCreate(&c->arena_pool, &props));
+            unsigned long long keep = ~0ull;
+            BS2E_CUDA(cudaMemPoolSetAttribute(c->arena_pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        BS2E_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&q->base), q->size, c->arena_pool, st));
         BS2E_CUDA(cudaEventCreateWithFlags(&q->free_after, cudaEventDisableTiming));
         q->busy = true;
         pick = q.release();
@@ -262,6 +284,7 @@ void ctx_release_plan_state(bs2e_ctx* c)
         delete q;
     }
     c->arenas.clear();
+    if (c->arena_pool) { cudaMemPoolDestroy(c->arena_pool); c->arena_pool = nullptr; }
     if (c->plan_stream) { cudaStreamSynchronize(c->plan_stream); cudaStreamDestroy(c->plan_stream); c->plan_stream = nullptr; }
     if (c->h_pin) cudaFreeHost(c->h_pin);
     c->h_pin = nullptr;
@@ -283,7 +306,7 @@ std::shared_ptr<GroupStructure> build_structure(bs2e_ctx* c, long long n_config,
     const int stride = hg.nb + 1;
     // counters + boundary list first (their size does not depend on the number of groups)
     DevArena tmp;
-    arena_take(c, tmp, DevArena::need(sizeof(int4) * kBoundCap) + DevArena::need(sizeof(int) * kCounters) + 1024);
+    arena_take(c, tmp, DevArena::need(sizeof(int4) * kBoundCap) + DevArena::need(sizeof(int) * kCounters) + 1024, st);
     struct Give { bs2e_ctx* c; DevArena& a; cudaStream_t st; ~Give() { arena_give(c, a, st); } } give{c, tmp, st};
     int4* d_bounds = tmp.take<int4>(kBoundCap);
     int* d_counters = tmp.take<int>(kCounters);
@@ -408,7 +431,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
         b->gs = cfg->gs;
     } else {
         if (!conf_n || !conf_l) throw Error("block_plan: null configuration arrays");
-        arena_take(c, b->arena0, 2 * DevArena::need(sizeof(long long) * 2 * n_config) + 1024);
+        arena_take(c, b->arena0, 2 * DevArena::need(sizeof(long long) * 2 * n_config) + 1024, st);
         long long* dn = b->arena0.take<long long>(2 * (size_t)n_config);
         long long* dl = b->arena0.take<long long>(2 * (size_t)n_config);
         BS2E_CUDA(cudaMemcpyAsync(dn, conf_n, sizeof(long long) * 2 * n_config, cudaMemcpyHostToDevice, st));
@@ -428,11 +451,11 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     b->site_cap = site_cap;
     b->use_site = site_kernel_usable(c, nblk, b->lmax);
     {   // Two site kernels fill the same CSR arrays: the tensor-core kernel (site_mma.cu) and the FMA kernel
-        // (block.cu).  Measured on B200 (scripts/fill_ab.py, profiles/r02_fill_ab.txt) the tensor-core kernel is
-        // ahead for 8..13 multipoles per parity list (cfg2, cfg3: -10 % time), the FMA kernel by 3-4 % for 21 and
-        // more (cfg4, cfg5) and on the small sites of cfg1.  BS2E_FILL=mma / fma forces one of them.
+        // (block.cu).  Measured on B200 (scripts/fill_ab.py, profiles/r02v_fill_ab.md): the tensor-core kernel is
+        // ahead from 8 multipoles on (cfg3: 5.85 against 6.80 ms, cfg4: 41.3 against 42.6 ms); the FMA kernel stays
+        // the choice for max_k <= 6, where a site is small (cfg1).  BS2E_FILL=mma / fma forces one of them.
         const char* mode = getenv("BS2E_FILL");
-        const bool want = mode ? strcmp(mode, "mma") == 0 : site_kmax_for(hg.K1) == 13;
+        const bool want = mode ? strcmp(mode, "mma") == 0 : site_kmax_for(hg.K1) >= 13;
         b->use_mma = b->use_site && want && !(mode && strcmp(mode, "fma") == 0) &&
                      site_mma_usable(c, nblk, b->ang->host.maxc, b->ang->host.maxrec, b->lmax);
     }
@@ -447,7 +470,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
                        4 * DevArena::need(sizeof(long long) * ((size_t)nrows + 1)) + DevArena::need(scan_tmp) +
                        DevArena::need(sort_tmp) + 1024;
         if (!b->use_site) bytes += 3 * DevArena::need(sizeof(unsigned short) * n_config);
-        arena_take(c, b->arena1, bytes);
+        arena_take(c, b->arena1, bytes, st);
     }
     b->d_counters = b->arena1.take<int>(kCounters);
     int* d_ranges = b->arena1.take<int>(3 * (size_t)nr);
@@ -511,6 +534,13 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     b->nsites = h_cnt[kCntSites];
     b->nsites_x = h_cnt[kCntSitesX];
     if (b->nsites > site_cap) throw Error("internal: site list overflow");
+    if (b->use_site && b->nsites > 0) {
+        b->a_need_lo = hg.nb + 1 - h_cnt[kCntALo];
+        b->a_need_hi = h_cnt[kCntAHi];
+    } else {
+        b->a_need_lo = 1;
+        b->a_need_hi = hg.nb;
+    }
     b->nnzH = h_tot[0] - 1;
     b->nnzS = h_tot[1] - 1;
     return guard.release();

@@ -102,11 +102,21 @@ struct alignas(16) RowC {   // per row of the group
 
 }  // namespace
 
-#ifndef BS2E_MMA_MINB
-#define BS2E_MMA_MINB 2
+// CTAs per SM: two (128 registers).  Three CTAs of 80 registers were measured for the sites without exchange
+// windows (-DBS2E_MMA_MINB_D=3; their shared memory fits with the half staging tiles): the compiler then keeps the
+// A fragments in local memory and reloads them per tile -- 5.70 instead of 4.61 ms on the L=6 block of cfg4
+// (profiles/r02w_*), long-scoreboard stalls 1.2 -> 6.4 per issue.
+#ifndef BS2E_MMA_MINB_X
+#define BS2E_MMA_MINB_X 2
+#endif
+#ifndef BS2E_MMA_MINB_D
+#define BS2E_MMA_MINB_D 2
+#endif
+#ifndef BS2E_MMA_HALF
+#define BS2E_MMA_HALF 1
 #endif
 template <int KMAX, bool WX, bool BULK>
-__global__ void __launch_bounds__(kMmaThreads, BS2E_MMA_MINB)
+__global__ void __launch_bounds__(kMmaThreads, WX ? BS2E_MMA_MINB_X : BS2E_MMA_MINB_D)
 site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl, const __grid_constant__ OneBody ob,
                 const unsigned long long* __restrict__ site_key, const __grid_constant__ MmaSmem lay, int site_off,
                 const double* __restrict__ R, const long long* __restrict__ Hptr, const long long* __restrict__ Sptr,
@@ -121,11 +131,13 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
     constexpr int STR = mma_cf_stride(CFS);
     constexpr int CT = kSegCand / 8;                   // candidate tiles per segment
     constexpr int CTH = WX ? CT / 2 : CT;              // tiles whose products are in flight together
+    constexpr bool HALF = BS2E_MMA_HALF && !WX && !BULK;   // values staged four rows at a time (half the staging tile)
     static_assert(4 * KS <= NKP, "k steps read inside the packed factors");
     extern __shared__ __align__(16) unsigned char smraw[];
     // the carve-up is computed on the host (mma_layout); the offsets live in the constant bank, not in registers
 #define BS2E_SM(type, off) (reinterpret_cast<type*>(smraw + lay.off))
     const int nblk = pl.nblk, ncmax = lay.ncmax, G = lay.G, nsegS = lay.nseg;
+    const int mstr = lay.mstr;   // words per row of the mask table (odd: rows of different records fall into different banks)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned key = (unsigned)(site_key[blockIdx.x + site_off] & 0xffffffffull);
@@ -225,7 +237,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
             for (int task = tid; task < nblk * mask_modes(WX) + 1; task += NT) {
                 if (task == nblk * mask_modes(WX)) {   // the all-zero row of the padding records
                     const int row = mask_row_zero(nblk, G, WX);
-                    for (int seg = 0; seg < nseg; ++seg) mtab[row * nsegS + seg] = MaskWord{0u, 0u};
+                    for (int seg = 0; seg < nseg; ++seg) mtab[row * mstr + seg] = MaskWord{0u, 0u};
                     tot[row] = 0;
                     continue;
                 }
@@ -234,7 +246,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                 for (int seg = 0; seg < nseg; ++seg) {
                     const unsigned d = mD[bj * nsegS + seg], x = mX[bj * nsegS + seg];
                     const unsigned m = mode == kModeD ? d : (mode == kModeX ? x : (d | x));
-                    mtab[task * nsegS + seg] = MaskWord{m, run};
+                    mtab[task * mstr + seg] = MaskWord{m, run};
                     run += __popc(m);
                 }
                 tot[task] = (unsigned short)run;
@@ -246,7 +258,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
     // candidate lane/4 of every candidate tile ct of the warp's segment; multipoles par + 2*(4 ks + lane%4)
     // (exchange window: parity par ^ pi); where the values sit comes from the candidate table of phase 1.
     const int l4 = lane >> 2, l3 = lane & 3;
-    char* const stile = reinterpret_cast<char*>(smraw) + lay.off_stage + warp * kMmaStageBytes;   // this warp's staging tile
+    char* const stile = reinterpret_cast<char*>(smraw) + lay.off_stage + warp * (HALF ? kMmaHalfBytes : kMmaStageBytes);   // this warp's staging tile
     int qn[CT];   // n_c slot as byte offset into a jbase row (low 12 bits) and n_d of the candidate of tile ct
     int ql = 0;   // the same for candidate `lane` of the segment (row-wise role)
     double Ad[CT][KS], Ax[CT][WX ? KS : 1];
@@ -341,7 +353,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                 const int row = isS ? mask_row_diagS(nblk, G, ri, WX) : mask_row_diagH(nblk, ri, WX);
                 unsigned run = 0;
                 for (int seg = 0; seg < nseg; ++seg) {
-                    mtab[row * nsegS + seg] = MaskWord{src[seg], run};
+                    mtab[row * mstr + seg] = MaskWord{src[seg], run};
                     run += __popc(src[seg]);
                 }
                 tot[row] = (unsigned short)run;
@@ -476,7 +488,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
             for (int rt = 0; rt < count; rt += 8, cfr += 8 * STR, rl += 8) {
                 // the two records this thread stores for: 2*(lane%4) and the next
                 const MmaRec ra = rl[0], rb = rl[1];
-                const MaskWord wa = mseg[ra.tbl * nsegS], wb = mseg[rb.tbl * nsegS];
+                const MaskWord wa = mseg[ra.tbl * mstr], wb = mseg[rb.tbl * mstr];
                 // B fragments: factors of record lane/4 of the tile, multipole slot 4 ks + lane%4
                 double bd[KS], bx[WX ? KS : 1];
 #pragma unroll
@@ -500,10 +512,57 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                     //     one barrier per tile.  Measured 7 % slower than the default at cfg4: the barrier per tile and
                     //     the issue slots of the copies cost more than the store path gains;
                     //   column indices: row-wise (lane = candidate of the segment), no staging.
+                    if constexpr (HALF) {
+                        // records 0,2,4,6 of the tile (first C register of every thread), then 1,3,5,7: four staged rows
+                        double c0[CT], c1[CT];
+#pragma unroll
+                        for (int ct = 0; ct < CT; ++ct) c0[ct] = c1[ct] = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                            for (int ct = 0; ct < CT; ++ct)
+                                dmma884(c0[ct], c1[ct], Ad[ct][ks], bd[ks], c0[ct], c1[ct]);   // (tiles past the last candidate hold zeros)
+                        const MmaRec* rt8 = rl - 2 * l3;   // first record of the tile
+                        const unsigned vh = smem_u32(stile) + l3 * kMmaHalfRow;
+                        const unsigned lt = (1u << lane) - 1u;
+                        const char* jbl = reinterpret_cast<const char*>(BS2E_SM(int, off_jb)) + (ql & 0xfff);
+                        const int ndl = ql >> 12;
+                        const double2* srow = reinterpret_cast<const double2*>(stile) + lane;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const unsigned wm = half ? wb.mask : wa.mask;
+                            __syncwarp();   // the rows staged before have been read
+#pragma unroll
+                            for (int ct = 0; ct < CT; ++ct) {
+                                const int bit = ct * 8 + l4;
+                                sts_value_if((wm >> bit) & 1u, vh, __popc(wm & ((1u << bit) - 1u)), half ? c1[ct] : c0[ct]);
+                            }
+                            __syncwarp();
+                            MmaRec rr[4];
+                            MaskWord wr[4];
+                            double2 v[4];
+                            int jc[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) rr[r] = rt8[2 * r + half];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                wr[r] = mseg[rr[r].tbl * mstr];
+                                v[r] = srow[r * (kMmaHalfRow / 16)];
+                                jc[r] = *reinterpret_cast<const int*>(jbl + rr[r].bj * ncmax * 4) + ndl;
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const long long start = rr[r].hpos + wr[r].pre;
+                                st_value2_if(lane < __popc(wr[r].mask) ? 1u : 0u, reinterpret_cast<const char*>(Hdat + start), lane, v[r]);
+                                st_index_if((wr[r].mask >> lane) & 1u, reinterpret_cast<const char*>(Hidx + start), __popc(wr[r].mask & lt), jc[r]);
+                            }
+                        }
+                        continue;
+                    }
                     unsigned va, vb, offa0, offb0;
                     if constexpr (!BULK) {
-                        va = smem_u32(stile) + (2 * l3) * 512;
-                        vb = va + 512;
+                        va = smem_u32(stile) + (2 * l3) * kMmaStageRow;
+                        vb = va + kMmaStageRow;
                         offa0 = offb0 = 0;
                         __syncwarp();   // the rows of the previous tile have been read
                     } else {
@@ -511,8 +570,8 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                         va = vbuf + (2 * l3) * lay.rowb;
                         vb = va + lay.rowb;
                         const int seg0 = pass * NW;   // first segment of the pass: rows are staged from its first entry on
-                        offa0 = wa.pre - BS2E_SM(MaskWord, off_mtab)[ra.tbl * nsegS + seg0].pre;
-                        offb0 = wb.pre - BS2E_SM(MaskWord, off_mtab)[rb.tbl * nsegS + seg0].pre;
+                        offa0 = wa.pre - BS2E_SM(MaskWord, off_mtab)[ra.tbl * mstr + seg0].pre;
+                        offb0 = wb.pre - BS2E_SM(MaskWord, off_mtab)[rb.tbl * mstr + seg0].pre;
                     }
                     if (any) {
                         // products of CTH tiles together: CTH (2 CTH with exchange windows) independent chains
@@ -556,7 +615,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                         __syncthreads();
                         {   // warp r hands row r of the tile to the bulk-copy engine
                             const MmaRec rr = rt8[warp];
-                            const MaskWord* mrow = BS2E_SM(MaskWord, off_mtab) + rr.tbl * nsegS;
+                            const MaskWord* mrow = BS2E_SM(MaskWord, off_mtab) + rr.tbl * mstr;
                             const int seg0 = pass * NW;
                             const unsigned pre0 = mrow[seg0].pre;
                             const unsigned pre1 = seg0 + NW < nseg ? mrow[seg0 + NW].pre : BS2E_SM(unsigned short, off_tot)[rr.tbl];
@@ -583,8 +642,8 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                             for (int r = 0; r < 4; ++r) rr[r] = rt8[r0 + r];
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
-                                wr[r] = mseg[rr[r].tbl * nsegS];
-                                if constexpr (!BULK) v[r] = srow[(r0 + r) * 32];
+                                wr[r] = mseg[rr[r].tbl * mstr];
+                                if constexpr (!BULK) v[r] = srow[(r0 + r) * (kMmaStageRow / 16)];
                                 jc[r] = *reinterpret_cast<const int*>(jbl + rr[r].bj * ncmax * 4) + ndl;
                             }
 #pragma unroll
@@ -600,7 +659,7 @@ site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl,
                     // diagonal pairs (column group == row group): one-body terms and the S entry
                     const RowC* rcache = BS2E_SM(RowC, off_rcache);
                     const RowC rca = rcache[ra.ri], rcb = rcache[rb.ri];
-                    const MaskWord sa = mseg[(ra.tbl + G) * nsegS], sb = mseg[(rb.tbl + G) * nsegS];
+                    const MaskWord sa = mseg[(ra.tbl + G) * mstr], sb = mseg[(rb.tbl + G) * mstr];
                     const double* ob_s = BS2E_SM(double, off_ob);
                     const SiteOneBody so{ob_s, ob_s + (size_t)lay.nl * 2 * (2 * g.w + 1) * 2};
                     const int na = (int)(key >> 16), nb = (int)(key & 0xffffu);
@@ -673,6 +732,7 @@ MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, i
     const int cfsn = (wx ? 2 : 1) * nkp, str = mma_cf_stride(cfsn);
     lay.ncmax = wx ? site_max_nc(g) : 2 * g.w + 1;
     lay.nseg = ((wx ? site_max_slots(g) : (2 * g.w + 1) * (2 * g.w + 1)) + kSegCand - 1) / kSegCand;
+    lay.mstr = lay.nseg | 1;
     lay.nl = std::max(c->lmax_1p, lmax) + 1;
     size_t cap_kb = 8;
     if (const char* e = getenv("BS2E_SITE_CHUNK_KB")) cap_kb = (size_t)std::max(1, atoi(e));
@@ -695,7 +755,7 @@ MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, i
     put(lay.off_recs, sizeof(MmaRec) * 2 * (size_t)lay.cap);
     put(lay.off_rcache, sizeof(RowC) * (size_t)G);
     put(lay.off_sblk, sizeof(BlockDesc) * (size_t)nblk);
-    put(lay.off_mtab, sizeof(MaskWord) * (size_t)mask_rows(nblk, G, wx) * lay.nseg);
+    put(lay.off_mtab, sizeof(MaskWord) * (size_t)mask_rows(nblk, G, wx) * lay.mstr);
     put(lay.off_mraw, sizeof(unsigned) * (size_t)(2 * nblk + 2 * G) * lay.nseg);
     put(lay.off_jb, sizeof(int) * (size_t)nblk * lay.ncmax);
     put(lay.off_ncq, sizeof(int) * (size_t)lay.ncmax);
@@ -708,7 +768,7 @@ MmaSmem mma_layout(const bs2e_ctx* c, int nblk, int maxc, int maxrec, bool wx, i
     b = (b + 127) & ~(size_t)127;
     // staging of the values: with exchange windows one tile per warp; without, two CTA-level buffers of 8 whole rows
     lay.rowb = (int)((std::min<size_t>((size_t)(kMmaThreads / 32) * kSegCand, (size_t)lay.nseg * kSegCand) * 16 + 127) & ~(size_t)127);
-    put(lay.off_stage, !bulk ? (size_t)(kMmaThreads / 32) * kMmaStageBytes : (size_t)2 * 8 * lay.rowb);
+    put(lay.off_stage, !bulk ? (size_t)(kMmaThreads / 32) * ((wx || !BS2E_MMA_HALF) ? kMmaStageBytes : kMmaHalfBytes) : (size_t)2 * 8 * lay.rowb);
     lay.bytes = b;
     return lay;
 }

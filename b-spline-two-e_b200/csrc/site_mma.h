@@ -11,11 +11,17 @@ namespace bs2e {
 
 constexpr int kMmaThreads = 256;
 constexpr size_t kMmaSmemLimit = 227 * 1024;   // per CTA; two CTAs per SM up to 113 KB
-constexpr int kMmaStageBytes = 8 * 512;         // staging tile of one warp: 8 rows of 32 values
+constexpr int kMmaStageRow = 512 + 16;          // bytes per row of a staging tile: 32 values + 16 B, so that the rows a
+                                                // quarter warp writes to (0,2,4,6 / 1,3,5,7) start in different banks
+constexpr int kMmaStageBytes = 8 * kMmaStageRow; // staging tile of one warp: 8 rows of 32 values
+// sites without exchange windows stage four rows at a time (rows l3 = 0..3 of a quarter warp in different banks)
+constexpr int kMmaHalfRow = 512 + 32;
+constexpr int kMmaHalfBytes = 4 * kMmaHalfRow;
 
 struct MmaSmem {    // element counts of the dynamic shared memory carve-up
     int ncmax;      // n_c slots
     int nseg;       // candidate segments (mask words per table row)
+    int mstr;       // stride of the mask table rows in words (nseg | 1)
     int G;          // rows per group
     int cap;        // records per parity list
     int chrec;      // records per staging buffer (multiple of 8)

@@ -32,18 +32,18 @@ cell_moments_kernel(Geom g, double* __restrict__ mom_rk, double* __restrict__ mo
 
 __global__ void pair_prefix_kernel(Geom g, const double* __restrict__ mom_rk,
                                    const double* __restrict__ mom_rmk,
-                                   double* __restrict__ pre, double* __restrict__ sufx)
+                                   double* __restrict__ pre, double* __restrict__ sufx, RkRow* __restrict__ rkrow)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)g.K1 * g.P) return;
-    pair_prefix_item(g, idx, mom_rk, mom_rmk, pre, sufx);
+    pair_prefix_item(g, idx, mom_rk, mom_rmk, pre, sufx, rkrow);
 }
 
 __global__ void __launch_bounds__(256)
-diag_cells_kernel(Geom g, double* __restrict__ rd)
+diag_cells_kernel(Geom g, double* __restrict__ rd, int v0)
 {
     extern __shared__ double sm[];
-    const int v = blockIdx.x + 1;
+    const int v = blockIdx.x + v0;
     const DiagSmem d = diag_smem_carve(g, sm);
     diag_phase_tables(g, v, d, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -71,6 +71,7 @@ void run_slater_cells(bs2e_ctx* c)
         c->d_pre = dev_alloc<double>(npre);
         c->d_sufx = dev_alloc<double>(npre);
         c->d_rd = dev_alloc<double>(nrd);
+        c->d_rkrow = dev_alloc<RkRow>((size_t)g.K1 * g.P);
     }
     BS2E_CUDA(cudaMemsetAsync(c->d_mom_rk, 0, sizeof(double) * nmom, c->stream));
     BS2E_CUDA(cudaMemsetAsync(c->d_mom_rmk, 0, sizeof(double) * nmom, c->stream));
@@ -86,7 +87,7 @@ void run_slater_cells(bs2e_ctx* c)
     {
         const size_t n = (size_t)g.K1 * g.P;
         pair_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-            g, c->d_mom_rk, c->d_mom_rmk, c->d_pre, c->d_sufx);
+            g, c->d_mom_rk, c->d_mom_rmk, c->d_pre, c->d_sufx, c->d_rkrow);
         BS2E_LAUNCHED();
     }
     {
@@ -95,12 +96,18 @@ void run_slater_cells(bs2e_ctx* c)
             throw Error("diag_cells: k_GL^2*k B-spline table does not fit in shared memory");
         BS2E_CUDA(cudaFuncSetAttribute(diag_cells_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int ksplit = (16 * 148 + g.cells - 1) / g.cells;
+        // same-cell integrals of the cells the rows of the slice live on (bs2e_rk_rows; all cells by default):
+        // pairs (a, c), a in [a_lo, a_hi], |a - c| <= w  ->  cells a_lo-ks+2 .. a_hi+1 (pair_lo_cell / pair_hi_cell)
+        const int v0 = std::max(1, c->slice_lo - g.ks + 2), v1 = std::min(g.cells, c->slice_hi + 1);
+        const int ncell = std::max(1, v1 - v0 + 1);
+        int ksplit = (16 * 148 + ncell - 1) / ncell;
         ksplit = std::max(1, std::min(ksplit, g.K1));
-        diag_cells_kernel<<<dim3(g.cells, ksplit), 256, smem, c->stream>>>(g, c->d_rd);
+        diag_cells_kernel<<<dim3(ncell, ksplit), 256, smem, c->stream>>>(g, c->d_rd, v0);
         BS2E_LAUNCHED();
     }
     c->have_cells = true;
+    c->cells_lo = c->slice_lo;
+    c->cells_hi = c->slice_hi;
 }
 
 // ---------------------------------------------------------------------------
@@ -149,6 +156,7 @@ void fetch_r_d_k(bs2e_ctx* c, double* r_d_k, int64_t* iv, int64_t* ia, int64_t* 
                  int64_t* jpa)
 {
     if (!c->have_cells) throw Error("bs2e_get_r_d_k: call bs2e_slater_cells first");
+    if (c->cells_lo != 1 || c->cells_hi != c->hg.nb) throw Error("bs2e_get_r_d_k: stage A ran for a row slice only (bs2e_rk_rows)");
     const Geom& g = c->hg;
     const size_t ks2 = (size_t)g.ks * g.ks;
     const size_t nrd = (size_t)g.cells * g.K1 * ks2 * ks2;

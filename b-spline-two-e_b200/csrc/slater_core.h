@@ -69,8 +69,9 @@ BS2E_HD void mom_phase_integrate(const Geom& g, int v, const MomSmem& m, int tid
 
 // pre[t]  = sum_{slot <  t} r_k ,  t = 0..ks   (pre[ks]  = total)
 // sufx[t] = sum_{slot >= t} r_m_k, t = 0..ks   (sufx[0] = total)
+// rkrow[idx]: the pair's cell range and the two totals, packed for the streaming role of stage B (core.h: RkRow)
 BS2E_HD void pair_prefix_item(const Geom& g, size_t idx, const double* mom_rk,
-                              const double* mom_rmk, double* pre, double* sufx)
+                              const double* mom_rmk, double* pre, double* sufx, RkRow* rkrow)
 {
     const int ks = g.ks;
     const double* rk = mom_rk + idx * ks;
@@ -83,6 +84,14 @@ BS2E_HD void pair_prefix_item(const Geom& g, size_t idx, const double* mom_rk,
     run = 0.0;
     sf[ks] = 0.0;
     for (int t = ks - 1; t >= 0; --t) { run += rmk[t]; sf[t] = run; }
+    const PairAC q = g.pair[idx % (size_t)g.P];
+    RkRow r;
+    r.lo = pair_lo_cell(g, q.a, q.c);
+    r.hi = pair_hi_cell(g, q.a, q.c);
+    r.trk = pr[ks];
+    r.trmk = sf[0];
+    r.pad = 0.0;
+    rkrow[idx] = r;
 }
 
 // ---- same-cell double integral (mat_els.f90:441-491) -----------------------

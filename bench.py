@@ -22,11 +22,13 @@ integrals/s of stages A+B is reported beside it ("rk_integrals_per_s").
           Fortran caller allocates them
   --impl reference : the CPU oracle port of the reference path on the host cores
 
-N>1 (torchrun, one rank per GPU): strong scaling.  Every rank builds the R^k
-tensor (cheaper than an all-gather) and assembles its
+N>1 (torchrun, one rank per GPU): strong scaling.  Every rank assembles its
 share of the rows of every symmetry block -- rows are dealt by the first radial
 index of their configuration so that radial sites stay whole, balanced on the
-stored entries (bs2e.sharding.site_partition); no data-path collective.
+stored entries and then on measured times (bs2e.sharding: site_units,
+refine_bounds; untimed set-up) -- and builds the rows of the R^k tensor its
+radial sites read (bs2e_rk_rows: a slice by first spline index; cheaper than an
+all-gather of the whole tensor); no data-path collective.
 value = elements of all ranks / max-over-ranks stage-C time.
 """
 import argparse
@@ -145,7 +147,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import bs2e
-    from bs2e.sharding import exchange_cost, site_partition
+    from bs2e.sharding import exchange_cost, ranges_of_bounds, refine_bounds, rk_rows_needed, site_units, unit_bounds
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus:
@@ -187,7 +189,7 @@ def run_ours(args):
     # ---- untimed setup: the inputs of the path made resident in HBM ----
     ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(H_vec, S)
     cfgs = [ctx.configs_upload(s) for s in syms]           # term%configs of every symmetry
-    ranges = []
+    ranges, units, bounds = [], [], []
     for s, c in zip(syms, cfgs):
         if world == 1:
             ranges.append([(1, s.n_config)])
@@ -196,10 +198,55 @@ def run_ours(args):
             tmp = ctx.block_plan(s, full, cfg=c)
             cH, cS = tmp.row_counts()
             tmp.free()
-            mine = site_partition(s.conf_n, cH + cS, world, setup.k, exchange_cost(setup.p['max_k']))[rank]
-            if not mine:
+            present, unit_w = site_units(s.conf_n, cH + cS, setup.k, exchange_cost(setup.p['max_k']))
+            units.append((present, unit_w))
+            bounds.append(unit_bounds(present, unit_w, world))
+            ranges.append(ranges_of_bounds(s.conf_n, bounds[-1])[rank])
+            if not ranges[-1]:
                 raise SystemExit(f"rank {rank}: empty share of block L={s.l} (more GPUs than radial indices)")
-            ranges.append(mine)
+    ctx.sync()
+    rebalance_log = []
+    if world > 1:
+        # measured rebalancing (untimed set-up, like the partition itself): every rank times stage C of its
+        # share of every block, the times are gathered and the n1 axis is cut again into intervals of equal
+        # measured cost (bs2e.sharding.refine_bounds); every rank computes the same cuts from the same numbers
+        for it in range(args.rebalance + 1):
+            mine = []
+            for s, c, r in zip(syms, cfgs, ranges):
+                best = None
+                for rep in range(2):
+                    with torch.cuda.stream(stream):
+                        a = torch.cuda.Event(enable_timing=True); a.record(stream)
+                        blk = ctx.block_plan(s, full, ranges=r, cfg=c)
+                        blk.assemble()
+                        blk.free()
+                        b = torch.cuda.Event(enable_timing=True); b.record(stream)
+                    ctx.sync()
+                    t = a.elapsed_time(b)
+                    best = t if best is None else min(best, t)
+                mine.append(best)
+            t_all = torch.zeros(world, len(syms), device="cuda", dtype=torch.float64)
+            dist.all_gather_into_tensor(t_all, torch.tensor(mine, device="cuda", dtype=torch.float64))
+            t_all = t_all.cpu().numpy()
+            rebalance_log.append({"max_over_mean": [float(t_all[:, q].max() / t_all[:, q].mean()) for q in range(len(syms))],
+                                  "sum_of_max_ms": float(t_all.max(axis=0).sum())})
+            if it == args.rebalance:
+                break
+            for q, s in enumerate(syms):
+                bounds[q] = refine_bounds(units[q][0], units[q][1], bounds[q], t_all[:, q])
+                ranges[q] = ranges_of_bounds(s.conf_n, bounds[q])[rank]
+                if not ranges[q]:
+                    raise SystemExit(f"rank {rank}: empty share of block L={s.l} after rebalancing")
+    rk_rows = None
+    if world > 1 and not args.whole_rk:
+        # stages A and B per rank: only the rows of the R^k tensor this rank's radial sites read (bs2e_rk_rows)
+        need = [rk_rows_needed(s.conf_n, bounds[q][rank], setup.k) for q, s in enumerate(syms)]
+        a_lo, a_hi = min(n[0] for n in need), max(n[1] for n in need)
+        ctx.rk_rows(a_lo, a_hi)
+        ctx.slater_cells(); ctx.rk_build(); ctx.sync()
+        g = torch.zeros(world, 2, device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(g, torch.tensor([a_lo, a_hi], device="cuda", dtype=torch.float64))
+        rk_rows = [[int(a), int(b)] for a, b in g.cpu().numpy()]
     ctx.sync()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -209,6 +256,7 @@ def run_ours(args):
         return e
 
     elems_of_step = [0]
+    host_ms = []   # host time of every block_plan / assemble call (BS2E_BENCH_TRACE)
 
     def one_step(rec):
         """stage A, stage B, then stage C block by block: plan (device-built, the host reads the totals),
@@ -222,10 +270,13 @@ def run_ours(args):
             e1 = ev()
             per_block, el = [], 0
             for s, c, r in zip(syms, cfgs, ranges):
+                h0 = time.perf_counter()
                 blk = ctx.block_plan(s, full, ranges=r, cfg=c)
+                h1 = time.perf_counter()
                 f0 = ev()
-                blk.assemble()                              # the two concurrent site_fill_kernel launches
+                blk.assemble()                              # the two concurrent launches of the site kernel
                 f1 = ev()
+                host_ms.append((1e3 * (h1 - h0), 1e3 * (time.perf_counter() - h1)))
                 n = blk.nnz_H + blk.nnz_S
                 per_block.append((f0, f1, n, blk.nnz_H, blk.nnz_S, blk.nrows))
                 blk.free()                                  # stream-ordered: the pool hands the pages to the next block
@@ -254,12 +305,30 @@ def run_ours(args):
     launches = bs2e.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
+    if os.environ.get("BS2E_BENCH_TRACE"):
+        nb_ = len(syms)
+        for k_, r in enumerate(rec):
+            fm = [round(q[0].elapsed_time(q[1]), 2) for q in r[4]]
+            hm = host_ms[-(len(rec) - k_) * nb_:][:nb_]
+            print(f"[trace rank {rank} step {k_}] stage C {r[2].elapsed_time(r[3]):.2f} ms; fill per block {fm}; "
+                  f"host plan/assemble ms {[(round(a, 2), round(b, 2)) for a, b in hm]}", file=sys.stderr)
     my_elems = elems_of_step[0]
     total_elems = sum_over_ranks(my_elems)
     tA = sum(r[0].elapsed_time(r[1]) for r in rec)
     tB = sum(r[1].elapsed_time(r[2]) for r in rec)
     tC = sum(r[2].elapsed_time(r[3]) for r in rec)
     fill_ms = [q[0].elapsed_time(q[1]) for r in rec for q in r[4]]
+    per_rank = None
+    if world > 1:   # stage times and fill times of every rank (the value uses the max)
+        g = torch.zeros(world, 4, device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(g, torch.tensor([tA, tB, tC, sum(fill_ms)], device="cuda", dtype=torch.float64))
+        g = (g / args.steps).cpu().numpy()
+        per_rank = {"A_cells_ms": g[:, 0].tolist(), "B_rk_ms": g[:, 1].tolist(), "C_blocks_ms": g[:, 2].tolist(),
+                    "C_fill_only_ms": g[:, 3].tolist()}
+        gs = torch.zeros(world, args.steps, device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(gs, torch.tensor([r[2].elapsed_time(r[3]) for r in rec], device="cuda",
+                                                     dtype=torch.float64))
+        per_rank["C_blocks_ms_of_every_step"] = gs.cpu().numpy().round(3).tolist()
     tA, tB, tC = max_over_ranks(tA), max_over_ranks(tB), max_over_ranks(tC)
     wall = max_over_ranks(wall)
     K = args.steps
@@ -273,12 +342,16 @@ def run_ours(args):
     avg_fill_ms = fill_total_ms / n_fill
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_per_launch / (avg_fill_ms * 1e-3) / 1e9
-    roofline = {"kernel": "site_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+    fill_mode = os.environ.get("BS2E_FILL")
+    fill_kernel = ("site_mma_kernel" if (fill_mode == "mma" or (fill_mode is None and K1 > 7)) else
+                   "block_fill_kernel" if fill_mode == "row" else "site_fill_kernel")
+    roofline = {"kernel": fill_kernel, "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_fill_ms,
                 "timed": "CUDA events around the fill of every block inside the timed steps (a launch = the two "
-                         "concurrent site_fill_kernel launches of one symmetry block; the stream is idle when they start)",
+                         "concurrent launches of the site kernel -- sites with / without exchange windows -- of one symmetry "
+                         "block; the stream is idle when they start)",
                 "share_of_stage_C": (fill_total_ms / K) / max(tC / K, 1e-9),
                 # the same bytes over the whole timed stage C (plans, count passes, scans, allocation included)
                 "achieved_over_timed_stage_C": 24.0 * my_elems * K / (tC * 1e-3) / 1e9,
@@ -310,9 +383,15 @@ def run_ours(args):
                        "stage_C": "per symmetry block: device-built plan + count pass + scan (host reads the totals), "
                                   "CSR arrays from the memory pool, fill, release; one block at a time",
                        "l2": "256 MiB buffer written between timed iterations; R^k and CSR output exceed L2",
-                       "parallelism": "R^k replicated per GPU, rows of every symmetry block dealt by first radial index (radial sites stay whole), no collective" if world > 1 else "single GPU"},
+                       "parallelism": ("rows of every symmetry block dealt by first radial index (radial sites stay whole), every GPU builds "
+                                       "the R^k rows its sites read, no collective") if world > 1 else "single GPU"},
             "stage_ms_per_step": {"A_cells": tA / K, "B_rk": tB / K, "C_blocks": tC / K,
-                                  "C_fill_only": fill_total_ms / K},
+                                  "C_fill_only": fill_total_ms / K,
+                                  "C_blocks_of_every_step": [round(r[2].elapsed_time(r[3]), 3) for r in rec]},
+            "per_rank_ms_per_step": per_rank,
+            "partition": ({"unit": "first radial index n1 (radial sites stay whole)",
+                           "rebalance_steps": args.rebalance, "measured": rebalance_log,
+                           "rk_rows_per_rank": rk_rows, "n_b": int(ctx.n_b)} if world > 1 else None),
             "rk_integrals_per_s": rk_per_s,
             "whole_step_elements_per_s": total_elems * K / ((tA + tB + tC) * 1e-3),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -587,6 +666,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-destination pass of the e2e leg")
     ap.add_argument("--no-fp64-peak", action="store_true", help="skip the cuBLAS DGEMM measurement")
+    ap.add_argument("--whole-rk", action="store_true", help="N>1: every rank builds the whole R^k tensor (A/B)")
+    ap.add_argument("--rebalance", type=int, default=3,
+                    help="N>1: steps of measured rebalancing of the row partition in the untimed set-up")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

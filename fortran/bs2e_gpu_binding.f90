@@ -221,6 +221,7 @@ contains
                                         int(max_k, c_int64_t), int(k_GL, c_int64_t), x, w, &
                                         device, ctx), "ctx_create")
         one_particle_set = .false.
+        radial_dip_set = .false.   ! a new context holds no radial dipole matrices either
         call bs2e_check(bs2e_slater_cells(ctx), "slater_cells")
         call bs2e_check(bs2e_get_r_k(ctx, r_k%data, r_m_k%data, r_k%iv, r_k%i, r_k%j), "get_r_k")
         r_m_k%iv = r_k%iv
@@ -364,6 +365,8 @@ contains
     subroutine bs2e_gpu_finalize()
         if (c_associated(ctx)) call bs2e_check(bs2e_ctx_destroy(ctx), "ctx_destroy")
         ctx = c_null_ptr
+        one_particle_set = .false.
+        radial_dip_set = .false.
     end subroutine bs2e_gpu_finalize
 
 end module bs2e_gpu

@@ -42,6 +42,9 @@ int bs2e_device_count(int64_t *count);
 int bs2e_ctx_create(int64_t k_spline, int64_t n_knots, const double *knots,
                     int64_t max_k, int64_t k_GL, const double *gl_x,
                     const double *gl_w, int64_t device, bs2e_ctx **ctx);
+/* Destroys the context and everything it holds on the device.  Block, configuration
+ * and dipole-block handles made from it must be freed BEFORE this call; blocks parked
+ * by bs2e_block_count for a later bs2e_block_fill are released here.               */
 int bs2e_ctx_destroy(bs2e_ctx *ctx);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t). */
 int bs2e_ctx_set_stream(bs2e_ctx *ctx, void *cuda_stream);
@@ -69,6 +72,15 @@ int bs2e_get_r_d_k(bs2e_ctx *ctx, double *r_d_k, int64_t *iv, int64_t *i,
  *      The R^k tensor stays on the device; the Fortran Nd_DOK becomes a
  *      holder of the context handle.                                        */
 int bs2e_rk_build(bs2e_ctx *ctx);
+/* Multi-GPU (the reference runs this stage once per process,
+ * src/apps/main_basis_setup.f90:80-85): a GPU that assembles a share of the rows of
+ * every symmetry block reads only the rows R^k(a .; . .) of the tensor whose first
+ * spline index a belongs to its radial sites.  After bs2e_rk_rows(ctx, a_lo, a_hi)
+ * bs2e_slater_cells computes the same-cell integrals of the cells those rows live on
+ * and bs2e_rk_build the rows a_lo <= a <= a_hi only; the default is 1..n_b.
+ * bs2e_block_fill of rows that read outside the built slice is an error, and so are
+ * the getters (bs2e_get_r_d_k, bs2e_rk_get, bs2e_rk_plane) on a partial tensor.     */
+int bs2e_rk_rows(bs2e_ctx *ctx, int64_t a_lo, int64_t a_hi);
 /* Nd_DOK%get_val (sparse_array_tools.f90:536-555) for n_keys keys (a,b,c,d):
  * keys is (4, n_keys), vals is (max_k+1, n_keys); a key outside the band
  * structure is an error, as in the reference.                               */

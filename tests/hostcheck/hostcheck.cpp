@@ -24,6 +24,7 @@ static std::string g_err;
 struct HcCtx {
     HostGeom hg;
     std::vector<double> mom_rk, mom_rmk, pre, sufx, rd, R;
+    std::vector<RkRow> rkrow;
     std::vector<double> Hb, Sb;
     int lmax_1p = -1;
     std::vector<double> dipA, dipB;
@@ -73,8 +74,9 @@ void hc_slater_cells(HcCtx* c, int64_t nthr_mom, int64_t nthr_diag, int64_t kspl
         for (int t = 0; t < nthr_mom; ++t)
             mom_phase_integrate(g, v, m, t, (int)nthr_mom, c->mom_rk.data(), c->mom_rmk.data());
     }
+    c->rkrow.assign((size_t)g.K1 * g.P, rk_row_empty());
     for (size_t idx = 0; idx < (size_t)g.K1 * g.P; ++idx)
-        pair_prefix_item(g, idx, c->mom_rk.data(), c->mom_rmk.data(), c->pre.data(), c->sufx.data());
+        pair_prefix_item(g, idx, c->mom_rk.data(), c->mom_rmk.data(), c->pre.data(), c->sufx.data(), c->rkrow.data());
     std::vector<double> sd(diag_smem_doubles(g));
     for (int v = 1; v <= g.cells; ++v)
         for (int by = 0; by < ksplit; ++by) {
@@ -96,24 +98,48 @@ void hc_get_moments(HcCtx* c, double* mom_rk, double* mom_rmk, double* rd)
     if (rd) memcpy(rd, c->rd.data(), sizeof(double) * c->rd.size());
 }
 
-// emulates run_rk_build with the same grid/thread decomposition
+// emulates run_rk_build with the same decomposition: band tiles (one thread per column of the band) and streaming
+// tiles (one thread per column pair), every entry written exactly once
 void hc_rk_build(HcCtx* c)
 {
     const Geom& g = c->hg.g;
-    c->R.assign((size_t)g.K1 * g.P * g.ldP, -3.0);
+    const double unset = -3.0;
+    c->R.assign((size_t)g.K1 * g.P * g.ldP, unset);
     CellData cd{c->mom_rk.data(), c->mom_rmk.data(), c->pre.data(), c->sufx.data(), c->rd.data()};
-    const int gx = (g.ldP / 2 + kRkThreads - 1) / kRkThreads, gy = (g.P + kRkRows - 1) / kRkRows;
-    for (int k = 0; k < g.K1; ++k)
-        for (int by = 0; by < gy; ++by)
-            for (int bx = 0; bx < gx; ++bx) {
-                RkRow rows[kRkRows];
-                std::vector<int> list;
-                for (int tx = 0; tx < kRkRows; ++tx) rows[tx] = rk_row_data(g, cd, k, by * kRkRows + tx);
-                for (int tx = 0; tx < kRkThreads; ++tx)
-                    rk_stream_thread(g, cd, c->R.data(), rows, bx, by, k, tx, [&](int code) { list.push_back(code); });
-                if (list.size() > (size_t)kRkRows * kRkThreads * 2) throw std::logic_error("tile list overflow");
-                for (int code : list) rk_general_item(g, cd, c->R.data(), bx, by, k, code);
+    const int row_lo = 0, row_hi = g.P;
+    for (int k = 0; k < g.K1; ++k) {
+        const RkRow* rk = c->rkrow.data() + (size_t)k * g.P;
+        for (int p = 0; p < g.P; ++p) {   // the packed records are what rk_row_data derives from the prefix tables
+            const RkRow a = rk[p], b = rk_row_data(g, cd, k, p);
+            if (a.lo != b.lo || a.hi != b.hi || a.trk != b.trk || a.trmk != b.trmk) throw std::logic_error("RkRow mismatch");
+        }
+        std::vector<double> before;
+        for (int r0 = row_lo; r0 < row_hi; r0 += kRkRowsB) {          // band role
+            const int nrows = std::min(kRkRowsB, row_hi - r0);
+            int c0, c1;
+            rk_band_columns(g, r0, r0 + nrows, &c0, &c1);
+            // even row tiles through the staged body (vectors handed in), odd ones through the direct one
+            for (int p2 = c0; p2 < c1; ++p2) {
+                if (((r0 - row_lo) / kRkRowsB) & 1) { rk_band_column(g, cd, c->R.data(), rk + r0, r0, nrows, k, p2, rk[p2]); continue; }
+                const size_t rb = ((size_t)k * g.P + r0) * (g.ks + 1), cb = ((size_t)k * g.P + p2) * g.ks;
+                rk_band_column_staged(g, cd, c->R.data(), rk + r0, r0, nrows, k, p2, rk[p2], c->pre.data() + rb,
+                                      c->sufx.data() + rb, c->mom_rk.data() + cb, c->mom_rmk.data() + cb);
             }
+        }
+        const double* plane = c->R.data() + (size_t)k * g.P * g.ldP;
+        before.assign(plane, plane + (size_t)g.P * g.ldP);
+        for (int r0 = row_lo; r0 < row_hi; r0 += kRkRowsS) {          // streaming role
+            const int nrows = std::min(kRkRowsS, row_hi - r0);
+            for (int p2 = 0; p2 < g.ldP; p2 += 2) {
+                const RkRow c0 = p2 < g.P ? rk[p2] : rk_row_empty(), c1 = p2 + 1 < g.P ? rk[p2 + 1] : rk_row_empty();
+                rk_stream_columns(g, c->R.data(), rk + r0, r0, nrows, k, p2, c0, c1);
+            }
+        }
+        for (size_t i = 0; i < before.size(); ++i) {   // the two roles write disjoint entries and together all of them
+            if (before[i] != unset && plane[i] != before[i]) throw std::logic_error("stage B: entry written by both roles");
+            if (plane[i] == unset) throw std::logic_error("stage B: entry not written");
+        }
+    }
 }
 
 void hc_get_R(HcCtx* c, double* R) { memcpy(R, c->R.data(), sizeof(double) * c->R.size()); }

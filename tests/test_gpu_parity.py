@@ -330,6 +330,54 @@ def test_site_partition_fragments_merge_to_whole_block():
     ctx.close()
 
 
+def test_rk_row_slices_per_share_equal_whole_tensor():
+    """bs2e_rk_rows: a 'rank' that builds only the R^k rows its radial sites read (stage A cells and stage B
+    rows restricted) assembles bit-identical fragments; reading outside the slice and the getters on a
+    partial tensor are errors"""
+    from bs2e.sharding import ranges_of_bounds, rk_rows_needed, site_units, unit_bounds
+    p = SMALL_CASES["wide_k6"]
+    run = O.OracleRun(**p)
+    run.one_particle(); run.basis()
+    ctx = _ctx(run)
+    ctx.slater_cells(); ctx.rk_build(); ctx.set_one_particle(run.H_vec, run.S)
+    parts, want = 3, {}
+    for q, s in enumerate(run.syms):
+        tmp = ctx.block_plan(s, False); cH, cS = tmp.row_counts(); tmp.free()
+        present, uw = site_units(s.conf_n, cH + cS)
+        bounds = unit_bounds(present, uw, parts)
+        for r, ranges in enumerate(ranges_of_bounds(s.conf_n, bounds)):
+            if not ranges:
+                continue
+            f = ctx.block_plan(s, False, ranges=ranges); f.assemble()
+            want[(q, r)] = (bounds[r], ranges, f.download()); f.free()
+    slices = []
+    for r in range(parts):
+        need = [rk_rows_needed(run.syms[q].conf_n, b, p["k"]) for (q, rr), (b, _, _) in want.items() if rr == r]
+        a_lo, a_hi = min(n[0] for n in need), max(n[1] for n in need)
+        slices.append((a_lo, a_hi))
+        ctx2 = _ctx(run)                      # a fresh context: nothing outside the slice is ever computed
+        ctx2.rk_rows(a_lo, a_hi)
+        ctx2.slater_cells(); ctx2.rk_build(); ctx2.set_one_particle(run.H_vec, run.S)
+        for (q, rr), (b, ranges, (H0, S0)) in want.items():
+            if rr != r:
+                continue
+            f = ctx2.block_plan(run.syms[q], False, ranges=ranges); f.assemble()
+            H, S = f.download(); f.free()
+            for A, B in ((H, H0), (S, S0)):
+                assert np.array_equal(A.index_ptr, B.index_ptr) and np.array_equal(A.indices, B.indices)
+                assert np.array_equal(A.data, B.data)
+        if (a_lo, a_hi) != (1, ctx2.n_b):
+            with pytest.raises(bs2e.Bs2eError):   # the whole block reads rows outside the slice
+                w = ctx2.block_plan(run.syms[0], False); w.assemble()
+            with pytest.raises(bs2e.Bs2eError):
+                ctx2.rk_plane(0)
+        ctx2.close()
+    assert any(sl != (1, ctx.n_b) for sl in slices)   # the case does exercise a proper slice
+    with pytest.raises(bs2e.Bs2eError):
+        ctx.rk_rows(0, 3)
+    ctx.close()
+
+
 def test_blocks_run_pipelined_equals_block_by_block(case):
     """bs2e_blocks_run (count + fill of all blocks over internal streams) == one block at a time"""
     run, ctx = case

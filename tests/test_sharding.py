@@ -93,6 +93,35 @@ def test_site_partition_keeps_sites_together_and_merges():
     assert rows(costly[0]) < rows(plain[0]) and rows(costly[0]) + rows(costly[1]) == n
 
 
+def test_measured_rebalancing_converges_and_keeps_the_tiling():
+    """refine_bounds: with a cost the model weights miss (rows at small n1 three times as dear), a few steps of
+    re-cutting on measured times bring max/mean of the parts down to the granularity of a unit; the parts
+    stay a tiling of the rows and every rank computes the same cuts from the same gathered numbers."""
+    from bs2e.sharding import ranges_of_bounds, refine_bounds, site_units, unit_bounds
+    rng = np.random.default_rng(5)
+    n1 = np.sort(rng.integers(1, 61, 8000))
+    conf_n = np.stack([n1, rng.integers(1, 80, 8000)], axis=1)
+    w = rng.integers(1, 200, 8000)
+    present, unit_w = site_units(conf_n, w)
+    true = np.where(present < 12, 3.0, 1.0) * unit_w
+    measure = lambda bounds: [float(true[(present >= a) & (present <= b)].sum()) for a, b in bounds]
+    bounds = unit_bounds(present, unit_w, 4)
+    first = max(measure(bounds)) / np.mean(measure(bounds))
+    for _ in range(3):
+        t = measure(bounds)
+        again = refine_bounds(present, unit_w, bounds, t)
+        assert again == refine_bounds(present.copy(), unit_w.copy(), list(bounds), list(t))   # deterministic
+        bounds = again
+    last = max(measure(bounds)) / np.mean(measure(bounds))
+    assert first > 1.5 and last < 1.12
+    parts = ranges_of_bounds(conf_n, bounds)
+    rows = np.sort(np.concatenate([np.arange(lo, hi + 1) for r in parts for lo, hi in r]))
+    assert np.array_equal(rows, np.arange(1, len(n1) + 1))
+    for (a, b), r in zip(bounds, parts):   # whole sites: every row of a part has its n1 inside the part's interval
+        for lo, hi in r:
+            assert n1[lo - 1] >= a and n1[hi - 1] <= b
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
