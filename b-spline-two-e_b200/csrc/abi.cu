@@ -154,6 +154,8 @@ int bs2e_ctx_destroy(bs2e_ctx* c)
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         purge_parked(c);          // plans parked by bs2e_block_count that no fill call collected
+        out_release_all(c);       // cached CSR output arrays
+        cudaStreamSynchronize(c->stream);
         stager_destroy(c);
         ctx_release_plan_state(c);
         cudaFree(c->d_t); cudaFree(c->d_bp); cudaFree(c->d_glx); cudaFree(c->d_glw);

@@ -896,11 +896,11 @@ void block_assemble(bs2e_block* b, const BlockStreams* bsp)
         throw Error("block_assemble: the planned rows read R^k rows outside the slice that was built (bs2e_rk_rows)");
     if (!c->have_1p) throw Error("block_assemble: call bs2e_set_one_particle first");
     if (b->lmax > c->lmax_1p) throw Error("block_assemble: configuration l exceeds max_l_1p of H_vec");
-    if (!b->d_Hidx) {
-        b->d_Hidx = dev_alloc_async<long long>(b->nnzH, bs.main);
-        b->d_Hdat = dev_alloc_async<double>(2 * (size_t)b->nnzH, bs.main);
-        b->d_Sidx = dev_alloc_async<long long>(b->nnzS, bs.main);
-        b->d_Sdat = dev_alloc_async<double>(2 * (size_t)b->nnzS, bs.main);
+    if (!b->d_Hidx) {   // largest first: each takes the smallest cached array that is large enough
+        b->d_Hdat = static_cast<double*>(out_take(c, sizeof(double) * 2 * (size_t)b->nnzH, bs.main, &b->cap_Hdat));
+        b->d_Hidx = static_cast<long long*>(out_take(c, sizeof(long long) * (size_t)b->nnzH, bs.main, &b->cap_Hidx));
+        b->d_Sdat = static_cast<double*>(out_take(c, sizeof(double) * 2 * (size_t)b->nnzS, bs.main, &b->cap_Sdat));
+        b->d_Sidx = static_cast<long long*>(out_take(c, sizeof(long long) * (size_t)b->nnzS, bs.main, &b->cap_Sidx));
     }
     const long long nrows = b->nrows;
     const Geom& g = c->dg;
@@ -1056,15 +1056,108 @@ void site_phase_cycles(unsigned long long* out8, bool reset)
 #endif
 }
 
+// ---------------------------------------------------------------------------
+// CSR output arrays.  They are multi-GB and live for one block; cudaMalloc / cudaFree cost 5-500 ms each, and the
+// driver's stream-ordered pool, which took their place first, was measured to stall a cudaMallocAsync for up to
+// 1.06 s now and then (gpurun_out/r03g: one step of 21 ms became 1081 ms; the pool regroups its free blocks when
+// requests of many sizes alternate).  So arrays given back by bs2e_block_free wait in a per-context cache and the
+// next block takes the smallest one that is large enough; only a request no cached array can serve goes to
+// cudaMallocAsync.  The cache is bounded (45 % of the device memory, 24 arrays): the smallest arrays leave first,
+// so that after one pass over the blocks of a configuration it holds arrays that serve every block.
+// ---------------------------------------------------------------------------
+void* out_take(bs2e_ctx* c, size_t bytes, cudaStream_t st, size_t* cap)
+{
+    if (bytes == 0) bytes = 16;
+    bs2e_ctx::OutBuf pick{nullptr, 0, nullptr};
+    {
+        std::lock_guard<std::mutex> lk(c->out_mu);
+        int at = -1;
+        for (int i = 0; i < (int)c->out_free.size(); ++i)
+            if (c->out_free[i].bytes >= bytes && (at < 0 || c->out_free[i].bytes < c->out_free[at].bytes)) at = i;
+        if (at >= 0) {
+            pick = c->out_free[at];
+            c->out_free.erase(c->out_free.begin() + at);
+            c->out_cached -= pick.bytes;
+        }
+    }
+    if (pick.p) {
+        BS2E_CUDA(cudaStreamWaitEvent(st, pick.ev, 0));   // the work that last used the array
+        cudaEventDestroy(pick.ev);
+        *cap = pick.bytes;
+        return pick.p;
+    }
+    void* p = nullptr;
+    const size_t want = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    if (cudaMallocAsync(&p, want, st) != cudaSuccess) {   // out of memory with arrays parked in the cache: drop them
+        cudaGetLastError();
+        out_release_all(c);
+        BS2E_CUDA(cudaStreamSynchronize(c->stream));
+        BS2E_CUDA(cudaMallocAsync(&p, want, st));
+    }
+    *cap = want;
+    return p;
+}
+
+void out_give(bs2e_ctx* c, void* p, size_t cap, cudaStream_t st)
+{
+    if (!p) return;
+    if (c->out_cap == 0) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        c->out_cap = (size_t)(0.45 * (double)tot);
+    }
+    bs2e_ctx::OutBuf b{p, cap, nullptr};
+    if (cap > c->out_cap || cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeAsync(p, st);
+        return;
+    }
+    cudaEventRecord(b.ev, st);
+    std::vector<bs2e_ctx::OutBuf> drop;
+    {
+        std::lock_guard<std::mutex> lk(c->out_mu);
+        c->out_free.push_back(b);
+        c->out_cached += cap;
+        while (c->out_cached > c->out_cap || c->out_free.size() > 24) {   // the smallest arrays leave first
+            int at = 0;
+            for (int i = 1; i < (int)c->out_free.size(); ++i)
+                if (c->out_free[i].bytes < c->out_free[at].bytes) at = i;
+            drop.push_back(c->out_free[at]);
+            c->out_cached -= c->out_free[at].bytes;
+            c->out_free.erase(c->out_free.begin() + at);
+        }
+    }
+    for (auto& d : drop) {
+        cudaStreamWaitEvent(st, d.ev, 0);
+        cudaFreeAsync(d.p, st);
+        cudaEventDestroy(d.ev);
+    }
+}
+
+void out_release_all(bs2e_ctx* c)
+{
+    std::vector<bs2e_ctx::OutBuf> all;
+    {
+        std::lock_guard<std::mutex> lk(c->out_mu);
+        all.swap(c->out_free);
+        c->out_cached = 0;
+    }
+    for (auto& d : all) {
+        cudaStreamWaitEvent(c->stream, d.ev, 0);
+        cudaFreeAsync(d.p, c->stream);
+        cudaEventDestroy(d.ev);
+    }
+}
+
 void block_free(bs2e_block* b)
 {
     if (!b) return;
-    {   // stream-ordered: returns at once, the pool keeps the pages for the next block
-        cudaStream_t st = b->ctx ? b->ctx->stream : nullptr;
-        if (b->d_Hidx) cudaFreeAsync(b->d_Hidx, st);
-        if (b->d_Sidx) cudaFreeAsync(b->d_Sidx, st);
-        if (b->d_Hdat) cudaFreeAsync(b->d_Hdat, st);
-        if (b->d_Sdat) cudaFreeAsync(b->d_Sdat, st);
+    if (b->ctx) {   // stream-ordered: returns at once, the arrays wait in the context's cache for the next block
+        cudaStream_t st = b->ctx->stream;
+        if (b->d_Hdat) out_give(b->ctx, b->d_Hdat, b->cap_Hdat, st);
+        if (b->d_Hidx) out_give(b->ctx, b->d_Hidx, b->cap_Hidx, st);
+        if (b->d_Sdat) out_give(b->ctx, b->d_Sdat, b->cap_Sdat, st);
+        if (b->d_Sidx) out_give(b->ctx, b->d_Sidx, b->cap_Sidx, st);
     }
     if (b->ctx) {   // the plan tables go back to the context's pool, reusable once the queued work has read them
         arena_give(b->ctx, b->arena1, b->ctx->stream);

@@ -152,6 +152,11 @@ struct bs2e_ctx {
     std::mutex arena_mu;
     std::vector<bs2e::ArenaBuf*> arenas;  // pool of plan buffers (arena_take / arena_give)
     cudaMemPool_t arena_pool = nullptr;   // the memory pool they are allocated from
+    // CSR output arrays handed back by bs2e_block_free, kept for the next block (out_take / out_give, block.cu)
+    struct OutBuf { void* p; size_t bytes; cudaEvent_t ev; };
+    std::vector<OutBuf> out_free;
+    std::mutex out_mu;
+    size_t out_cached = 0, out_cap = 0;   // bytes held in out_free / upper bound for them
     int* h_pin = nullptr;        // pinned staging for the small read-backs of a plan
     size_t h_pin_bytes = 0;
     // copy stream + pinned bounce buffers for downloads into pageable memory (download.cu)
@@ -226,6 +231,7 @@ struct bs2e_block {
     long long *d_Hptr = nullptr, *d_Sptr = nullptr;  // [nrows+1] 1-based
     long long *d_Hidx = nullptr, *d_Sidx = nullptr;
     double *d_Hdat = nullptr, *d_Sdat = nullptr;
+    size_t cap_Hidx = 0, cap_Sidx = 0, cap_Hdat = 0, cap_Sdat = 0;   // capacities of the arrays (out_take)
     long long nnzH = 0, nnzS = 0;
     void* d_scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
@@ -249,6 +255,10 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
 bs2e_configs* configs_upload(bs2e_ctx* c, long long n_config, const int64_t* conf_n, const int64_t* conf_l);
 void configs_free(bs2e_configs* cfg);
 void ctx_release_plan_state(bs2e_ctx* c);
+// CSR output arrays: a per-context cache in front of the stream-ordered allocator (block.cu)
+void* out_take(bs2e_ctx* c, size_t bytes, cudaStream_t st, size_t* cap);
+void out_give(bs2e_ctx* c, void* p, size_t cap, cudaStream_t st);
+void out_release_all(bs2e_ctx* c);
 void arena_take(bs2e_ctx* c, DevArena& a, size_t bytes, cudaStream_t first_use);   // a free pool buffer of at least `bytes`
 void arena_give(bs2e_ctx* c, DevArena& a, cudaStream_t last_use);  // back to the pool, reusable after the work queued on last_use
 // per-row tables (row_n1 / row_n2 / row_blk) of a configuration list, built on the device

@@ -451,7 +451,7 @@ bs2e_block* block_plan(bs2e_ctx* c, int L, long long n_config, const int64_t* co
     b->site_cap = site_cap;
     b->use_site = site_kernel_usable(c, nblk, b->lmax);
     {   // Two site kernels fill the same CSR arrays: the tensor-core kernel (site_mma.cu) and the FMA kernel
-        // (block.cu).  Measured on B200 (scripts/fill_ab.py, profiles/r02v_fill_ab.md): the tensor-core kernel is
+        // (block.cu).  Measured on B200 (scripts/fill_ab.py, profiles/r02v_fill_ncu_summary.md): the tensor-core kernel is
         // ahead from 8 multipoles on (cfg3: 5.85 against 6.80 ms, cfg4: 41.3 against 42.6 ms); the FMA kernel stays
         // the choice for max_k <= 6, where a site is small (cfg1).  BS2E_FILL=mma / fma forces one of them.
         const char* mode = getenv("BS2E_FILL");

@@ -32,9 +32,14 @@ rk_build_kernel(const __grid_constant__ Geom g, const __grid_constant__ CellData
     extern __shared__ double stage[];   // band role: per-pair vectors of the tile's rows and columns (q.staged)
     const int k = blockIdx.y, tx = threadIdx.x;
     const RkRow* rk = rkrow + (size_t)k * g.P;
-    int b = blockIdx.x;
-    if (b < q.band_x * q.band_y) {
-        // ---- band role (scheduled first: these CTAs are latency-bound and run beside the streaming ones) ----
+    // the band tiles are spread evenly over the launch order, so that every SM holds a mix of the latency-bound
+    // band CTAs and the bandwidth-bound streaming CTAs at any time
+    const long long nband = (long long)q.band_x * q.band_y, ntot = gridDim.x;
+    const long long before = (long long)blockIdx.x * nband / ntot, upto = ((long long)blockIdx.x + 1) * nband / ntot;
+    int b;
+    if (upto > before) {
+        // ---- band role ----
+        b = (int)before;
         const int ty = b / q.band_x, bt = b - ty * q.band_x;
         const int r0 = q.row_lo + ty * kRkRowsB, nrows = imin(kRkRowsB, q.row_hi - r0);
         int c0, c1;
@@ -74,7 +79,7 @@ rk_build_kernel(const __grid_constant__ Geom g, const __grid_constant__ CellData
         return;
     }
     // ---- streaming role ----
-    b -= q.band_x * q.band_y;
+    b = (int)(blockIdx.x - before);
     const int ty = b / q.stream_x, bx = b - ty * q.stream_x;
     const int r0 = q.row_lo + ty * kRkRowsS, nrows = imin(kRkRowsS, q.row_hi - r0);
     if (tx < nrows) rows[tx] = rk[r0 + tx];

@@ -105,7 +105,7 @@ struct alignas(16) RowC {   // per row of the group
 // CTAs per SM: two (128 registers).  Three CTAs of 80 registers were measured for the sites without exchange
 // windows (-DBS2E_MMA_MINB_D=3; their shared memory fits with the half staging tiles): the compiler then keeps the
 // A fragments in local memory and reloads them per tile -- 5.70 instead of 4.61 ms on the L=6 block of cfg4
-// (profiles/r02w_*), long-scoreboard stalls 1.2 -> 6.4 per issue.
+// (profiles/r02v_fill_ncu_summary.md, section r02w), long-scoreboard stalls 1.2 -> 6.4 per issue.
 #ifndef BS2E_MMA_MINB_X
 #define BS2E_MMA_MINB_X 2
 #endif

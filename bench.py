@@ -289,7 +289,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.5)                                     # let nvidia-smi reach its sampling loop
+        # let nvidia-smi reach its sampling loop: its start-up (NVML initialisation) stalls the GPU for 0.1-0.5 s
+        # on some boxes and must not land in a timed step (seen as one 126 / 549 ms first step, gpurun_out/r03b,d)
+        t_wait = time.perf_counter()
+        while len(sampler.lines) < 3 and time.perf_counter() - t_wait < 10.0 and sampler.proc is not None:
+            time.sleep(0.05)
     for _ in range(args.warmup):
         one_step(None)
     barrier()
