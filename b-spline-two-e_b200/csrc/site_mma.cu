@@ -115,6 +115,9 @@ struct alignas(16) RowC {   // per row of the group
 #ifndef BS2E_MMA_HALF
 #define BS2E_MMA_HALF 1
 #endif
+// Measured and not kept (profiles/r02v_fill_ncu_summary.md, gpurun_out/r03k): an L2 prefetch of the next (pass, parity)'s
+// R^k values one record sweep ahead (41.25 against 41.28 ms over cfg4: the fetches are not what the kernel waits for),
+// and a warp-uniform skip of the store sequence of rows whose mask is empty in the warp's segment (41.68 ms: slower).
 template <int KMAX, bool WX, bool BULK>
 __global__ void __launch_bounds__(kMmaThreads, WX ? BS2E_MMA_MINB_X : BS2E_MMA_MINB_D)
 site_mma_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan pl, const __grid_constant__ OneBody ob,

@@ -74,9 +74,10 @@ def traffic(path, workload, nblocks):
     hdr, units, data = rows[0], rows[1], rows[2:]
     kn = hdr.index("Kernel Name")
     rd, wr, tm = (hdr.index(m) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
-    fills = [r for r in data if "site_fill" in r[kn] or "block_fill" in r[kn]]
+    fills = [r for r in data if "site_mma" in r[kn] or "site_fill" in r[kn] or "block_fill" in r[kn]]
     tot_r = sum(float(r[rd].replace(",", "")) * UNIT[units[rd]] for r in fills)
     tot_w = sum(float(r[wr].replace(",", "")) * UNIT[units[wr]] for r in fills)
+    # merged into the committed table: bench.py reads profiles/ncu_fill_traffic.json
     print(json.dumps({workload: {"dram_bytes_per_launch": (tot_r + tot_w) / int(nblocks),
                                  "dram_read_bytes_per_launch": tot_r / int(nblocks),
                                  "dram_write_bytes_per_launch": tot_w / int(nblocks),

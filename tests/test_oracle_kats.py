@@ -136,6 +136,29 @@ def test_he_singlet_S_block(test_grid_run):
     assert abs(ev[0] + 2.90276684) < 2e-8 and abs(ev[1] + 2.14584449) < 2e-8
 
 
+def test_reference_check_symmetric_pair_of_c_mat_neq_tens(test_grid_run):
+    """tests/test_mat_els.f90:297-306 prints c_mat_neq_tens for the configuration pair (n_b, n_b-2 | n_b, n_b-1)
+    of l = [0,0] and for the swapped pair: the two numbers agree (the two-electron operator is symmetric).  Restated
+    on the whole block: stored with full = .true. (both triangles through the same element routine,
+    hamiltonian.f90:150-205), H - H^T vanishes to rounding, and so does it for the pair the reference prints."""
+    run = test_grid_run
+    sym = run.syms[0]
+    n = sym.n_config
+    H, S, _ = O.construct_block_tensor(run.bs, run.H_vec, run.S, sym, run.p["max_k"], run.R, True)
+    Hd = sp.csr_matrix((H.data, H.indices - 1, H.index_ptr - 1), shape=(n, n))
+    D = abs(Hd - Hd.T)
+    assert D.max() <= 1e-13 * abs(Hd).max()
+    nb = run.bs.n_b
+    conf = {(int(a), int(b), int(la), int(lb)): q for q, ((a, b), (la, lb)) in enumerate(zip(sym.conf_n, sym.conf_l))}
+    lo = min(int(v) for v in np.asarray(sym.conf_n)[:, 0])
+    pick = [(a, b) for (a, b, la, lb) in conf if (la, lb) == (0, 0)]
+    # the reference's pair uses the two largest radial indices of the (0,0) group; take the same kind of pair
+    a = max(p[0] for p in pick)
+    bs_ = sorted({p[1] for p in pick if p[0] == a})
+    i, j = conf[(a, bs_[-1], 0, 0)], conf[(a, bs_[-2], 0, 0)]
+    assert Hd[i, j] != 0 and abs(Hd[i, j] - Hd[j, i]) <= 1e-13 * abs(Hd[i, j])
+
+
 def test_diag_tabulation_is_bit_identical():
     run = O.OracleRun(k=4, m=2, Z=1, h_max=1.0, r_max=5.0, k_GL=7, max_k=2)
     a = O.setup_Slater_diag(run.bs, 2, 7, tabulate=0, par_mode=0)

@@ -122,6 +122,20 @@ def test_measured_rebalancing_converges_and_keeps_the_tiling():
             assert n1[lo - 1] >= a and n1[hi - 1] <= b
 
 
+def test_rk_rows_needed_covers_direct_and_exchange_rows():
+    """rk_rows_needed: the R^k rows (first spline index) a share reads = its n1 interval, widened by the n2 values
+    of its radial sites that have exchange windows (site_core.h: site_own_cand reads rows (n2, .) there)"""
+    from bs2e.sharding import rk_rows_needed
+    k = 6                                           # w = 5
+    conf_n = np.array([(a, b) for a in range(1, 41) for b in range(1, 13)])   # n2 <= 12
+    # a share far from the exchange region: n1 - w > max n2 for all of its rows
+    assert rk_rows_needed(conf_n, (25, 32), k) == (25, 32)
+    # a share that touches it (n1 - 5 <= 12 for n1 <= 17): rows (n2, .) with n2 = 1..12 are read as well
+    assert rk_rows_needed(conf_n, (15, 20), k) == (1, 20)
+    assert rk_rows_needed(conf_n, (1, 8), k) == (1, 12)
+    assert rk_rows_needed(conf_n, (41, 50), k) is None
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
