@@ -56,7 +56,9 @@ dip_fill_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan plC
         const Union2 win = nc_windows(g, plC, r, bj);
         const int n0 = win.n > 0 ? win.hi[0] - win.lo[0] + 1 : 0;
         const int nslots = n0 + (win.n > 1 ? win.hi[1] - win.lo[1] + 1 : 0);
-        const double* cf = dt.coef + ((size_t)bi * dt.nblkC + bj) * 8;
+        double cf[8];   // the pair's folded coefficients, in registers for all of its entries
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cf[t] = dt.coef[((size_t)bi * dt.nblkC + bj) * 8 + t];
         for (int s0 = 0; s0 < nslots; s0 += 32) {
             // lane = n_c slot
             const int sl = s0 + lane;

@@ -101,8 +101,12 @@ BS2E_HD Cplx dip_value_cf(const Geom& g, const double* cf, const DipBand& bd, co
     for (int t = 0; t < 4; ++t) {
         const double al = cf[2 * t], be = cf[2 * t + 1];
         if (al == 0.0 && be == 0.0) continue;
-        const Cplx a = band_at(g, bd.A, n_[t], np_[t]), b = band_at(g, bd.B, n_[t], np_[t]);
-        const Cplx d = Cplx{al * a.re + be * b.re, al * a.im + be * b.im};
+        const Cplx a = band_at(g, bd.A, n_[t], np_[t]);
+        Cplx d = Cplx{al * a.re, al * a.im};
+        if (be != 0.0) {   // (length gauge: no second matrix; the products with beta = 0 are skipped, their value is +0)
+            const Cplx b = band_at(g, bd.B, n_[t], np_[t]);
+            d = Cplx{al * a.re + be * b.re, al * a.im + be * b.im};
+        }
         acc = cadd(acc, cmul(d, band_at(g, bd.S, m_[t], mp_[t])));
     }
     return acc;
