@@ -350,7 +350,9 @@ def run_ours(args):
     fill_kernel = ("site_mma_kernel" if (fill_mode == "mma" or (fill_mode is None and K1 > 7)) else
                    "block_fill_kernel" if fill_mode == "row" else "site_fill_kernel")
     roofline = {"kernel": fill_kernel, "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(args.workload),
+                "unit": "GB/s", "frac": achieved / peak,
+                # ncu DRAM bytes per launch of the whole blocks (captured on one GPU); a share's launches at N>1 were not captured
+                "traffic": ncu_traffic_per_launch(args.workload) if world == 1 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_fill_ms,
                 "timed": "CUDA events around the fill of every block inside the timed steps (a launch = the two "
