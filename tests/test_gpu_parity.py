@@ -445,18 +445,21 @@ def test_driver_writes_result_files_streamed_and_whole(tmp_path):
 
 
 def test_small_factor_chunks_are_bit_identical(case, monkeypatch):
-    """large bases stage the packed angular factors of a site in several chunks (double-buffered
-    bulk copies); forcing tiny chunks on the small cases must give the same bits as one chunk"""
+    """large bases stage the packed angular factors of a site in several chunks (double-buffered bulk copies);
+    forcing tiny chunks on the small cases must give the same bits as one chunk, in both site kernels"""
     run, ctx = case
     syms = [s for s in run.syms if s.n_config > 0]
-    ref = []
-    for s in syms:
-        b = ctx.block_plan(s, False); b.assemble(); ref.append(b.download()); b.free()
-    monkeypatch.setenv("BS2E_SITE_CHUNK_KB", "1")
-    for s, (H0, S0) in zip(syms, ref):
-        b = ctx.block_plan(s, False); b.assemble(); H, S = b.download(); b.free()
-        assert np.array_equal(H.indices, H0.indices) and np.array_equal(H.data, H0.data)
-        assert np.array_equal(S.indices, S0.indices) and np.array_equal(S.data, S0.data)
+    for fill in ("fma", "mma"):
+        monkeypatch.setenv("BS2E_FILL", fill)
+        monkeypatch.delenv("BS2E_SITE_CHUNK_KB", raising=False)
+        ref = []
+        for s in syms:
+            b = ctx.block_plan(s, False); b.assemble(); ref.append(b.download()); b.free()
+        monkeypatch.setenv("BS2E_SITE_CHUNK_KB", "1")
+        for s, (H0, S0) in zip(syms, ref):
+            b = ctx.block_plan(s, False); b.assemble(); H, S = b.download(); b.free()
+            assert np.array_equal(H.indices, H0.indices) and np.array_equal(H.data, H0.data), fill
+            assert np.array_equal(S.indices, S0.indices) and np.array_equal(S.data, S0.data), fill
 
 
 # ---------------------------------------------------------------------------
