@@ -20,6 +20,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -1088,6 +1089,8 @@ void* out_take(bs2e_ctx* c, size_t bytes, cudaStream_t st, size_t* cap)
     }
     void* p = nullptr;
     const size_t want = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    if (getenv("BS2E_TRACE")) fprintf(stderr, "[bs2e] out_take: no cached array for %.2f GB (cache holds %zu arrays, %.1f GB)\n",
+                                      1e-9 * (double)bytes, c->out_free.size(), 1e-9 * (double)c->out_cached);
     if (cudaMallocAsync(&p, want, st) != cudaSuccess) {   // out of memory with arrays parked in the cache: drop them
         cudaGetLastError();
         out_release_all(c);
@@ -1104,7 +1107,9 @@ void out_give(bs2e_ctx* c, void* p, size_t cap, cudaStream_t st)
     if (c->out_cap == 0) {
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
-        c->out_cap = (size_t)(0.45 * (double)tot);
+        double frac = 0.45;
+        if (const char* e = getenv("BS2E_OUT_CACHE_FRAC")) frac = std::min(0.9, std::max(0.0, atof(e)));   // A/B measurements
+        c->out_cap = (size_t)(frac * (double)tot);
     }
     bs2e_ctx::OutBuf b{p, cap, nullptr};
     if (cap > c->out_cap || cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) {
