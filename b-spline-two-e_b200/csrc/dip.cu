@@ -38,11 +38,12 @@ struct DipArena {   // device arrays of one call, released on every exit path
 // the n_c slots one after the other with one lane per n_d: 15 of 32 lanes at best and the whole interval
 // arithmetic repeated by every lane for every slot -- 42 warp instructions per stored entry, 0.08 of the HBM
 // rate, profiles/r01t_*).
-__global__ void __launch_bounds__(kDipWarps * 32)
+__global__ void __launch_bounds__(kDipWarps * 32, 4)
 dip_fill_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan plC, const __grid_constant__ DipTables dt,
                 const __grid_constant__ DipBand bd, const long long* __restrict__ ptr, long long* __restrict__ idx,
                 double2* __restrict__ dat)
 {
+    extern __shared__ double2 dtab[];   // per warp: the band rows n_a and n_b of A, B, S ([6][2w+2], last slot = 0)
     const long long wrow = (long long)blockIdx.x * kDipWarps + (threadIdx.x >> 5);
     if (wrow >= dt.nrows) return;
     const int lane = threadIdx.x & 31;
@@ -51,6 +52,48 @@ dip_fill_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan plC
     const int bi = r.bi;
     r.bi = -1;   // never the "own" group of the column list: no triangle cut (dip_for_each_chunk)
     long long pos = ptr[wrow] - 1;
+    // Every band-matrix value an entry of this row needs has n_a or n_b as its first index (dip_value_cf: A(n_a,.),
+    // A(n_b,.), S(n_a,.), S(n_b,.), the same for B): the six band rows are copied to shared memory once per row,
+    // and the twelve look-ups per entry become shared-memory reads (slot 2w+1 holds the zero outside the band).
+    const int W = g.w, W2 = 2 * W + 2;
+    double2* tb = dtab + (size_t)(threadIdx.x >> 5) * 6 * W2;
+    for (int i = lane; i < 6 * W2; i += 32) {
+        const int which = i / W2, d = i - which * W2;
+        const int n = which < 3 ? r.na : r.nb;
+        const double* M = (which % 3 == 0) ? bd.A : ((which % 3 == 1) ? bd.B : bd.S);
+        double2 v = make_double2(0.0, 0.0);
+        if (d <= 2 * W) {
+            const double* q = M + ((size_t)n * (2 * W + 1) + d) * 2;
+            v = make_double2(q[0], q[1]);
+        }
+        tb[i] = v;
+    }
+    __syncwarp();
+    auto look = [&](int which, int n, int np) {
+        const int d = np - n + W;
+        const double2 v = tb[which * W2 + ((unsigned)d <= (unsigned)(2 * W) ? d : 2 * W + 1)];
+        return Cplx{v.x, v.y};
+    };
+    // the statements of dip_value_cf with the look-ups above
+    auto value = [&](const double* cf, int nc, int nd) {
+        Cplx acc = Cplx{0.0, 0.0};
+        const int sel[4] = {0, 1, 0, 1};                       // first index of the dipole factor: n_a / n_b
+        const int n_[4] = {r.na, r.nb, r.na, r.nb}, np_[4] = {nc, nd, nd, nc};
+        const int m_[4] = {r.nb, r.na, r.nb, r.na}, mp_[4] = {nd, nc, nc, nd};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const double al = cf[2 * t], be = cf[2 * t + 1];
+            if (al == 0.0 && be == 0.0) continue;
+            const Cplx a = look(3 * sel[t], n_[t], np_[t]);
+            Cplx d = Cplx{al * a.re, al * a.im};
+            if (be != 0.0) {
+                const Cplx b = look(3 * sel[t] + 1, n_[t], np_[t]);
+                d = Cplx{al * a.re + be * b.re, al * a.im + be * b.im};
+            }
+            acc = cadd(acc, cmul(d, look(3 * (1 - sel[t]) + 2, m_[t], mp_[t])));
+        }
+        return acc;
+    };
     for (int bj = 0; bj < plC.nblk; ++bj) {
         if (!dt.flag[(size_t)bi * dt.nblkC + bj]) continue;
         const Union2 win = nc_windows(g, plC, r, bj);
@@ -97,9 +140,7 @@ dip_fill_kernel(const __grid_constant__ Geom g, const __grid_constant__ Plan plC
                 if (p < total) {
                     const int off = p - s_ex;
                     const int nd = off < s_c0 ? s_lo0 + off : s_lo1 + (off - s_c0);
-                    RowInfo rv = r;
-                    rv.bi = bi;
-                    const Cplx v = dip_value_cf(g, cf, bd, rv, s_nc, nd);
+                    const Cplx v = value(cf, s_nc, nd);
                     __stcs(idx + pos + p, (long long)s_jb + nd);
                     __stcs(dat + pos + p, make_double2(v.re, v.im));
                 }
@@ -158,7 +199,8 @@ long long dip_block_run(bs2e_ctx* c, int q, const int64_t* sym1, long long n1, c
     double* d_dat = dev_alloc_async<double>(2 * (size_t)nnz, st);
     try {
         const DipBand bd{c->d_dipA, c->d_dipB ? c->d_dipB : c->d_dipA, c->d_Sb};
-        dip_fill_kernel<<<(unsigned)((nrows + kDipWarps - 1) / kDipWarps), kDipWarps * 32, 0, st>>>(
+        const size_t tab_bytes = sizeof(double2) * kDipWarps * 6 * (2 * (size_t)c->hg.w + 2);
+        dip_fill_kernel<<<(unsigned)((nrows + kDipWarps - 1) / kDipWarps), kDipWarps * 32, tab_bytes, st>>>(
             c->dg, plC, dt, bd, d_ptr, d_idx, reinterpret_cast<double2*>(d_dat));
         BS2E_LAUNCHED();
         BS2E_CUDA(cudaMemcpyAsync(index_ptr, d_ptr, sizeof(long long) * (nrows + 1), cudaMemcpyDeviceToHost, st));
